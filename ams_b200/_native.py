@@ -1,0 +1,109 @@
+"""ctypes binding of libams_b200.so (the C ABI declared in include/ams_b200.h).
+
+There is NO fallback: if the shared library is missing, was not built for this machine, or no sm_100a
+device is present, importing/creating fails loudly.  Nothing here touches the CPU oracle.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libams_b200.so')
+
+AMS_MAX_CLASSES = 32
+BN_MOVING, BN_BATCH = 0, 1
+FRAMES_U8, FRAMES_F32 = 0, 1
+
+
+class AmsConfig(C.Structure):
+    _fields_ = [('num_classes', C.c_int), ('graph_variant', C.c_int), ('height', C.c_int), ('width', C.c_int),
+                ('device', C.c_int), ('class_count', C.c_int), ('class_indices', C.c_int * AMS_MAX_CLASSES),
+                ('label_depth', C.c_int), ('queue_capacity', C.c_int)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+_SIGNATURES = {
+    'ams_last_error': (C.c_char_p, []),
+    'ams_abi_version': (_i, []),
+    'ams_create': (_vp, [C.POINTER(AmsConfig)]),
+    'ams_destroy': (None, [_vp]),
+    'ams_set_stream': (_i, [_vp, _vp]),
+    'ams_synchronize': (_i, [_vp]),
+    'ams_num_tensors': (_i, [_vp]),
+    'ams_tensor_info': (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll)]),
+    'ams_set_tensor': (_i, [_vp, C.c_char_p, _vp, _ll]),
+    'ams_get_tensor': (_i, [_vp, C.c_char_p, _vp, _ll]),
+    'ams_trainable_count': (_ll, [_vp]),
+    'ams_get_trainable': (_i, [_vp, _vp]),
+    'ams_set_trainable': (_i, [_vp, _vp]),
+    'ams_reset_optimizer': (_i, [_vp]),
+    'ams_enqueue': (_i, [_vp, _vp, _i, _vp, _i]),
+    'ams_queue_size': (_i, [_vp]),
+    'ams_infer': (_i, [_vp, _i, _vp]),
+    'ams_infer_metric': (_i, [_vp, _i, _vp, _vp, C.POINTER(_f)]),
+    'ams_confmat_labels': (_i, [_vp, _vp, _vp, _ll, _vp]),
+    'ams_train_step': (_i, [_vp, _f, _i, C.POINTER(_f)]),
+    'ams_set_mask': (_i, [_vp, _vp]),
+    'ams_get_mask': (_i, [_vp, _vp]),
+    'ams_snapshot_before': (_i, [_vp]),
+    'ams_select_topk': (_i, [_vp, _d, C.POINTER(_ll), C.POINTER(_f)]),
+    'ams_pack_delta': (_i, [_vp, _vp, _ll, C.POINTER(_ll)]),
+    'ams_train_forward_backward': (_i, [_vp, C.POINTER(_ll), C.POINTER(_d)]),
+    'ams_gradient_arena': (_vp, [_vp, C.POINTER(_ll)]),
+    'ams_apply_optimizer': (_i, [_vp, _f, _i, _f]),
+    'ams_get_logits': (_i, [_vp, _vp, _ll]),
+    'ams_get_gradients': (_i, [_vp, _vp]),
+    'ams_num_layers': (_i, [_vp]),
+    'ams_layer_info': (_i, [_vp, _i, C.c_char_p, _i] + [C.POINTER(_i)] * 6 + [C.POINTER(_f)] * 2 + [C.POINTER(_i)]),
+    'ams_get_activation': (_i, [_vp, _i, _i, _vp, _ll]),
+    'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
+    'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
+    'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    'ams_op_depthwise_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'ams_op_stem': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    'ams_op_stem_bwd': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'ams_op_bn_train': (_i, [_vp, _ll, _i, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    'ams_op_bn_backward': (_i, [_vp, _vp, _ll, _i, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp]),
+    'ams_op_head_infer': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, C.POINTER(_d), C.POINTER(_ll), _vp]),
+    'ams_op_head_backward': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp, C.POINTER(_f), _vp]),
+    'ams_op_select': (_i, [_vp, _vp, _ll, _d, _vp, C.POINTER(_ll), C.POINTER(_f), _vp]),
+    'ams_op_adam': (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _vp]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/ams_b200.h declares (used by the no-GPU ABI test)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load libams_b200.so once; raise if it is not there (no CPU path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError('%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                              '(nvcc, sm_100a). ams_b200 has no CPU fallback.' % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)        # AttributeError if the ABI and the header disagree
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().ams_last_error().decode('utf-8', 'replace')
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = last_error()
+        if msg.startswith('KeyError'):
+            raise KeyError(msg[len('KeyError: '):])
+        raise NativeError('%s failed: %s' % (what or 'libams_b200 call', msg))

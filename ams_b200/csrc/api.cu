@@ -1,0 +1,695 @@
+// extern "C" surface of libams_b200 (see include/ams_b200.h for the reference call site each entry replaces).
+#include <cmath>
+#include <cstring>
+
+#include "net.cuh"
+
+namespace ams {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace ams
+
+using namespace ams;
+
+namespace {
+
+int fill_head_geom(const ams_config& c, int h, int w, HeadGeom* g) {
+    AMS_REQUIRE(c.class_count > 0 && c.class_count <= 21, "class_count must be in [1,21]");
+    g->N = 0; g->h = h; g->w = w; g->ldl = 32; g->H = c.height; g->W = c.width; g->class_count = c.class_count;
+    g->normalize = 1;
+    for (int i = 0; i < kMaxClasses; ++i) g->cls_idx[i] = 0;
+    for (int i = 0; i < 256; ++i) g->label_lut[i] = -1;
+    const int depth = c.label_depth > 0 ? c.label_depth : 19;
+    for (int j = 0; j < c.class_count; ++j) {
+        const int ch = c.class_indices[j];
+        AMS_REQUIRE(ch >= 0 && ch < c.num_classes, "class index outside the logits");
+        AMS_REQUIRE(j == 0 || ch > c.class_indices[j - 1], "class_indices must be ascending");
+        g->cls_idx[j] = ch;
+        if (ch < depth) g->label_lut[ch] = j;      // one_hot(labels, depth) -> gather(class_indices)
+    }
+    return 0;
+}
+
+int find_var(Net* net, const char* name) {
+    auto it = net->var_index.find(name);
+    return it == net->var_index.end() ? -1 : it->second;
+}
+
+int ensure_slot(QueueSlot& q, size_t fbytes, size_t lbytes) {
+    if (q.frames_cap < fbytes) {
+        if (q.frames) cudaFree(q.frames);
+        AMS_CUDA_CHECK(cudaMalloc(&q.frames, fbytes));
+        q.frames_cap = fbytes;
+    }
+    if (q.labels_cap < lbytes) {
+        if (q.labels) cudaFree(q.labels);
+        AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&q.labels), lbytes));
+        q.labels_cap = lbytes;
+    }
+    return 0;
+}
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+extern "C" {
+
+const char* ams_last_error(void) { return g_last_error.c_str(); }
+int ams_abi_version(void) { return 1; }
+
+ams_net* ams_create(const ams_config* cfg) {
+    if (!cfg) { set_last_error("null config"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_last_error("libams_b200 needs a CUDA device (sm_100a); there is no CPU fallback");
+        return nullptr;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_last_error("bad device ordinal"); return nullptr; }
+    if (cfg->height <= 0 || cfg->width <= 0) { set_last_error("bad frame size"); return nullptr; }
+    Net* net = new Net();
+    net->cfg = *cfg;
+    auto fail = [&](const char* what) -> ams_net* {
+        if (g_last_error.empty()) set_last_error(what);
+        delete net;
+        return nullptr;
+    };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return fail("cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail("cudaGetDeviceProperties failed");
+    if (prop.major != 10) {
+        set_last_error(std::string("libams_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor));
+        delete net;
+        return nullptr;
+    }
+    net->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&net->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    net->stream = net->own_stream;
+    if (net_build_topology(net)) return fail("topology");
+    const LayerDef& lg = net->layers.back();
+    if (fill_head_geom(net->cfg, lg.out_h, lg.out_w, &net->head)) return fail("head");
+    const size_t nt = static_cast<size_t>(net->n_train);
+    bool ok = true;
+    auto A = [&](auto** p, size_t count) {
+        void* q = nullptr;
+        if (ok && cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(**p)) != cudaSuccess) ok = false;
+        *p = static_cast<std::remove_reference_t<decltype(*p)>>(q);
+        if (ok) cudaMemset(q, 0, std::max<size_t>(count, 1) * sizeof(**p));
+    };
+    A(&net->params, nt); A(&net->grads, nt); A(&net->adam_m, nt); A(&net->adam_v, nt); A(&net->before, nt);
+    A(&net->delta_scratch, nt); A(&net->mask, nt);
+    A(&net->moving, static_cast<size_t>(net->n_moving));
+    A(&net->bnpool, static_cast<size_t>(net->n_bnpool));
+    A(&net->wpool, static_cast<size_t>(net->n_bf16));
+    A(&net->select_sc, 1); A(&net->head_st, 1);
+    if (!ok) return fail("device allocation failed");
+    cudaMemset(net->mask, 1, nt);
+    // weight-cast table and per-variable bit segments
+    std::vector<WeightCast> table;
+    for (const LayerDef& d : net->layers) {
+        if (d.kind != kConv1x1 && d.kind != kLogits) continue;
+        WeightCast t;
+        t.w = net->params + d.w_off; t.w_fwd = net->wpool + d.wfwd_off; t.w_bwd = net->wpool + d.wbwd_off;
+        t.Cin = d.cin; t.Cout = d.cout; t.ld_fwd = d.ld_fwd; t.ld_bwd = d.ld_bwd; t.row0 = d.k_rows0; t.rows = d.k_rows;
+        table.push_back(t);
+        net->cast_max = std::max(net->cast_max, d.k_rows * d.cout);
+    }
+    net->cast_layers = static_cast<int>(table.size());
+    A(&net->cast_table, table.size());
+    std::vector<VarSeg> segs;
+    long long boff = 0;
+    for (int vi : net->trainable_order) {
+        const VarInfo& v = net->vars[vi];
+        segs.push_back(VarSeg{v.offset, v.count, boff});
+        boff += (v.count + 7) / 8;
+    }
+    net->mask_bytes = boff;
+    A(&net->segs_dev, segs.size());
+    A(&net->pack_bits, static_cast<size_t>(boff));
+    A(&net->pack_vals, nt);
+    A(&net->pack_counts, static_cast<size_t>(pack_delta_blocks(net->n_train)));
+    A(&net->pack_kept, 1);
+    if (!ok) return fail("device allocation failed");
+    cudaMemcpy(net->cast_table, table.data(), table.size() * sizeof(WeightCast), cudaMemcpyHostToDevice);
+    cudaMemcpy(net->segs_dev, segs.data(), segs.size() * sizeof(VarSeg), cudaMemcpyHostToDevice);
+    const int cap = cfg->queue_capacity > 0 ? cfg->queue_capacity : 4;
+    net->slots.resize(cap);
+    for (int i = 0; i < cap; ++i) {
+        if (cudaEventCreateWithFlags(&net->slots[i].consumed, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+        net->free_slots.push_back(i);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail("device sync failed");
+    return reinterpret_cast<ams_net*>(net);
+}
+
+void ams_destroy(ams_net* h) {
+    if (!h) return;
+    Net* net = reinterpret_cast<Net*>(h);
+    cudaSetDevice(net->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : net->plans) for (void* p : kv.second->allocations) cudaFree(p);
+    for (auto& q : net->slots) { if (q.frames) cudaFree(q.frames); if (q.labels) cudaFree(q.labels); if (q.consumed) cudaEventDestroy(q.consumed); }
+    void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->before, net->delta_scratch, net->mask, net->moving,
+                    net->bnpool, net->wpool, net->select_sc, net->head_st, net->cast_table, net->segs_dev, net->pack_bits,
+                    net->pack_vals, net->pack_counts, net->pack_kept};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (net->own_stream) cudaStreamDestroy(net->own_stream);
+    if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
+    delete net;
+}
+
+#define NET(h) Net* net = reinterpret_cast<Net*>(h); if (!net) { set_last_error("null handle"); return -1; } cudaSetDevice(net->cfg.device)
+
+int ams_set_stream(ams_net* h, void* stream) {
+    NET(h);
+    net->stream = stream ? as_stream(stream) : net->own_stream;
+    return 0;
+}
+int ams_synchronize(ams_net* h) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+int ams_num_tensors(const ams_net* h) { return h ? static_cast<int>(reinterpret_cast<const Net*>(h)->vars.size()) : -1; }
+
+int ams_tensor_info(const ams_net* h, int index, char* name, int cap, int shape4[4], int* ndim, int* trainable, long long* off) {
+    const Net* net = reinterpret_cast<const Net*>(h);
+    if (!net || index < 0 || index >= static_cast<int>(net->vars.size())) { set_last_error("bad tensor index"); return -1; }
+    const VarInfo& v = net->vars[index];
+    if (name && cap > 0) { std::strncpy(name, v.name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (shape4) for (int i = 0; i < 4; ++i) shape4[i] = v.shape[i];
+    if (ndim) *ndim = v.ndim;
+    if (trainable) *trainable = v.trainable ? 1 : 0;
+    if (off) *off = v.offset;
+    return 0;
+}
+
+static int resolve(Net* net, const char* name, float** dev, long long* count, bool* is_param) {
+    std::string s(name ? name : "");
+    *is_param = false;
+    if (s == "beta1_power:0" || s == "beta2_power:0") { *dev = nullptr; *count = 1; return 0; }
+    float* base_t = net->params; float* base_m = net->moving;
+    std::string var = s;
+    auto ends_with = [&](const std::string& suf) { return s.size() > suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0; };
+    bool slot = false;
+    if (ends_with("/Adam_1:0")) { var = s.substr(0, s.size() - 9) + ":0"; base_t = net->adam_v; slot = true; }
+    else if (ends_with("/Adam:0")) { var = s.substr(0, s.size() - 7) + ":0"; base_t = net->adam_m; slot = true; }
+    const int vi = find_var(net, var.c_str());
+    AMS_REQUIRE(vi >= 0, std::string("KeyError: no variable named '") + s + "'");
+    const VarInfo& v = net->vars[vi];
+    AMS_REQUIRE(!slot || v.trainable, "optimizer slots exist for trainable variables only");
+    *dev = (v.trainable ? base_t : base_m) + v.offset;
+    *count = v.count;
+    *is_param = !slot;
+    return 0;
+}
+
+int ams_set_tensor(ams_net* h, const char* name, const float* host, long long count) {
+    NET(h);
+    std::string s(name ? name : "");
+    if (s == "beta1_power:0") { net->beta1_power = host[0]; return 0; }
+    if (s == "beta2_power:0") { net->beta2_power = host[0]; return 0; }
+    float* dev; long long n; bool is_param;
+    if (resolve(net, name, &dev, &n, &is_param)) return -1;
+    AMS_REQUIRE(n == count, "element count does not match the variable's shape");
+    AMS_CUDA_CHECK(cudaMemcpyAsync(dev, host, n * sizeof(float), cudaMemcpyHostToDevice, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    if (is_param) { net->weights_dirty = true; net->fold_dirty = true; }
+    return 0;
+}
+
+int ams_get_tensor(ams_net* h, const char* name, float* host, long long count) {
+    NET(h);
+    std::string s(name ? name : "");
+    if (s == "beta1_power:0") { host[0] = net->beta1_power; return 0; }
+    if (s == "beta2_power:0") { host[0] = net->beta2_power; return 0; }
+    float* dev; long long n; bool is_param;
+    if (resolve(net, name, &dev, &n, &is_param)) return -1;
+    AMS_REQUIRE(n == count, "element count does not match the variable's shape");
+    AMS_CUDA_CHECK(cudaMemcpyAsync(host, dev, n * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+long long ams_trainable_count(const ams_net* h) { return h ? reinterpret_cast<const Net*>(h)->n_train : -1; }
+int ams_get_trainable(ams_net* h, float* host) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(host, net->params, net->n_train * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+int ams_set_trainable(ams_net* h, const float* host) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(net->params, host, net->n_train * sizeof(float), cudaMemcpyHostToDevice, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->weights_dirty = true; net->fold_dirty = true;
+    return 0;
+}
+int ams_reset_optimizer(ams_net* h) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaMemsetAsync(net->adam_m, 0, net->n_train * sizeof(float), net->stream));
+    AMS_CUDA_CHECK(cudaMemsetAsync(net->adam_v, 0, net->n_train * sizeof(float), net->stream));
+    net->beta1_power = 0.9f; net->beta2_power = 0.999f;
+    return 0;
+}
+
+int ams_enqueue(ams_net* h, const void* frames, int dtype, const uint8_t* labels, int n) {
+    NET(h);
+    AMS_REQUIRE(frames && n > 0, "frames must be non-empty");
+    AMS_REQUIRE(dtype == AMS_FRAMES_U8 || dtype == AMS_FRAMES_F32, "frames_dtype must be u8 or f32");
+    int slot = -1;
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        net->qcv.wait(lk, [&] { return !net->free_slots.empty(); });
+        slot = net->free_slots.front();
+        net->free_slots.pop_front();
+    }
+    QueueSlot& q = net->slots[slot];
+    if (q.consumed_pending) { AMS_CUDA_CHECK(cudaEventSynchronize(q.consumed)); q.consumed_pending = false; }
+    const size_t px = static_cast<size_t>(n) * net->cfg.height * net->cfg.width;
+    const size_t fbytes = px * 3 * (dtype == AMS_FRAMES_U8 ? 1 : 4);
+    if (ensure_slot(q, fbytes, px)) return -1;
+    AMS_CUDA_CHECK(cudaMemcpyAsync(q.frames, frames, fbytes, cudaMemcpyHostToDevice, net->copy_stream));
+    if (labels) AMS_CUDA_CHECK(cudaMemcpyAsync(q.labels, labels, px, cudaMemcpyHostToDevice, net->copy_stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->copy_stream));
+    q.n = n; q.dtype = dtype; q.has_labels = labels != nullptr;
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        net->filled.push_back(slot);
+    }
+    return 0;
+}
+int ams_queue_size(ams_net* h) {
+    NET(h);
+    std::unique_lock<std::mutex> lk(net->qmu);
+    return static_cast<int>(net->filled.size());
+}
+
+static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels, int64_t* out_cm, float* out_loss) {
+    Plan* p = nullptr;
+    if (net_dequeue(net, &p, false)) return -1;
+    if (net_forward(net, p, bn_mode, false)) return -1;
+    HeadGeom hg = net->head; hg.N = p->N;
+    HeadStats hs;
+    if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
+    if (head_infer(p->logits, hg, metric ? p->in_labels : nullptr, p->pred, net->head_st, net->stream)) return -1;
+    const size_t px = static_cast<size_t>(p->N) * net->cfg.height * net->cfg.width;
+    if (out_labels) AMS_CUDA_CHECK(cudaMemcpyAsync(out_labels, p->pred, px * sizeof(int32_t), cudaMemcpyDeviceToHost, net->stream));
+    if (metric) AMS_CUDA_CHECK(cudaMemcpyAsync(&hs, net->head_st, sizeof(HeadStats), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    if (metric) {
+        const int cc = net->cfg.class_count;
+        if (out_cm) for (int i = 0; i < cc; ++i) for (int j = 0; j < cc; ++j) out_cm[i * cc + j] = hs.confmat[i * kMaxClasses + j];
+        if (out_loss) *out_loss = hs.n_valid > 0 ? static_cast<float>(hs.loss_sum / static_cast<double>(hs.n_valid)) : NAN;
+    }
+    return 0;
+}
+
+int ams_infer(ams_net* h, int bn_mode, int32_t* out_labels) {
+    NET(h);
+    return infer_common(net, bn_mode, false, out_labels, nullptr, nullptr);
+}
+int ams_infer_metric(ams_net* h, int bn_mode, int32_t* out_labels, int64_t* out_cm, float* out_loss) {
+    NET(h);
+    return infer_common(net, bn_mode, true, out_labels, out_cm, out_loss);
+}
+
+int ams_confmat_labels(ams_net* h, const uint8_t* before, const uint8_t* after, long long n, int64_t* out_cm) {
+    NET(h);
+    AMS_REQUIRE(n > 0, "empty label maps");
+    uint8_t* dev = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev), 2 * n));
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(dev, before, n, cudaMemcpyHostToDevice, net->stream) != cudaSuccess ||
+            cudaMemcpyAsync(dev + n, after, n, cudaMemcpyHostToDevice, net->stream) != cudaSuccess) { set_last_error("H2D failed"); rc = -1; break; }
+        if (head_reset(net->head_st, net->stream) || head_label_confmat(dev, dev + n, n, net->head, net->head_st, net->stream)) { rc = -1; break; }
+        HeadStats hs;
+        if (cudaMemcpyAsync(&hs, net->head_st, sizeof(HeadStats), cudaMemcpyDeviceToHost, net->stream) != cudaSuccess ||
+            cudaStreamSynchronize(net->stream) != cudaSuccess) { set_last_error("D2H failed"); rc = -1; break; }
+        const int cc = net->cfg.class_count;
+        for (int i = 0; i < cc; ++i) for (int j = 0; j < cc; ++j) out_cm[i * cc + j] = hs.confmat[i * kMaxClasses + j];
+    } while (0);
+    cudaFree(dev);
+    return rc;
+}
+
+static int apply_optimizer(Net* net, float lr, int masked, float grad_scale) {
+    // TF1 Adam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), all in fp32
+    const float alpha = lr * std::sqrt(1.0f - net->beta2_power) / (1.0f - net->beta1_power);
+    const uint8_t* mask = (masked && !net->mask_all_ones) ? net->mask : nullptr;
+    if (adam_masked(net->params, net->grads, grad_scale, net->adam_m, net->adam_v, mask, net->n_train, alpha,
+                    1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, net->stream)) return -1;
+    net->beta1_power *= 0.9f;
+    net->beta2_power *= 0.999f;
+    net->weights_dirty = true; net->fold_dirty = true;
+    return 0;
+}
+
+int ams_train_forward_backward(ams_net* h, long long* out_n_valid, double* out_loss_sum) {
+    NET(h);
+    Plan* p = nullptr;
+    if (net_dequeue(net, &p, true)) return -1;
+    if (net_forward(net, p, AMS_BN_BATCH, true)) return -1;
+    if (net_backward(net, p, false)) return -1;
+    HeadStats hs;
+    AMS_CUDA_CHECK(cudaMemcpyAsync(&hs, net->head_st, sizeof(HeadStats), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    if (out_n_valid) *out_n_valid = hs.n_valid;
+    if (out_loss_sum) *out_loss_sum = hs.loss_sum;
+    return 0;
+}
+void* ams_gradient_arena(ams_net* h, long long* count) {
+    Net* net = reinterpret_cast<Net*>(h);
+    if (!net) return nullptr;
+    if (count) *count = net->n_train;
+    return net->grads;
+}
+int ams_apply_optimizer(ams_net* h, float lr, int masked, float grad_scale) {
+    NET(h);
+    return apply_optimizer(net, lr, masked, grad_scale);
+}
+
+int ams_train_step(ams_net* h, float lr, int masked, float* out_loss) {
+    NET(h);
+    Plan* p = nullptr;
+    if (net_dequeue(net, &p, true)) return -1;
+    if (net_forward(net, p, AMS_BN_BATCH, true)) return -1;
+    if (net_backward(net, p, true)) return -1;
+    if (apply_optimizer(net, lr, masked, 1.0f)) return -1;
+    if (out_loss) {
+        AMS_CUDA_CHECK(cudaMemcpyAsync(out_loss, p->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+        AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    }
+    return 0;
+}
+
+int ams_set_mask(ams_net* h, const uint8_t* host_mask) {
+    NET(h);
+    if (!host_mask) {
+        AMS_CUDA_CHECK(cudaMemsetAsync(net->mask, 1, net->n_train, net->stream));
+        net->mask_all_ones = true;
+    } else {
+        AMS_CUDA_CHECK(cudaMemcpyAsync(net->mask, host_mask, net->n_train, cudaMemcpyHostToDevice, net->stream));
+        AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+        net->mask_all_ones = false;
+    }
+    return 0;
+}
+int ams_get_mask(ams_net* h, uint8_t* host_mask) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(host_mask, net->mask, net->n_train, cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+int ams_snapshot_before(ams_net* h) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(net->before, net->params, net->n_train * sizeof(float), cudaMemcpyDeviceToDevice, net->stream));
+    return 0;
+}
+
+static void percentile_rank(double coord_frac, long long n, long long* lo, double* w_hi) {
+    // NumPy 1.19: q = 100*(1-frac); q /= 100; idx = q*(n-1); lo = floor(idx); w_hi = idx - lo
+    const double q = 100 * (1 - coord_frac);
+    const double idx = (q / 100.0) * static_cast<double>(n - 1);
+    long long l = static_cast<long long>(std::floor(idx));
+    if (l > n - 1) l = n - 1;
+    if (l < 0) l = 0;
+    *lo = l;
+    *w_hi = idx - static_cast<double>(l);
+}
+
+int ams_select_topk(ams_net* h, double coord_frac, long long* out_kept, float* out_thr) {
+    NET(h);
+    long long lo; double w_hi;
+    percentile_rank(coord_frac, net->n_train, &lo, &w_hi);
+    if (select_coordinates(net->params, net->before, net->delta_scratch, net->mask, net->n_train, lo, w_hi, net->select_sc, net->stream)) return -1;
+    SelectScratch sc;
+    AMS_CUDA_CHECK(cudaMemcpyAsync(&sc, net->select_sc, sizeof(sc), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->mask_all_ones = false;
+    net->weights_dirty = true; net->fold_dirty = true;
+    if (out_kept) *out_kept = static_cast<long long>(sc.kept);
+    if (out_thr) *out_thr = sc.threshold;
+    return 0;
+}
+
+int ams_pack_delta(ams_net* h, uint8_t* out, long long cap, long long* out_len) {
+    NET(h);
+    if (pack_delta(net->params, net->mask, net->segs_dev, static_cast<int>(net->trainable_order.size()), net->n_train,
+                   net->mask_bytes, net->pack_bits, net->pack_vals, net->pack_counts, pack_delta_blocks(net->n_train),
+                   net->pack_kept, net->stream)) return -1;
+    unsigned long long kept = 0;
+    AMS_CUDA_CHECK(cudaMemcpyAsync(&kept, net->pack_kept, sizeof(kept), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    const long long len = net->mask_bytes + 2 * static_cast<long long>(kept);
+    if (out_len) *out_len = len;
+    if (out && cap >= len) {
+        AMS_CUDA_CHECK(cudaMemcpyAsync(out, net->pack_bits, net->mask_bytes, cudaMemcpyDeviceToHost, net->stream));
+        if (kept) AMS_CUDA_CHECK(cudaMemcpyAsync(out + net->mask_bytes, net->pack_vals, 2 * kept, cudaMemcpyDeviceToHost, net->stream));
+        AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    }
+    return 0;
+}
+
+int ams_get_logits(ams_net* h, float* host, long long count) {
+    NET(h);
+    auto it = net->plans.find(net->last_n);
+    AMS_REQUIRE(it != net->plans.end(), "no forward pass has run yet");
+    Plan* p = it->second.get();
+    const LayerDef& lg = net->layers.back();
+    const long long M = static_cast<long long>(p->N) * lg.out_h * lg.out_w;
+    AMS_REQUIRE(count == M * lg.cout, "logits element count mismatch");
+    AMS_CUDA_CHECK(cudaMemcpy2DAsync(host, lg.cout * sizeof(float), p->logits, 32 * sizeof(float), lg.cout * sizeof(float), M,
+                                     cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+int ams_get_gradients(ams_net* h, float* host) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(host, net->grads, net->n_train * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+int ams_num_layers(const ams_net* h) { return h ? static_cast<int>(reinterpret_cast<const Net*>(h)->layers.size()) : -1; }
+int ams_layer_info(const ams_net* h, int index, char* name, int cap, int* kind, int* cin, int* cout, int* stride, int* dil,
+                   int* act, float* eps, float* k, int* residual_from) {
+    const Net* net = reinterpret_cast<const Net*>(h);
+    if (!net || index < 0 || index >= static_cast<int>(net->layers.size())) { set_last_error("bad layer index"); return -1; }
+    const LayerDef& d = net->layers[index];
+    if (name && cap > 0) { std::strncpy(name, d.name.c_str(), cap - 1); name[cap - 1] = 0; }
+    if (kind) *kind = d.kind; if (cin) *cin = d.cin; if (cout) *cout = d.cout; if (stride) *stride = d.stride;
+    if (dil) *dil = d.dil; if (act) *act = d.act; if (eps) *eps = d.eps; if (k) *k = d.one_minus_decay;
+    if (residual_from) *residual_from = d.residual;
+    return 0;
+}
+int ams_get_activation(ams_net* h, int index, int which, uint16_t* host, long long count) {
+    NET(h);
+    auto it = net->plans.find(net->last_n);
+    AMS_REQUIRE(it != net->plans.end(), "no forward pass has run yet");
+    AMS_REQUIRE(index >= 0 && index < static_cast<int>(net->layers.size()), "bad layer index");
+    Plan* p = it->second.get();
+    const LayerDef& d = net->layers[index];
+    const bf16* src = which == 0 ? p->buf[index].y : (which == 1 ? p->buf[index].z : p->buf[index].g);
+    AMS_REQUIRE(src != nullptr, "layer has no such buffer");
+    const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
+    AMS_REQUIRE(count == M * d.cout, "activation element count mismatch");
+    AMS_CUDA_CHECK(cudaMemcpyAsync(host, src, count * 2, cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    return 0;
+}
+
+// =============================================================================================== op-level hooks
+int ams_op_conv1x1(const void* a, const void* w, int M, int N, int K, const float* scale, const float* shift,
+                   const float* rowbias, int rows_per_image, const void* residual, int act, void* out, int out_fp32, int ldc,
+                   void* stream) {
+    GemmDesc d;
+    d.A = static_cast<const bf16*>(a); d.lda = K; d.B = static_cast<const bf16*>(w); d.ldb = K;
+    d.M = M; d.N = N; d.K = K; d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32; d.scale = scale; d.shift = shift;
+    d.rowbias = rowbias; d.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
+    d.residual = static_cast<const bf16*>(residual); d.ldr = N; d.act = act;
+    int dev = 0; cudaGetDevice(&dev);
+    int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    GemmPlan pl;
+    if (gemm_plan(d, sms, &pl)) return -1;
+    return gemm_launch(pl, as_stream(stream));
+}
+
+int ams_op_wgrad(const void* x, int cin, const void* dz, int cout, long long M, float* dw, void* stream) {
+    int dev = 0; cudaGetDevice(&dev);
+    int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    WgradDesc d;
+    d.X = static_cast<const bf16*>(x); d.ldx = cin; d.Cin = cin; d.dZ = static_cast<const bf16*>(dz); d.ldz = cout; d.Cout = cout;
+    d.M = M; d.dW = dw; d.lddw = cout;
+    const size_t wsf = wgrad_workspace_floats(cin, cout, M, sms);
+    float* ws = nullptr;
+    if (wsf) AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), wsf * sizeof(float)));
+    d.workspace = ws; d.workspace_floats = wsf;
+    WgradPlan pl;
+    int rc = wgrad_plan(d, sms, &pl);
+    if (!rc) rc = wgrad_launch(pl, as_stream(stream));
+    if (ws) { cudaStreamSynchronize(as_stream(stream)); cudaFree(ws); }
+    return rc;
+}
+
+static Conv2dGeom make_geom(int n, int h, int w, int c, int stride, int dil) {
+    Conv2dGeom g;
+    g.N = n; g.H = h; g.W = w; g.C = c; g.stride = stride; g.dil = dil;
+    g.Ho = (h + stride - 1) / stride; g.Wo = (w + stride - 1) / stride;
+    g.pad_top = std::max((g.Ho - 1) * stride + 2 * dil + 1 - h, 0) / 2;
+    g.pad_left = std::max((g.Wo - 1) * stride + 2 * dil + 1 - w, 0) / 2;
+    return g;
+}
+
+int ams_op_depthwise(const void* in, const float* w, int n, int h, int w_, int c, int stride, int dil, const float* scale,
+                     const float* shift, int act, void* out, void* stream) {
+    return dw_conv_fwd(static_cast<const bf16*>(in), w, make_geom(n, h, w_, c, stride, dil), scale, shift, act,
+                       static_cast<bf16*>(out), as_stream(stream));
+}
+
+int ams_op_depthwise_bwd(const void* x, const void* dz, const float* w, int n, int h, int w_, int c, int stride, int dil,
+                         void* dx, float* dw, void* stream) {
+    const Conv2dGeom g = make_geom(n, h, w_, c, stride, dil);
+    if (dx && dw_conv_bwd_data(static_cast<const bf16*>(dz), w, g, static_cast<bf16*>(dx), as_stream(stream))) return -1;
+    if (dw) {
+        const size_t wsf = dw_bwd_workspace_floats(g);
+        float* ws = nullptr;
+        AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), wsf * sizeof(float)));
+        int rc = dw_conv_bwd_filter(static_cast<const bf16*>(x), static_cast<const bf16*>(dz), g, dw, ws, wsf, as_stream(stream));
+        cudaStreamSynchronize(as_stream(stream));
+        cudaFree(ws);
+        return rc;
+    }
+    return 0;
+}
+
+static void stem_geom(int h, int w, int* Hp, int* Wp, int* Ho, int* Wo, int* pt, int* pl) {
+    *Hp = h + 1; *Wp = w + 1;
+    *Ho = (*Hp + 1) / 2; *Wo = (*Wp + 1) / 2;
+    *pt = std::max((*Ho - 1) * 2 + 3 - *Hp, 0) / 2;
+    *pl = std::max((*Wo - 1) * 2 + 3 - *Wp, 0) / 2;
+}
+
+int ams_op_stem(const void* frames, int dtype, int n, int h, int w_, const float* w, const float* scale, const float* shift,
+                void* out, void* stream) {
+    int Hp, Wp, Ho, Wo, pt, pl;
+    stem_geom(h, w_, &Hp, &Wp, &Ho, &Wo, &pt, &pl);
+    return stem_conv_fwd(frames, dtype == AMS_FRAMES_U8, n, h, w_, Hp, Wp, Ho, Wo, pt, pl, 127.5f, 0.007843137718737125f, 1.0f, w,
+                         scale, shift, static_cast<bf16*>(out), as_stream(stream));
+}
+
+int ams_op_stem_bwd(const void* frames, int dtype, int n, int h, int w_, const void* dz, float* dw, void* stream) {
+    int Hp, Wp, Ho, Wo, pt, pl;
+    stem_geom(h, w_, &Hp, &Wp, &Ho, &Wo, &pt, &pl);
+    const size_t wsf = stem_bwd_workspace_floats(n, Ho, Wo);
+    float* ws = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), wsf * sizeof(float)));
+    int rc = stem_conv_bwd_filter(frames, dtype == AMS_FRAMES_U8, n, h, w_, Hp, Wp, Ho, Wo, pt, pl, 127.5f, 0.007843137718737125f,
+                                  1.0f, static_cast<const bf16*>(dz), dw, ws, wsf, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(ws);
+    return rc;
+}
+
+int ams_op_bn_train(const void* z, long long M, int C, const float* gamma, const float* beta, float eps, int act,
+                    const void* residual, void* y, float* mean, float* rstd, void* stream) {
+    float* tmp = nullptr; double* ws = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmp), 4 * C * sizeof(float)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), bn_workspace_doubles(M, C) * sizeof(double)));
+    BnLayer L;
+    L.C = C; L.M = M; L.eps = eps; L.one_minus_decay = 0.f; L.gamma = gamma; L.beta = beta;
+    L.moving_mean = tmp + 2 * C; L.moving_var = tmp + 3 * C; L.mean = mean; L.rstd = rstd; L.scale = tmp; L.shift = tmp + C;
+    int rc = bn_forward_stats(static_cast<const bf16*>(z), L, 0, ws, as_stream(stream));
+    if (!rc) rc = bn_apply(static_cast<const bf16*>(z), L.scale, L.shift, act, static_cast<const bf16*>(residual),
+                           static_cast<bf16*>(y), M, C, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(tmp); cudaFree(ws);
+    return rc;
+}
+
+int ams_op_bn_backward(const void* dy, const void* z, long long M, int C, const float* gamma, const float* beta, float eps,
+                       int act, void* dz, float* dgamma, float* dbeta, void* stream) {
+    float* tmp = nullptr; double* ws = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmp), 6 * C * sizeof(float)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), bn_workspace_doubles(M, C) * sizeof(double)));
+    BnLayer L;
+    L.C = C; L.M = M; L.eps = eps; L.one_minus_decay = 0.f; L.gamma = gamma; L.beta = beta;
+    L.moving_mean = tmp + 4 * C; L.moving_var = tmp + 5 * C; L.mean = tmp + 2 * C; L.rstd = tmp + 3 * C; L.scale = tmp; L.shift = tmp + C;
+    int rc = bn_forward_stats(static_cast<const bf16*>(z), L, 0, ws, as_stream(stream));
+    if (!rc) rc = bn_backward(static_cast<const bf16*>(dy), nullptr, static_cast<const bf16*>(z), L, act, static_cast<bf16*>(dz),
+                              dgamma, dbeta, ws, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(tmp); cudaFree(ws);
+    return rc;
+}
+
+static int op_head_geom(int n, int h, int w, int ldl, int H, int W, int cc, const int* cls, int depth, HeadGeom* g) {
+    ams_config c{};
+    c.num_classes = 32; c.height = H; c.width = W; c.class_count = cc; c.label_depth = depth;
+    for (int i = 0; i < cc && i < AMS_MAX_CLASSES; ++i) c.class_indices[i] = cls[i];
+    if (fill_head_geom(c, h, w, g)) return -1;
+    g->N = n; g->ldl = ldl;
+    return 0;
+}
+
+int ams_op_head_infer(const float* logits, int n, int h, int w_, int ldl, int H, int W, int cc, const int* cls, int depth,
+                      const uint8_t* labels, int32_t* pred, int64_t* confmat, double* loss_sum, long long* n_valid, void* stream) {
+    HeadGeom g;
+    if (op_head_geom(n, h, w_, ldl, H, W, cc, cls, depth, &g)) return -1;
+    HeadStats* st = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&st), sizeof(HeadStats)));
+    int rc = head_reset(st, as_stream(stream));
+    if (!rc) rc = head_infer(logits, g, labels, pred, st, as_stream(stream));
+    HeadStats hs;
+    cudaMemcpyAsync(&hs, st, sizeof(hs), cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(st);
+    if (confmat) for (int i = 0; i < cc; ++i) for (int j = 0; j < cc; ++j) confmat[i * cc + j] = hs.confmat[i * kMaxClasses + j];
+    if (loss_sum) *loss_sum = hs.loss_sum;
+    if (n_valid) *n_valid = hs.n_valid;
+    return rc;
+}
+
+int ams_op_head_backward(const float* logits, int n, int h, int w_, int H, int W, int cc, const int* cls, int depth,
+                         const uint8_t* labels, float* dlogits, float* loss, void* stream) {
+    HeadGeom g;
+    if (op_head_geom(n, h, w_, 32, H, W, cc, cls, depth, &g)) return -1;
+    g.normalize = 1;
+    HeadStats* st = nullptr; float* rowbuf = nullptr; bf16* d16 = nullptr; float* loss_dev = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&st), sizeof(HeadStats)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&rowbuf), head_rowbuf_floats(g) * sizeof(float)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d16), static_cast<size_t>(n) * h * w_ * 32 * sizeof(bf16)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&loss_dev), sizeof(float)));
+    int rc = head_loss_backward(logits, g, labels, rowbuf, dlogits, d16, st, loss_dev, as_stream(stream));
+    if (loss) cudaMemcpyAsync(loss, loss_dev, sizeof(float), cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(st); cudaFree(rowbuf); cudaFree(d16); cudaFree(loss_dev);
+    return rc;
+}
+
+int ams_op_select(float* after, const float* before, long long n, double coord_frac, uint8_t* mask, long long* kept,
+                  float* threshold, void* stream) {
+    long long lo; double w_hi;
+    percentile_rank(coord_frac, n, &lo, &w_hi);
+    float* d = nullptr; SelectScratch* sc = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d), n * sizeof(float)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&sc), sizeof(SelectScratch)));
+    int rc = select_coordinates(after, before, d, mask, n, lo, w_hi, sc, as_stream(stream));
+    SelectScratch hs;
+    cudaMemcpyAsync(&hs, sc, sizeof(hs), cudaMemcpyDeviceToHost, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(d); cudaFree(sc);
+    if (kept) *kept = static_cast<long long>(hs.kept);
+    if (threshold) *threshold = hs.threshold;
+    return rc;
+}
+
+int ams_op_adam(float* p, const float* g, float* m, float* v, const uint8_t* mask, long long n, float lr, float b1p, float b2p,
+                void* stream) {
+    const float alpha = lr * std::sqrt(1.0f - b2p) / (1.0f - b1p);
+    return adam_masked(p, g, 1.0f, m, v, mask, n, alpha, 1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, as_stream(stream));
+}
+
+}  // extern "C"

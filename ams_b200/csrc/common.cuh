@@ -1,0 +1,88 @@
+// Shared device/host helpers for the sm_100a kernels of libams_b200.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace ams {
+
+// ----------------------------------------------------------------------------- errors
+void set_last_error(const std::string& msg);
+#define AMS_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ams::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +    \
+                                __FILE__ + ":" + std::to_string(__LINE__));                      \
+            return -1;                                                                           \
+        }                                                                                        \
+    } while (0)
+#define AMS_REQUIRE(cond, msg)                                                                   \
+    do {                                                                                         \
+        if (!(cond)) {                                                                           \
+            ams::set_last_error(std::string("requirement failed: ") + #cond + " -- " + (msg) +  \
+                                " at " + __FILE__ + ":" + std::to_string(__LINE__));             \
+            return -2;                                                                           \
+        }                                                                                        \
+    } while (0)
+#define AMS_LAUNCH_CHECK() AMS_CUDA_CHECK(cudaGetLastError())
+
+constexpr int kNumSMs = 148;   // B200; grids of the persistent kernels are sized from the runtime value
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- bf16 pack / unpack
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+// streaming 128-bit loads/stores (read-once / write-once tensors: keep them out of L1)
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 256-bit store (sm_100+): one full 32-byte sector per thread
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {   // 0 none, 1 relu, 2 relu6
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return fminf(fmaxf(v, 0.f), 6.f);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ams

@@ -1,0 +1,403 @@
+// Direct (CUDA-core) convolution kernels: the 3x3 stem (Cin=3: K=27 is too small for tensor cores) and the
+// 17 depthwise 3x3 layers with their gradients.  All are HBM-bound (AI 1.8-19.7 flop/B):
+// 128-bit NHWC channel-vector accesses, register sliding windows, no materialised padding.
+// Replaces: `MobilenetV2/Conv/Conv2D`, the `DepthwiseConv2dNative` nodes (+ SpaceToBatchND/BatchToSpaceND
+// atrous wrappers) of checkpoints/*/model.meta and their TF-generated gradients.
+#include "kernels.cuh"
+
+namespace ams {
+namespace {
+
+// ============================================================================================ stem
+template <typename T> __device__ __forceinline__ float load_px(const T* p);
+template <> __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return static_cast<float>(*p); }
+template <> __device__ __forceinline__ float load_px<float>(const float* p) { return *p; }
+
+struct StemGeom {
+    int N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left;
+    float pad_value, norm_scale, norm_shift;
+};
+
+// value of the padded + normalised input at padded coordinate (y, x) of image n, channel c
+template <typename T>
+__device__ __forceinline__ void stem_pixel(const T* in, const StemGeom& g, int n, int y, int x, float* v3) {
+    if (y < 0 || x < 0 || y >= g.Hp || x >= g.Wp) { v3[0] = v3[1] = v3[2] = 0.f; return; }   // conv zero pad
+    if (y >= g.H || x >= g.W) {                                                               // graph mean-pixel pad
+        const float t = __fsub_rn(__fmul_rn(g.norm_scale, g.pad_value), g.norm_shift);
+        v3[0] = v3[1] = v3[2] = t;
+        return;
+    }
+    const T* p = in + (static_cast<long long>(n) * g.H * g.W + static_cast<long long>(y) * g.W + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v3[c] = __fsub_rn(__fmul_rn(g.norm_scale, load_px<T>(p + c)), g.norm_shift);
+}
+
+// one thread = one output pixel x 16 output channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ w, const float* __restrict__ scale,
+                const float* __restrict__ shift, bf16* __restrict__ out) {
+    __shared__ float sw[27 * 32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo * 2;
+    if (tid >= total) return;
+    const int half = static_cast<int>(tid & 1);
+    const long long pix = tid >> 1;
+    const int ox = static_cast<int>(pix % g.Wo);
+    const int oy = static_cast<int>((pix / g.Wo) % g.Ho);
+    const int n = static_cast<int>(pix / (static_cast<long long>(g.Wo) * g.Ho));
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            float v[3];
+            stem_pixel<T>(in, g, n, oy * 2 - g.pad_top + ky, ox * 2 - g.pad_left + kx, v);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* wr = sw + ((ky * 3 + kx) * 3 + c) * 32 + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = fmaf(v[c], wr[j], acc[j]);
+            }
+        }
+    }
+    if (scale) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            acc[j] = fminf(fmaxf(fmaf(acc[j], scale[half * 16 + j], shift[half * 16 + j]), 0.f), 6.f);
+    }
+    bf16* o = out + pix * 32 + half * 16;
+    stg256(o, pack8(acc), pack8(acc + 8));
+}
+
+// filter gradient: block stages P output pixels (27-tap patches + 32 dz values), thread (k, co4) owns 4 weights
+constexpr int kStemBwdPix = 128;
+constexpr int kStemBwdThreads = 27 * 8;
+template <typename T>
+__global__ void __launch_bounds__(kStemBwdThreads)
+stem_bwd_filter_kernel(const T* __restrict__ in, StemGeom g, const bf16* __restrict__ dz, float* __restrict__ partial,
+                       int pix_per_block) {
+    __shared__ float s_patch[kStemBwdPix][28];
+    __shared__ __align__(16) float s_dz[kStemBwdPix][32];
+    const int k = threadIdx.x / 8, co4 = threadIdx.x % 8;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
+    const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_block;
+    const long long p_end = min(p_begin + pix_per_block, total);
+    for (long long p0 = p_begin; p0 < p_end; p0 += kStemBwdPix) {
+        const int np = static_cast<int>(min(static_cast<long long>(kStemBwdPix), p_end - p0));
+        __syncthreads();
+        for (int i = threadIdx.x; i < np * 9; i += blockDim.x) {
+            const int pp = i / 9, tap = i % 9;
+            const long long pix = p0 + pp;
+            const int ox = static_cast<int>(pix % g.Wo);
+            const int oy = static_cast<int>((pix / g.Wo) % g.Ho);
+            const int n = static_cast<int>(pix / (static_cast<long long>(g.Wo) * g.Ho));
+            float v[3];
+            stem_pixel<T>(in, g, n, oy * 2 - g.pad_top + tap / 3, ox * 2 - g.pad_left + tap % 3, v);
+            s_patch[pp][tap * 3 + 0] = v[0]; s_patch[pp][tap * 3 + 1] = v[1]; s_patch[pp][tap * 3 + 2] = v[2];
+        }
+        for (int i = threadIdx.x; i < np * 4; i += blockDim.x) {
+            const int pp = i / 4, c8 = i % 4;
+            float f[8];
+            unpack8(ldg_stream(dz + (p0 + pp) * 32 + c8 * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_dz[pp][c8 * 8 + j] = f[j];
+        }
+        __syncthreads();
+        for (int pp = 0; pp < np; ++pp) {
+            const float a = s_patch[pp][k];
+            const float4 d = *reinterpret_cast<const float4*>(&s_dz[pp][co4 * 4]);
+            acc[0] = fmaf(a, d.x, acc[0]); acc[1] = fmaf(a, d.y, acc[1]);
+            acc[2] = fmaf(a, d.z, acc[2]); acc[3] = fmaf(a, d.w, acc[3]);
+        }
+    }
+    float* o = partial + static_cast<long long>(blockIdx.x) * 864 + k * 32 + co4 * 4;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int chunks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int c = 0; c < chunks; ++c) acc += static_cast<double>(partial[static_cast<long long>(c) * n + i]);
+    out[i] = static_cast<float>(acc);
+}
+
+// ============================================================================================ depthwise
+// thread = 8 channels x TW consecutive output pixels along W; sliding window over the needed input columns
+template <int S, int D, int TW>
+__global__ void __launch_bounds__(256)
+dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGeom g, const float* __restrict__ scale,
+              const float* __restrict__ shift, int act, bf16* __restrict__ out) {
+    const int C8 = g.C >> 3;
+    const int WG = (g.Wo + TW - 1) / TW;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(g.N) * g.Ho * WG * C8;
+    if (tid >= total) return;
+    const int c8 = static_cast<int>(tid % C8);
+    long long r = tid / C8;
+    const int xg = static_cast<int>(r % WG); r /= WG;
+    const int oy = static_cast<int>(r % g.Ho);
+    const int n = static_cast<int>(r / g.Ho);
+    const int ox0 = xg * TW;
+    const int c0 = c8 * 8;
+    constexpr int NCOLS = (TW - 1) * S + 2 * D + 1;
+    float acc[TW][8];
+#pragma unroll
+    for (int t = 0; t < TW; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+    const int ix0 = ox0 * S - g.pad_left;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * S - g.pad_top + ky * D;
+        if (iy < 0 || iy >= g.H) continue;
+        float wk[3][8];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float4 a = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * g.C + c0);
+            const float4 b = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * g.C + c0 + 4);
+            wk[kx][0] = a.x; wk[kx][1] = a.y; wk[kx][2] = a.z; wk[kx][3] = a.w;
+            wk[kx][4] = b.x; wk[kx][5] = b.y; wk[kx][6] = b.z; wk[kx][7] = b.w;
+        }
+        const bf16* row = in + ((static_cast<long long>(n) * g.H + iy) * g.W) * g.C + c0;
+#pragma unroll
+        for (int j = 0; j < NCOLS; ++j) {
+            // does any (t, kx) use column j?  t*S + kx*D == j
+            bool used = false;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) used = used || ((j - kx * D) >= 0 && (j - kx * D) % S == 0 && (j - kx * D) / S < TW);
+            if (!used) continue;
+            const int ix = ix0 + j;
+            if (ix < 0 || ix >= g.W) continue;
+            float v[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * g.C)), v);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tt = j - kx * D;
+                if (tt >= 0 && tt % S == 0 && tt / S < TW) {
+                    const int t = tt / S;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[t][q] = fmaf(v[q], wk[kx][q], acc[t][q]);
+                }
+            }
+        }
+    }
+    float sc[8], sh[8];
+    if (scale) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { sc[q] = scale[c0 + q]; sh[q] = shift[c0 + q]; }
+    }
+#pragma unroll
+    for (int t = 0; t < TW; ++t) {
+        const int ox = ox0 + t;
+        if (ox >= g.Wo) break;
+        if (scale) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[t][q] = act_apply(fmaf(acc[t][q], sc[q], sh[q]), act);
+        }
+        stg_stream(out + ((static_cast<long long>(n) * g.Ho + oy) * g.Wo + ox) * g.C + c0, pack8(acc[t]));
+    }
+}
+
+// dx[iy,ix,c] = sum_{ky,kx} dz[(iy+pt-ky*D)/S, (ix+pl-kx*D)/S, c] * w[ky,kx,c]   (where divisible and in range)
+template <int S, int D>
+__global__ void __launch_bounds__(256)
+dw_bwd_data_kernel(const bf16* __restrict__ dz, const float* __restrict__ w, Conv2dGeom g, bf16* __restrict__ dx) {
+    const int C8 = g.C >> 3;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(g.N) * g.H * g.W * C8;
+    if (tid >= total) return;
+    const int c0 = static_cast<int>(tid % C8) * 8;
+    long long r = tid / C8;
+    const int ix = static_cast<int>(r % g.W); r /= g.W;
+    const int iy = static_cast<int>(r % g.H);
+    const int n = static_cast<int>(r / g.H);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ty = iy + g.pad_top - ky * D;
+        if (ty < 0 || ty % S != 0) continue;
+        const int oy = ty / S;
+        if (oy >= g.Ho) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int tx = ix + g.pad_left - kx * D;
+            if (tx < 0 || tx % S != 0) continue;
+            const int ox = tx / S;
+            if (ox >= g.Wo) continue;
+            float v[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dz + ((static_cast<long long>(n) * g.Ho + oy) * g.Wo + ox) * g.C + c0)), v);
+            const float4 a = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * g.C + c0);
+            const float4 b = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * g.C + c0 + 4);
+            acc[0] = fmaf(v[0], a.x, acc[0]); acc[1] = fmaf(v[1], a.y, acc[1]);
+            acc[2] = fmaf(v[2], a.z, acc[2]); acc[3] = fmaf(v[3], a.w, acc[3]);
+            acc[4] = fmaf(v[4], b.x, acc[4]); acc[5] = fmaf(v[5], b.y, acc[5]);
+            acc[6] = fmaf(v[6], b.z, acc[6]); acc[7] = fmaf(v[7], b.w, acc[7]);
+        }
+    }
+    stg_stream(dx + ((static_cast<long long>(n) * g.H + iy) * g.W + ix) * g.C + c0, pack8(acc));
+}
+
+// dW[ky,kx,c] = sum_{n,oy,ox} x[iy,ix,c] * dz[oy,ox,c].  block = (32 channel-groups) x (8 pixel lanes);
+// each block owns a contiguous run of output pixels, partial [chunk][9][C] reduced in fixed order afterwards.
+constexpr int kDwBwdLanesC = 32, kDwBwdLanesP = 4;
+__global__ void __launch_bounds__(kDwBwdLanesC * kDwBwdLanesP)
+dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Conv2dGeom g, float* __restrict__ partial,
+                     int pix_per_block) {
+    __shared__ float s_red[kDwBwdLanesP][kDwBwdLanesC][9 * 8 + 1];
+    const int C8 = g.C >> 3;
+    const int lc = threadIdx.x % kDwBwdLanesC, lp = threadIdx.x / kDwBwdLanesC;
+    const int c8 = blockIdx.y * kDwBwdLanesC + lc;
+    const bool c_ok = c8 < C8;
+    const int c0 = c8 * 8;
+    float acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[t][q] = 0.f;
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
+    const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_block;
+    const long long p_end = min(p_begin + pix_per_block, total);
+    if (c_ok) {
+        for (long long pix = p_begin + lp; pix < p_end; pix += kDwBwdLanesP) {
+            const int ox = static_cast<int>(pix % g.Wo);
+            const int oy = static_cast<int>((pix / g.Wo) % g.Ho);
+            const int n = static_cast<int>(pix / (static_cast<long long>(g.Wo) * g.Ho));
+            float d[8];
+            unpack8(ldg_stream(dz + pix * g.C + c0), d);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = oy * g.stride - g.pad_top + ky * g.dil;
+                if (iy < 0 || iy >= g.H) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox * g.stride - g.pad_left + kx * g.dil;
+                    if (ix < 0 || ix >= g.W) continue;
+                    float v[8];
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * g.H + iy) * g.W + ix) * g.C + c0)), v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[ky * 3 + kx][q] = fmaf(v[q], d[q], acc[ky * 3 + kx][q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_red[lp][lc][t * 8 + q] = acc[t][q];
+    __syncthreads();
+    // thread (lp, lc): sum the kDwBwdLanesP pixel lanes for 9 of the 72 (tap, q) entries
+    if (c_ok) {
+        for (int e = lp; e < 72; e += kDwBwdLanesP) {
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < kDwBwdLanesP; ++l) sum += s_red[l][lc][e];
+            const int t = e / 8, q = e % 8;
+            partial[(static_cast<long long>(blockIdx.x) * 9 + t) * g.C + c0 + q] = sum;
+        }
+    }
+}
+
+int blocks_for(long long total, int threads) { return static_cast<int>((total + threads - 1) / threads); }
+
+constexpr int kStemPixPerBlock = 2048;
+int dw_pix_per_block(const Conv2dGeom& g) {
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
+    const int cgroups = ceil_div(g.C / 8, kDwBwdLanesC);
+    long long want_blocks = std::max<long long>(1, (4LL * kNumSMs) / cgroups);
+    long long ppb = std::max<long long>(64, ceil_div_ll(total, want_blocks));
+    return static_cast<int>(ppb);
+}
+
+}  // namespace
+
+// ============================================================================================ host
+int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
+                  int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w, const float* scale,
+                  const float* shift, bf16* out, cudaStream_t s) {
+    StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
+    const long long total = static_cast<long long>(N) * Ho * Wo * 2;
+    if (in_is_u8)
+        stem_fwd_kernel<uint8_t><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const uint8_t*>(in), g, w, scale, shift, out);
+    else
+        stem_fwd_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const float*>(in), g, w, scale, shift, out);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t stem_bwd_workspace_floats(int N, int Ho, int Wo) {
+    const long long total = static_cast<long long>(N) * Ho * Wo;
+    return static_cast<size_t>(ceil_div_ll(total, kStemPixPerBlock)) * 864;
+}
+
+int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
+                         int pad_left, float pad_value, float norm_scale, float norm_shift, const bf16* dz, float* dw,
+                         float* workspace, size_t workspace_floats, cudaStream_t s) {
+    StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
+    const long long total = static_cast<long long>(N) * Ho * Wo;
+    const int chunks = static_cast<int>(ceil_div_ll(total, kStemPixPerBlock));
+    AMS_REQUIRE(workspace_floats >= static_cast<size_t>(chunks) * 864, "stem bwd workspace too small");
+    if (in_is_u8)
+        stem_bwd_filter_kernel<uint8_t><<<chunks, kStemBwdThreads, 0, s>>>(static_cast<const uint8_t*>(in), g, dz, workspace, kStemPixPerBlock);
+    else
+        stem_bwd_filter_kernel<float><<<chunks, kStemBwdThreads, 0, s>>>(static_cast<const float*>(in), g, dz, workspace, kStemPixPerBlock);
+    AMS_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div(864, 256), 256, 0, s>>>(workspace, dw, 864, chunks);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+int dw_conv_fwd(const bf16* in, const float* w, const Conv2dGeom& g, const float* scale, const float* shift, int act,
+                bf16* out, cudaStream_t s) {
+    AMS_REQUIRE(g.C % 8 == 0, "depthwise channels must be a multiple of 8");
+    constexpr int TW = 4;
+    const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, TW) * (g.C / 8);
+    const int nb = blocks_for(total, 256);
+    if (g.stride == 1 && g.dil == 1) dw_fwd_kernel<1, 1, TW><<<nb, 256, 0, s>>>(in, w, g, scale, shift, act, out);
+    else if (g.stride == 2 && g.dil == 1) dw_fwd_kernel<2, 1, TW><<<nb, 256, 0, s>>>(in, w, g, scale, shift, act, out);
+    else if (g.stride == 1 && g.dil == 2) dw_fwd_kernel<1, 2, TW><<<nb, 256, 0, s>>>(in, w, g, scale, shift, act, out);
+    else AMS_REQUIRE(false, "unsupported depthwise stride/dilation");
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+int dw_conv_bwd_data(const bf16* dz, const float* w, const Conv2dGeom& g, bf16* dx, cudaStream_t s) {
+    const long long total = static_cast<long long>(g.N) * g.H * g.W * (g.C / 8);
+    const int nb = blocks_for(total, 256);
+    if (g.stride == 1 && g.dil == 1) dw_bwd_data_kernel<1, 1><<<nb, 256, 0, s>>>(dz, w, g, dx);
+    else if (g.stride == 2 && g.dil == 1) dw_bwd_data_kernel<2, 1><<<nb, 256, 0, s>>>(dz, w, g, dx);
+    else if (g.stride == 1 && g.dil == 2) dw_bwd_data_kernel<1, 2><<<nb, 256, 0, s>>>(dz, w, g, dx);
+    else AMS_REQUIRE(false, "unsupported depthwise stride/dilation");
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+size_t dw_bwd_workspace_floats(const Conv2dGeom& g) {
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
+    const int ppb = dw_pix_per_block(g);
+    return static_cast<size_t>(ceil_div_ll(total, ppb)) * 9 * g.C;
+}
+
+int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
+                       size_t workspace_floats, cudaStream_t s) {
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
+    const int ppb = dw_pix_per_block(g);
+    const int chunks = static_cast<int>(ceil_div_ll(total, ppb));
+    AMS_REQUIRE(workspace_floats >= static_cast<size_t>(chunks) * 9 * g.C, "depthwise bwd workspace too small");
+    dim3 grid(chunks, ceil_div(g.C / 8, kDwBwdLanesC));
+    dw_bwd_filter_kernel<<<grid, kDwBwdLanesC * kDwBwdLanesP, 0, s>>>(x, dz, g, workspace, ppb);
+    AMS_LAUNCH_CHECK();
+    reduce_partials_kernel<<<ceil_div(9 * g.C, 256), 256, 0, s>>>(workspace, dw, 9 * g.C, chunks);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace ams

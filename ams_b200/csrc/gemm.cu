@@ -1,0 +1,487 @@
+// tcgen05 / TMEM / TMA GEMM kernels for the 1x1 convolutions of the AMS student (sm_100a only).
+//
+//  gemm_kmajor_kernel : OUT[M,N] = epi(A[M,K] * B[N,K]^T)   forward 1x1 conv and its data gradient.
+//      Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
+//      tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> fused BN/act/residual -> HBM).
+//      Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+//      These layers are HBM-bound (AI = K*N/(K+N) flop/B): the kernel's job is to stream
+//      A once and write OUT once; weights stay L2-resident.
+//  gemm_wgrad_kernel  : dW[Cin,Cout] = sum_m X[m,Cin] * dZ[m,Cout]  (filter gradient).
+//      Both operands are consumed MN-major straight from their NHWC layout (no transpose pass);
+//      the pixel dimension is split across CTAs, partials are reduced in a fixed order (deterministic).
+//
+// Replaces: cuDNN implicit-GEMM calls behind tf.Session.run for every 1x1 `Conv2D` node of
+// checkpoints/*/model.meta and their gradients (reference SemanticNetwork.py:260, :179).
+#include "gemm.cuh"
+#include "tcgen05.cuh"
+
+#include <cudaTypedefs.h>
+#include <algorithm>
+
+namespace ams {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;    // 6 warps
+constexpr int kMaxStages = 8;
+constexpr size_t kSmemBudget = 200 * 1024;
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor [outer][inner] with a 128B-swizzled box; out-of-bounds elements read as zero.
+int encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                   uint32_t box_inner, uint32_t box_outer) {
+    auto fn = get_encode_fn();
+    AMS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+    AMS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+    AMS_REQUIRE(row_stride_bytes % 16 == 0, "TMA row stride must be a multiple of 16 bytes");
+    AMS_REQUIRE(box_inner * 2 <= 128 && box_outer <= 256, "TMA box too large");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AMS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+    return 0;
+}
+
+uint32_t tmem_cols_for(int n) {
+    uint32_t c = 32;
+    while (c < static_cast<uint32_t>(n)) c <<= 1;
+    return c;
+}
+
+// =============================================================================================
+//                                   K-major GEMM (forward / dgrad)
+// =============================================================================================
+struct GemmKParams {
+    int M, N, K;
+    int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc;
+    uint32_t tmem_cols;
+    void* out; int ldc; int out_fp32;
+    const float* scale; const float* shift; const float* rowbias; int rows_per_image;
+    const __nv_bfloat16* residual; int ldr;
+    int act;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const GemmKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_a = BLOCK_M * BLOCK_K * 2;
+    const int stage_b = p.block_n * BLOCK_K * 2;
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + p.stages * stage_a;
+    float* s_scale = reinterpret_cast<float*>(smB + p.stages * stage_b);
+    float* s_shift = s_scale + p.n_alloc;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_shift + p.n_alloc);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        t5::tma_prefetch_desc(&tmA);
+        t5::tma_prefetch_desc(&tmB);
+        for (int s = 0; s < p.stages; ++s) { t5::mbar_init(&full_bar[s], 1); t5::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { t5::mbar_init(&tfull_bar[s], 1); t5::mbar_init(&tempty_bar[s], 128); }
+        t5::fence_barrier_init();
+    }
+    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
+    for (int n = threadIdx.x; n < p.n_alloc; n += kGemmThreads) {
+        s_scale[n] = (n < p.N) ? (p.scale ? p.scale[n] : 1.f) : 0.f;
+        s_shift[n] = (n < p.N && p.shift) ? p.shift[n] : 0.f;
+    }
+    t5::fence_before_thread_sync();
+    __syncthreads();
+    t5::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    t5::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + stage_b);
+                    t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+                    t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+            t5::mbar_wait(&tempty_bar[as], aphase ^ 1);
+            t5::fence_after_thread_sync();
+            const uint32_t tmem_d = tmem_base + as * p.block_n;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                t5::mbar_wait(&full_bar[stage], phase);
+                t5::fence_after_thread_sync();
+                if (lane == 0) {
+                    const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
+                    const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // K-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO); +32 B per UMMA_K step
+                        const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                        t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
+                    }
+                    t5::mma_commit(&empty_bar[stage]);                    // frees the smem slot when MMAs retire
+                    if (kb == p.k_blocks - 1) t5::mma_commit(&tfull_bar[as]);   // accumulator ready
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const bool st256 = (!p.out_fp32) && (p.ldc % 16 == 0);
+        int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
+            const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+            t5::mbar_wait(&tfull_bar[as], aphase);
+            t5::fence_after_thread_sync();
+            const long long m = static_cast<long long>(m_tile) * BLOCK_M + row;
+            const bool row_ok = m < p.M;
+            const float* rb = nullptr;
+            if (p.rowbias && row_ok) rb = p.rowbias + (m / p.rows_per_image) * p.N;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.block_n;
+            for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+                uint32_t r[16];
+                t5::tmem_ld16(taddr0 + c0, r);
+                t5::tmem_ld_wait();
+                const int n0 = n_tile * p.block_n + c0;
+                if (!row_ok) continue;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (rb) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n0 + j < p.N) v[j] += rb[n0 + j];
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = act_apply(fmaf(v[j], s_scale[n0 + j], s_shift[n0 + j]), p.act);
+                if (p.out_fp32) {
+                    float* o = reinterpret_cast<float*>(p.out) + m * p.ldc + n0;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        if (n0 + j < p.ldc) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                    const int valid = p.N - n0;       // N % 8 == 0 for every bf16 output
+                    if (valid <= 0) continue;
+                    if (p.residual) {
+                        const __nv_bfloat16* rp = p.residual + m * p.ldr + n0;
+                        float f[8];
+                        unpack8(ldg_stream(rp), f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] += f[j];
+                        if (valid >= 16) {
+                            unpack8(ldg_stream(rp + 8), f);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[8 + j] += f[j];
+                        }
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
+                    const uint4 lo = pack8(v), hi = pack8(v + 8);
+                    if (valid >= 16) {
+                        if (st256) stg256(o, lo, hi);
+                        else { stg_stream(o, lo); stg_stream(o + 8, hi); }
+                    } else {
+                        stg_stream(o, lo);
+                    }
+                }
+            }
+            t5::fence_before_thread_sync();
+            t5::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    t5::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) {
+        t5::fence_after_thread_sync();
+        t5::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// =============================================================================================
+//                                   MN-major split-K GEMM (wgrad)
+// =============================================================================================
+struct WgradKParams {
+    int Cin, Cout, block_n, boxes_b, co_tiles, ci_tiles, splits, kb_per_split, k_blocks, stages;
+    uint32_t tmem_cols;
+    float* out;            // splits==1: dW [Cin][lddw]; else workspace [split][Cin][Cout]
+    int ld_out;
+    long long split_stride;
+};
+
+constexpr int kWgradBoxBytes = BLOCK_K * 128;      // one TMA box: 64 pixels x 64 channels bf16 = 8 KB
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmZ,
+                  const WgradKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_a = 2 * kWgradBoxBytes;                 // 128 input channels
+    const int stage_b = p.boxes_b * kWgradBoxBytes;
+    uint8_t* smA = smem;
+    uint8_t* smB = smem + p.stages * stage_a;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smB + p.stages * stage_b);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* done_bar = empty_bar + kMaxStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // work item
+    const int split = blockIdx.x % p.splits;
+    const int tile = blockIdx.x / p.splits;
+    const int co_tile = tile % p.co_tiles, ci_tile = tile / p.co_tiles;
+    const int kb0 = split * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.k_blocks);
+    const int nkb = max(kb1 - kb0, 0);
+
+    if (threadIdx.x == 0) {
+        t5::tma_prefetch_desc(&tmX);
+        t5::tma_prefetch_desc(&tmZ);
+        for (int s = 0; s < p.stages; ++s) { t5::mbar_init(&full_bar[s], 1); t5::mbar_init(&empty_bar[s], 1); }
+        t5::mbar_init(done_bar, 1);
+        t5::fence_barrier_init();
+    }
+    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
+    t5::fence_before_thread_sync();
+    __syncthreads();
+    t5::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                t5::mbar_wait(&empty_bar[stage], phase ^ 1);
+                t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + stage_b);
+                uint8_t* a = smA + stage * stage_a;
+                uint8_t* b = smB + stage * stage_b;
+                // box = [64 channels (inner), 64 pixels (outer)]; channels beyond the tensor read as zero
+                t5::tma_load_2d(a, &tmX, &full_bar[stage], ci_tile * 128, kb * BLOCK_K);
+                t5::tma_load_2d(a + kWgradBoxBytes, &tmX, &full_bar[stage], ci_tile * 128 + 64, kb * BLOCK_K);
+                for (int j = 0; j < p.boxes_b; ++j)
+                    t5::tma_load_2d(b + j * kWgradBoxBytes, &tmZ, &full_bar[stage], co_tile * p.block_n + j * 64,
+                                    kb * BLOCK_K);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int i = 0; i < nkb; ++i) {
+            t5::mbar_wait(&full_bar[stage], phase);
+            t5::fence_after_thread_sync();
+            if (lane == 0) {
+                const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
+                const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // MN-major SWIZZLE_128B: 64-channel atoms one TMA box apart (LBO), 8-pixel groups
+                    // 1024 B apart (SBO); a UMMA_K=16 step advances two pixel groups = 2048 B.
+                    const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * 2048, kWgradBoxBytes, 1024);
+                    const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * 2048, kWgradBoxBytes, 1024);
+                    t5::mma_bf16_ss(tmem_base, da, db, idesc, (i | k) != 0);
+                }
+                t5::mma_commit(&empty_bar[stage]);
+                if (i == nkb - 1) t5::mma_commit(done_bar);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ci = ci_tile * 128 + row;
+        float* o = p.out + static_cast<long long>(split) * p.split_stride + static_cast<long long>(ci) * p.ld_out;
+        if (nkb > 0) {
+            t5::mbar_wait(done_bar, 0);
+            t5::fence_after_thread_sync();
+        }
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+            uint32_t r[16];
+            if (nkb > 0) { t5::tmem_ld16(taddr0 + c0, r); t5::tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            const int n0 = co_tile * p.block_n + c0;
+            if (ci < p.Cin) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + j < p.Cout) o[n0 + j] = __uint_as_float(r[j]);
+            }
+        }
+    }
+    t5::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) {
+        t5::fence_after_thread_sync();
+        t5::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int lddw,
+                                    int splits, long long split_stride) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(Cin) * Cout) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[s * split_stride + i];     // fixed order => deterministic
+    dw[(i / Cout) * lddw + (i % Cout)] = acc;
+}
+
+}  // namespace
+
+// ============================================================================================= host
+int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
+    AMS_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "empty GEMM");
+    AMS_REQUIRE(d.lda % 8 == 0 && d.ldb % 8 == 0, "bf16 operand strides must be multiples of 8 elements");
+    AMS_REQUIRE(d.out_fp32 || (d.N % 8 == 0 && d.ldc % 8 == 0), "bf16 output needs N, ldc multiples of 8");
+    AMS_REQUIRE(!d.out_fp32 || d.ldc % 4 == 0, "fp32 output needs ldc multiple of 4");
+    AMS_REQUIRE(!d.residual || d.ldr % 8 == 0, "residual stride must be a multiple of 8");
+    plan->d = d;
+    const int npad = ceil_div(d.N, 16) * 16;
+    int t = ceil_div(npad, 256);
+    while (npad % (16 * t) != 0) ++t;
+    plan->block_n = npad / t;
+    plan->n_tiles = t;
+    plan->m_tiles = ceil_div(d.M, BLOCK_M);
+    plan->k_blocks = ceil_div(d.K, BLOCK_K);
+    plan->tmem_cols = tmem_cols_for(2 * plan->block_n);
+    AMS_REQUIRE(plan->tmem_cols <= 512, "TMEM overflow");
+    const size_t stage_bytes = size_t(BLOCK_M) * BLOCK_K * 2 + size_t(plan->block_n) * BLOCK_K * 2;
+    const size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 4) * 8 + 16;
+    int stages = int((kSmemBudget - fixed) / stage_bytes);
+    stages = std::max(2, std::min(stages, kMaxStages));
+    plan->stages = stages;
+    plan->smem_bytes = fixed + stages * stage_bytes;
+    const int tiles = plan->m_tiles * plan->n_tiles;
+    plan->grid = std::min(tiles, num_sms);
+    if (encode_2d_bf16(&plan->tmA, d.A, d.K, d.M, size_t(d.lda) * 2, BLOCK_K, BLOCK_M)) return -1;
+    if (encode_2d_bf16(&plan->tmB, d.B, d.K, d.N, size_t(d.ldb) * 2, BLOCK_K, plan->block_n)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    return 0;
+}
+
+int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
+    const GemmDesc& d = pl.d;
+    GemmKParams p;
+    p.M = d.M; p.N = d.N; p.K = d.K;
+    p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;
+    p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.n_alloc = pl.n_tiles * pl.block_n;
+    p.tmem_cols = pl.tmem_cols;
+    p.out = d.out; p.ldc = d.ldc; p.out_fp32 = d.out_fp32;
+    p.scale = d.scale; p.shift = d.shift; p.rowbias = d.rowbias; p.rows_per_image = d.rows_per_image;
+    p.residual = d.residual; p.ldr = d.ldr; p.act = d.act;
+    gemm_kmajor_kernel<<<pl.grid, kGemmThreads, pl.smem_bytes, stream>>>(pl.tmA, pl.tmB, p);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+static void wgrad_shape(int Cin, int Cout, long long M, int num_sms, int* ci_tiles, int* co_tiles, int* block_n,
+                        int* boxes_b, int* splits, int* kb_per_split, int* k_blocks) {
+    *ci_tiles = ceil_div(Cin, 128);
+    const int cpad = ceil_div(Cout, 16) * 16;
+    int t = ceil_div(cpad, 256);
+    // block_n must be a whole number of 64-channel TMA boxes unless it is the only tile
+    int bn = (t == 1) ? cpad : ceil_div(ceil_div(cpad, t), 64) * 64;
+    *co_tiles = ceil_div(cpad, bn);
+    *block_n = bn;
+    *boxes_b = ceil_div(bn, 64);
+    *k_blocks = int(ceil_div_ll(M, BLOCK_K));
+    const int tiles = (*ci_tiles) * (*co_tiles);
+    int want = std::max(1, (2 * num_sms) / tiles);
+    int max_splits = std::max(1, *k_blocks / 8);           // at least 8 k-blocks (512 pixels) per CTA
+    int s = std::min(want, max_splits);
+    *kb_per_split = ceil_div(*k_blocks, s);
+    *splits = ceil_div(*k_blocks, *kb_per_split);
+}
+
+size_t wgrad_workspace_floats(int Cin, int Cout, long long M, int num_sms) {
+    int a, b, c, d, s, e, f;
+    wgrad_shape(Cin, Cout, M, num_sms, &a, &b, &c, &d, &s, &e, &f);
+    return s > 1 ? size_t(s) * Cin * Cout : 0;
+}
+
+int wgrad_plan(const WgradDesc& d, int num_sms, WgradPlan* plan) {
+    AMS_REQUIRE(d.ldx % 8 == 0 && d.ldz % 8 == 0, "bf16 operand strides must be multiples of 8 elements");
+    plan->d = d;
+    wgrad_shape(d.Cin, d.Cout, d.M, num_sms, &plan->ci_tiles, &plan->co_tiles, &plan->block_n, &plan->boxes_b,
+                &plan->splits, &plan->kb_per_split, &plan->k_blocks);
+    AMS_REQUIRE(plan->splits == 1 || d.workspace_floats >= size_t(plan->splits) * d.Cin * d.Cout,
+                "wgrad workspace too small");
+    plan->tmem_cols = tmem_cols_for(plan->block_n);
+    const size_t stage_bytes = size_t(2 + plan->boxes_b) * kWgradBoxBytes;
+    const size_t fixed = 1024 + (2 * kMaxStages + 2) * 8 + 16;
+    int stages = int((kSmemBudget - fixed) / stage_bytes);
+    plan->stages = std::max(2, std::min(stages, kMaxStages));
+    plan->smem_bytes = fixed + plan->stages * stage_bytes;
+    if (encode_2d_bf16(&plan->tmX, d.X, d.Cin, d.M, size_t(d.ldx) * 2, 64, BLOCK_K)) return -1;
+    if (encode_2d_bf16(&plan->tmZ, d.dZ, d.Cout, d.M, size_t(d.ldz) * 2, 64, BLOCK_K)) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    return 0;
+}
+
+int wgrad_launch(const WgradPlan& pl, cudaStream_t stream) {
+    const WgradDesc& d = pl.d;
+    WgradKParams p;
+    p.Cin = d.Cin; p.Cout = d.Cout; p.block_n = pl.block_n; p.boxes_b = pl.boxes_b;
+    p.co_tiles = pl.co_tiles; p.ci_tiles = pl.ci_tiles; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
+    p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    if (pl.splits == 1) { p.out = d.dW; p.ld_out = d.lddw; p.split_stride = 0; }
+    else { p.out = d.workspace; p.ld_out = d.Cout; p.split_stride = static_cast<long long>(d.Cin) * d.Cout; }
+    const int grid = pl.ci_tiles * pl.co_tiles * pl.splits;
+    gemm_wgrad_kernel<<<grid, kGemmThreads, pl.smem_bytes, stream>>>(pl.tmX, pl.tmZ, p);
+    AMS_LAUNCH_CHECK();
+    if (pl.splits > 1) {
+        const long long n = static_cast<long long>(d.Cin) * d.Cout;
+        wgrad_reduce_kernel<<<int(ceil_div_ll(n, 256)), 256, 0, stream>>>(d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
+                                                                          pl.splits, p.split_stride);
+        AMS_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace ams

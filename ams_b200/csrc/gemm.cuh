@@ -1,0 +1,55 @@
+// Host-side interface of the tcgen05 GEMM kernels (gemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ams {
+
+// One 1x1-convolution-shaped contraction  OUT[M,N] = epilogue( A[M,K] * B[N,K]^T )
+//   A: activations, row-major [M, lda] bf16 (NHWC pixels x channels), K-major
+//   B: weights,     row-major [N, ldb] bf16, K-major (forward: [Cout][Cin]; dgrad: [Cin][Cout])
+// epilogue, in this order (fp32):  v = acc (+ rowbias[m / rows_per_image][n]) ; v = v*scale[n]+shift[n] ;
+//   v = act(v) ; v += residual[m][n] ; store bf16 or fp32.
+struct GemmDesc {
+    const __nv_bfloat16* A = nullptr; int lda = 0;
+    const __nv_bfloat16* B = nullptr; int ldb = 0;
+    int M = 0, N = 0, K = 0;
+    void* out = nullptr; int ldc = 0; int out_fp32 = 0;
+    const float* scale = nullptr;      // [N] or null (=1)
+    const float* shift = nullptr;      // [N] or null (=0)
+    const float* rowbias = nullptr;    // [M / rows_per_image][N] or null
+    int rows_per_image = 1;
+    const __nv_bfloat16* residual = nullptr; int ldr = 0;
+    int act = 0;                       // 0 none, 1 relu, 2 relu6
+};
+
+// A prepared launch: tensor maps encoded once, reused every step (buffers are static in the plan).
+struct GemmPlan {
+    CUtensorMap tmA, tmB;
+    GemmDesc d;
+    int block_n = 0, n_tiles = 0, m_tiles = 0, k_blocks = 0, stages = 0, tmem_cols = 0;
+    size_t smem_bytes = 0;
+    int grid = 0;
+};
+int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan);
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+
+// Weight gradient  dW[Cin,Cout] = sum_m X[m,Cin] * dZ[m,Cout]   (both operands MN-major, split over m)
+struct WgradDesc {
+    const __nv_bfloat16* X = nullptr; int ldx = 0; int Cin = 0;
+    const __nv_bfloat16* dZ = nullptr; int ldz = 0; int Cout = 0;
+    long long M = 0;
+    float* dW = nullptr; int lddw = 0;          // fp32 [Cin][lddw]
+    float* workspace = nullptr; size_t workspace_floats = 0;   // split-K partials
+};
+struct WgradPlan {
+    CUtensorMap tmX, tmZ;
+    WgradDesc d;
+    int ci_tiles = 0, co_tiles = 0, block_n = 0, boxes_b = 0, splits = 0, kb_per_split = 0, k_blocks = 0, stages = 0;
+    int tmem_cols = 0;
+    size_t smem_bytes = 0;
+};
+size_t wgrad_workspace_floats(int Cin, int Cout, long long M, int num_sms);
+int wgrad_plan(const WgradDesc& d, int num_sms, WgradPlan* plan);
+int wgrad_launch(const WgradPlan& plan, cudaStream_t stream);
+
+}  // namespace ams

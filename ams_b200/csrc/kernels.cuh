@@ -1,0 +1,146 @@
+// Launch interfaces of the non-GEMM kernels (HBM-bound byte/elementwise/reduction work).
+// All tensors NHWC; activations bf16, statistics / parameters / gradients fp32, counters int64.
+#pragma once
+#include "common.cuh"
+
+namespace ams {
+
+typedef __nv_bfloat16 bf16;
+
+struct Conv2dGeom {          // one image-plane geometry; TF 'SAME' pads resolved on the host
+    int N, H, W, C;          // input
+    int Ho, Wo;              // output
+    int stride, dil;
+    int pad_top, pad_left;
+};
+
+// ---- stem: pad(127.5) + (x*2/255-1) + 3x3 s2 conv 3->32, fused (SURVEY K1+K2)
+// in: u8 or f32 [N,H,W,3] un-padded frame; the graph's 1-px bottom/right mean-pixel pad is virtual.
+// out bf16 [N,Ho,Wo,32]; scale/shift != null => y = relu6(acc*scale+shift) (frozen BN fold), else raw z.
+int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
+                  int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w /*[3,3,3,32]*/,
+                  const float* scale, const float* shift, bf16* out, cudaStream_t s);
+// dW[3,3,3,32] = sum_pixels patch(in) (x) dz ; partials [chunks][864] then fixed-order reduce.
+int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo,
+                         int pad_top, int pad_left, float pad_value, float norm_scale, float norm_shift,
+                         const bf16* dz, float* dw, float* workspace, size_t workspace_floats, cudaStream_t s);
+size_t stem_bwd_workspace_floats(int N, int Ho, int Wo);
+
+// ---- depthwise 3x3
+int dw_conv_fwd(const bf16* in, const float* w /*[3,3,C]*/, const Conv2dGeom& g, const float* scale,
+                const float* shift, int act, bf16* out, cudaStream_t s);
+int dw_conv_bwd_data(const bf16* dz, const float* w, const Conv2dGeom& g, bf16* dx, cudaStream_t s);
+int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
+                       size_t workspace_floats, cudaStream_t s);
+size_t dw_bwd_workspace_floats(const Conv2dGeom& g);
+
+// ---- BatchNorm, training mode
+struct BnLayer {            // device pointers into the parameter / state arenas, all [C] fp32
+    int C;
+    long long M;            // N*H*W reduction length
+    float eps, one_minus_decay;
+    const float* gamma; const float* beta;
+    float* moving_mean; float* moving_var;     // updated in place when update_moving != 0
+    float* mean; float* rstd;                  // saved batch statistics
+    float* scale; float* shift;                // y = z*scale + shift
+};
+size_t bn_workspace_doubles(long long M, int C);
+// batch statistics of z (bf16 [M,C]) -> scale/shift/mean/rstd (+ moving-average update)
+int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double* workspace, cudaStream_t s);
+// y = act(z*scale+shift) (+ residual)
+int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y,
+             long long M, int C, cudaStream_t s);
+// frozen fold: scale = gamma*rsqrt(mv_var+eps), shift = beta - mv_mean*scale
+int bn_fold_frozen(const float* gamma, const float* beta, const float* mv_mean, const float* mv_var, float eps,
+                   float* scale, float* shift, int C, cudaStream_t s);
+// backward: given dy (grad wrt act(BN(z))) and z; writes dz (dz_out may alias dy), d_gamma, d_beta.
+// If dy2 != null the incoming gradient is dy + dy2 (two consumers).
+int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, bf16* dz_out,
+                float* d_gamma, float* d_beta, double* workspace, cudaStream_t s);
+
+// ---- ASPP image-pooling branch folded into a per-image bias
+struct ImgPoolFwd {
+    int N, HW, Cin /*320*/, Cmid /*256*/, Cout /*256*/;
+    const bf16* feat;            // [N,HW,Cin]
+    const float* w_pool;         // [Cin][Cmid]
+    const float* w_proj_top;     // concat_projection rows 0..Cmid-1: [Cmid][Cout]
+    BnLayer bn;                  // image_pooling BN (M = N)
+    int frozen, update_moving;
+    float* pooled;               // [N][Cin]   saved
+    float* z;                    // [N][Cmid]  saved (pre-BN)
+    float* act;                  // [N][Cmid]  saved (post relu)
+    float* bias_img;             // [N][Cout]  -> rowbias of concat_projection
+};
+int imgpool_forward(const ImgPoolFwd& a, cudaStream_t s);
+struct ImgPoolBwd {
+    ImgPoolFwd f;
+    const bf16* dz_proj;         // [N,HW,Cout] gradient wrt concat_projection pre-BN output
+    float* dbias;                // [N][Cout] scratch
+    float* d_w_proj_top;         // [Cmid][Cout]
+    float* d_w_pool;             // [Cin][Cmid]
+    float* d_gamma; float* d_beta;
+    float* dfeat_rowbias;        // [N][Cin]  = d pooled / HW  -> rowbias of the aspp0 dgrad GEMM
+};
+int imgpool_backward(const ImgPoolBwd& a, cudaStream_t s);
+
+// ---- head: bilinear upsample (align_corners) fused with argmax / confusion matrix / softmax-CE
+constexpr int kMaxClasses = 32;
+struct HeadGeom {
+    int N, h, w, ldl;            // low-res logits fp32 [N,h,w,ldl]
+    int H, W;                    // output size
+    int class_count;             // selected classes
+    int cls_idx[kMaxClasses];    // logits channel of reduced class j
+    int label_lut[256];          // teacher label id -> reduced class, -1 = ignored pixel
+    int normalize;               // training head: 1 = gradient of the MEAN loss (divide by n_valid), 0 = of the SUM
+};
+struct HeadStats {               // device, zeroed by head_reset()
+    long long confmat[kMaxClasses * kMaxClasses];
+    double loss_sum;
+    long long n_valid;
+};
+int head_reset(HeadStats* st, cudaStream_t s);
+// pred int32 [N,H,W] (may be null); labels u8 [N,H,W] or null; st accumulates confmat / loss / n_valid
+int head_infer(const float* logits, const HeadGeom& g, const uint8_t* labels, int32_t* pred, HeadStats* st,
+               cudaStream_t s);
+// label-vs-label confusion matrix (calc_cross_miou): weight = both valid
+int head_label_confmat(const uint8_t* before, const uint8_t* after, long long n, const HeadGeom& g, HeadStats* st,
+                       cudaStream_t s);
+// training: loss + d loss / d low-res logits, never materialising full-res logits.
+// dlogits_f32 [N,h,w,ldl] fp32 (bias grad source), dlogits_bf16 [N*h*w, 32] bf16 (GEMM operand);
+// rowbuf: [N,H,w,class_count] fp32 scratch.
+size_t head_rowbuf_floats(const HeadGeom& g);
+int head_loss_backward(const float* logits, const HeadGeom& g, const uint8_t* labels, float* rowbuf,
+                       float* dlogits_f32, bf16* dlogits_bf16, HeadStats* st, float* loss_out /*device*/,
+                       cudaStream_t s);
+
+// ---- generic reductions
+// colsum[g][c] = sum over rows of group g (rows_per_group consecutive rows) of x[row][c]   (deterministic)
+int colsum_groups(const float* x_f32, const bf16* x_bf16, int ld, long long rows_per_group, int groups, int C,
+                  float* out, cudaStream_t s);
+
+// ---- optimizer / selection / delta
+int adam_masked(float* p, const float* g, float grad_scale, float* m, float* v, const uint8_t* mask, long long n,
+                float alpha, float one_minus_b1, float one_minus_b2, float eps, cudaStream_t s);
+struct SelectScratch {           // device
+    unsigned int hist[256];
+    unsigned int prefix, rank, v_lo, count_le, next_gt, pad;
+    float threshold;
+    unsigned long long kept;
+};
+// mask[i] = |after-before| > thr  with thr = float32(a[lo]*(1-w_hi) + a[lo+1]*w_hi) over the n deltas
+// (NumPy-1.19 percentile + value-based float32 demotion, see oracle/student_oracle.py);
+// unselected coordinates are reverted: after[i] = before[i].
+int select_coordinates(float* after, const float* before, float* delta_scratch, uint8_t* mask, long long n,
+                       long long lo, double w_hi, SelectScratch* sc, cudaStream_t s);
+struct VarSeg { long long offset; long long size; long long bit_byte_offset; };
+// packbits per variable (MSB first) then fp16 values of masked coordinates in order
+int pack_delta(const float* params, const uint8_t* mask, const VarSeg* segs_dev, int nseg, long long n,
+               long long mask_bytes, uint8_t* out_bits, __half* out_vals, unsigned int* block_counts,
+               int nblocks_alloc, unsigned long long* kept_out, cudaStream_t s);
+int pack_delta_blocks(long long n);
+
+// fp32 HWIO 1x1 weights -> bf16 [Cout][Cin] (forward B operand) and bf16 [Cin][ldb] (dgrad B operand)
+struct WeightCast { const float* w; bf16* w_fwd; bf16* w_bwd; int Cin, Cout, ld_fwd, ld_bwd; int row0, rows; };
+int cast_weights(const WeightCast* table_dev, int n_layers, int max_elems, cudaStream_t s);
+
+}  // namespace ams

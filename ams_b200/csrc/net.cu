@@ -1,0 +1,444 @@
+// Topology, memory plan and the forward / backward schedules of the AMS student network.
+// Replaces the TF1 graph executor behind tf.Session.run for the subgraph features -> student_logits of
+// checkpoints/*/model.meta plus the head/loss/optimizer nodes added by utils/graph_utils.py:338-533.
+#include "net.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace ams {
+
+namespace {
+
+struct BlockSpec { int t, c, s, d; };
+// MobileNetV2 (depth multiplier 1, output stride 16: stride of block 13 turned into dilation 2 for blocks 14-16),
+// as decoded from the shipped model.meta.
+const BlockSpec kBlocks[17] = {
+    {1, 16, 1, 1},  {6, 24, 2, 1},  {6, 24, 1, 1},  {6, 32, 2, 1},  {6, 32, 1, 1},  {6, 32, 1, 1},
+    {6, 64, 2, 1},  {6, 64, 1, 1},  {6, 64, 1, 1},  {6, 64, 1, 1},  {6, 96, 1, 1},  {6, 96, 1, 1},
+    {6, 96, 1, 1},  {6, 160, 1, 1}, {6, 160, 1, 2}, {6, 160, 1, 2}, {6, 320, 1, 2}};
+
+void same_pad(int in, int k, int s, int d, int* out, int* pad_before) {
+    *out = (in + s - 1) / s;
+    const int total = std::max((*out - 1) * s + (k - 1) * d + 1 - in, 0);
+    *pad_before = total / 2;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t count, std::vector<void*>* track = nullptr) {
+    void* q = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    *p = static_cast<T*>(q);
+    if (track) track->push_back(q);
+    return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- topology
+int net_build_topology(Net* net) {
+    const ams_config& c = net->cfg;
+    AMS_REQUIRE(c.num_classes > 0 && c.num_classes <= 21, "num_classes must be in [1,21]");
+    const float eps_backbone = 0.001f, eps_aspp = 1.001e-05f;
+    const float k_default = 1.0f - 0.9f;                     // graph computes 1 - decay in fp32
+    const float k_dw = c.graph_variant == 1 ? (1.0f - 0.98f) : k_default;   // VOC graph: depthwise BN decay 0.98
+    auto& L = net->layers;
+    L.clear();
+    net->vars.clear();
+    long long t_off = 0, m_off = 0, bn_off = 0, w16_off = 0;
+
+    auto add_var = [&](const std::string& name, std::initializer_list<int> shape, bool trainable) -> long long {
+        VarInfo v;
+        v.name = name;
+        v.ndim = static_cast<int>(shape.size());
+        long long cnt = 1;
+        int i = 0;
+        for (int s : shape) { v.shape[i++] = s; cnt *= s; }
+        v.count = cnt;
+        v.trainable = trainable;
+        long long& off = trainable ? t_off : m_off;
+        v.offset = off;
+        off += cnt;
+        net->var_index[name] = static_cast<int>(net->vars.size());
+        if (trainable) net->trainable_order.push_back(static_cast<int>(net->vars.size()));
+        net->vars.push_back(v);
+        return v.offset;
+    };
+    auto add_layer = [&](const std::string& name, int kind, int cin, int cout, int stride, int dil, int act, bool bn,
+                         float eps, float k, int input, int residual) -> int {
+        LayerDef d;
+        d.name = name; d.kind = kind; d.cin = cin; d.cout = cout; d.stride = stride; d.dil = dil; d.act = act;
+        d.has_bn = bn; d.eps = eps; d.one_minus_decay = k; d.input = input; d.residual = residual;
+        const std::string wname = (kind == kDepthwise) ? name + "/depthwise_weights:0" : name + "/weights:0";
+        if (kind == kStem) d.w_off = add_var(wname, {3, 3, cin, cout}, true);
+        else if (kind == kDepthwise) d.w_off = add_var(wname, {3, 3, cin, 1}, true);
+        else d.w_off = add_var(wname, {1, 1, cin, cout}, true);
+        if (bn) {
+            d.gamma_off = add_var(name + "/BatchNorm/gamma:0", {cout}, true);
+            d.beta_off = add_var(name + "/BatchNorm/beta:0", {cout}, true);
+            d.mm_off = add_var(name + "/BatchNorm/moving_mean:0", {cout}, false);
+            d.mv_off = add_var(name + "/BatchNorm/moving_variance:0", {cout}, false);
+            d.bn_off = bn_off;
+            bn_off += 6LL * cout;
+        } else {
+            d.bias_off = add_var(name + "/biases:0", {cout}, true);
+        }
+        L.push_back(d);
+        return static_cast<int>(L.size()) - 1;
+    };
+
+    int prev = add_layer("MobilenetV2/Conv", kStem, 3, 32, 2, 1, 2, true, eps_backbone, k_default, -1, -1);
+    int cin = 32;
+    for (int b = 0; b < 17; ++b) {
+        const BlockSpec& bs = kBlocks[b];
+        const std::string base = "MobilenetV2/expanded_conv" + (b == 0 ? std::string("") : "_" + std::to_string(b));
+        const int block_in = prev;
+        int cur = prev, cexp = cin * bs.t;
+        if (bs.t != 1) cur = add_layer(base + "/expand", kConv1x1, cin, cexp, 1, 1, 2, true, eps_backbone, k_default, cur, -1);
+        // graph: depthwise node is ".../depthwise/depthwise", variable scope ".../depthwise"
+        cur = add_layer(base + "/depthwise", kDepthwise, cexp, cexp, bs.s, bs.d, 2, true, eps_backbone, k_dw, cur, -1);
+        const bool res = (bs.s == 1 && cin == bs.c);
+        cur = add_layer(base + "/project", kConv1x1, cexp, bs.c, 1, 1, 0, true, eps_backbone, k_default, cur, res ? block_in : -1);
+        prev = cur;
+        cin = bs.c;
+    }
+    const int feat = prev;
+    const int ip = add_layer("image_pooling", kImagePool, 320, 256, 1, 1, 1, true, eps_aspp, k_default, feat, -1);
+    const int aspp = add_layer("aspp0", kConv1x1, 320, 256, 1, 1, 1, true, eps_aspp, k_default, feat, -1);
+    const int cp = add_layer("concat_projection", kConv1x1, 512, 256, 1, 1, 1, true, eps_aspp, k_default, aspp, -1);
+    add_layer("logits/semantic", kLogits, 256, c.num_classes, 1, 1, 0, false, 0.f, 0.f, cp, -1);
+    (void)ip;
+    net->n_train = t_off;
+    net->n_moving = m_off;
+    net->n_bnpool = bn_off;
+
+    // geometry + bf16 weight copies
+    const int Hp = c.height + 1, Wp = c.width + 1;            // graph pads 1 px bottom/right with the mean pixel
+    for (size_t i = 0; i < L.size(); ++i) {
+        LayerDef& d = L[i];
+        if (d.kind == kStem) { d.in_h = Hp; d.in_w = Wp; }
+        else if (d.kind == kImagePool) { d.in_h = 1; d.in_w = 1; }
+        else { d.in_h = L[d.input].out_h; d.in_w = L[d.input].out_w; }
+        if (d.kind == kStem || d.kind == kDepthwise) {
+            same_pad(d.in_h, 3, d.stride, d.dil, &d.out_h, &d.pad_top);
+            same_pad(d.in_w, 3, d.stride, d.dil, &d.out_w, &d.pad_left);
+        } else { d.out_h = d.in_h; d.out_w = d.in_w; }
+        if (d.kind == kConv1x1 || d.kind == kLogits) {
+            d.k_rows0 = (d.name == "concat_projection") ? 256 : 0;
+            d.k_rows = d.cin - d.k_rows0;
+            d.ld_fwd = d.k_rows;                                   // [cout][k_rows]
+            d.ld_bwd = (d.kind == kLogits) ? 32 : d.cout;          // [k_rows][cout] (logits: K padded to 32)
+            d.wfwd_off = w16_off; w16_off += static_cast<long long>(d.cout) * d.ld_fwd;
+            w16_off = (w16_off + 63) & ~63LL;
+            d.wbwd_off = w16_off; w16_off += static_cast<long long>(d.k_rows) * d.ld_bwd;
+            w16_off = (w16_off + 63) & ~63LL;
+        }
+    }
+    net->n_bf16 = w16_off;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- plan
+static BnLayer bn_layer(Net* net, const LayerDef& d, long long M) {
+    BnLayer b;
+    b.C = d.cout; b.M = M; b.eps = d.eps; b.one_minus_decay = d.one_minus_decay;
+    b.gamma = net->params + d.gamma_off; b.beta = net->params + d.beta_off;
+    b.moving_mean = net->moving + d.mm_off; b.moving_var = net->moving + d.mv_off;
+    float* pool = net->bnpool + d.bn_off;
+    b.scale = pool; b.shift = pool + d.cout; b.mean = pool + 2 * d.cout; b.rstd = pool + 3 * d.cout;
+    return b;
+}
+static float* fscale(Net* net, const LayerDef& d) { return net->bnpool + d.bn_off + 4 * d.cout; }
+static float* fshift(Net* net, const LayerDef& d) { return net->bnpool + d.bn_off + 5 * d.cout; }
+
+static int build_plan(Net* net, Plan* p, bool need_backward);
+
+Plan* net_get_plan(Net* net, int N, bool need_backward) {
+    auto it = net->plans.find(N);
+    if (it == net->plans.end()) {
+        std::unique_ptr<Plan> p(new Plan());
+        p->N = N;
+        if (build_plan(net, p.get(), need_backward)) return nullptr;
+        it = net->plans.emplace(N, std::move(p)).first;
+    } else if (need_backward && !it->second->have_backward) {
+        if (build_plan(net, it->second.get(), true)) return nullptr;
+    }
+    return it->second.get();
+}
+
+static int build_plan(Net* net, Plan* p, bool need_backward) {
+    const auto& L = net->layers;
+    const int N = p->N;
+    const ams_config& c = net->cfg;
+    const bool first = p->buf.empty();
+    if (first) {
+        p->buf.resize(L.size());
+        p->fwd_frozen.resize(L.size()); p->fwd_train.resize(L.size()); p->dgrad.resize(L.size()); p->wgrad.resize(L.size());
+        p->has_fwd.assign(L.size(), 0); p->has_dgrad.assign(L.size(), 0); p->has_wgrad.assign(L.size(), 0);
+        if (dev_alloc(reinterpret_cast<float**>(&p->in_frames), static_cast<size_t>(N) * c.height * c.width * 3, &p->allocations)) return -1;
+        if (dev_alloc(&p->in_labels, static_cast<size_t>(N) * c.height * c.width, &p->allocations)) return -1;
+        if (dev_alloc(&p->pred, static_cast<size_t>(N) * c.height * c.width, &p->allocations)) return -1;
+        if (dev_alloc(&p->loss_dev, 4, &p->allocations)) return -1;
+        size_t bn_ws = 0;
+        for (size_t i = 0; i < L.size(); ++i) {
+            const LayerDef& d = L[i];
+            if (d.kind == kImagePool) continue;
+            const long long M = static_cast<long long>(N) * d.out_h * d.out_w;
+            if (d.kind == kLogits) {
+                if (dev_alloc(&p->logits, static_cast<size_t>(M) * 32, &p->allocations)) return -1;
+                AMS_CUDA_CHECK(cudaMemset(p->logits, 0, static_cast<size_t>(M) * 32 * sizeof(float)));
+                continue;
+            }
+            if (dev_alloc(&p->buf[i].y, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
+            if (dev_alloc(&p->buf[i].z, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
+            bn_ws = std::max(bn_ws, bn_workspace_doubles(M, d.cout));
+        }
+        if (dev_alloc(&p->bn_ws, bn_ws, &p->allocations)) return -1;
+        const LayerDef& ipd = L[L.size() - 4];
+        if (dev_alloc(&p->pooled, static_cast<size_t>(N) * ipd.cin, &p->allocations)) return -1;
+        if (dev_alloc(&p->ip_z, static_cast<size_t>(N) * ipd.cout, &p->allocations)) return -1;
+        if (dev_alloc(&p->ip_act, static_cast<size_t>(N) * ipd.cout, &p->allocations)) return -1;
+        if (dev_alloc(&p->bias_img, static_cast<size_t>(N) * 256, &p->allocations)) return -1;
+        if (dev_alloc(&p->ip_dbias, static_cast<size_t>(N) * (256 + ipd.cout), &p->allocations)) return -1;
+        if (dev_alloc(&p->dfeat_rowbias, static_cast<size_t>(N) * ipd.cin, &p->allocations)) return -1;
+        // forward GEMM plans
+        for (size_t i = 0; i < L.size(); ++i) {
+            const LayerDef& d = L[i];
+            if (d.kind != kConv1x1 && d.kind != kLogits) continue;
+            const long long M = static_cast<long long>(N) * d.out_h * d.out_w;
+            GemmDesc g;
+            g.A = p->buf[d.input].y; g.lda = L[d.input].cout;
+            g.B = net->wpool + d.wfwd_off; g.ldb = d.ld_fwd;
+            g.M = static_cast<int>(M); g.N = d.cout; g.K = d.k_rows;
+            if (d.name == "concat_projection") { g.rowbias = p->bias_img; g.rows_per_image = d.out_h * d.out_w; }
+            if (d.kind == kLogits) {
+                g.out = p->logits; g.ldc = 32; g.out_fp32 = 1; g.shift = net->params + d.bias_off;
+                if (gemm_plan(g, net->num_sms, &p->fwd_frozen[i])) return -1;
+                p->fwd_train[i] = p->fwd_frozen[i];
+            } else {
+                GemmDesc f = g;
+                f.out = p->buf[i].y; f.ldc = d.cout; f.scale = fscale(net, d); f.shift = fshift(net, d); f.act = d.act;
+                if (d.residual >= 0) { f.residual = p->buf[d.residual].y; f.ldr = d.cout; }
+                if (gemm_plan(f, net->num_sms, &p->fwd_frozen[i])) return -1;
+                GemmDesc t = g;
+                t.out = p->buf[i].z; t.ldc = d.cout;
+                if (gemm_plan(t, net->num_sms, &p->fwd_train[i])) return -1;
+            }
+            p->has_fwd[i] = 1;
+        }
+    }
+    if (need_backward && !p->have_backward) {
+        size_t red_ws = 0;
+        const LayerDef& lg = L.back();
+        const long long M16 = static_cast<long long>(N) * lg.out_h * lg.out_w;
+        if (dev_alloc(&p->dlogits_f32, static_cast<size_t>(M16) * 32, &p->allocations)) return -1;
+        if (dev_alloc(&p->dlogits_bf16, static_cast<size_t>(M16) * 32, &p->allocations)) return -1;
+        HeadGeom hg = net->head; hg.N = N;
+        if (dev_alloc(&p->rowbuf, head_rowbuf_floats(hg), &p->allocations)) return -1;
+        for (size_t i = 0; i < L.size(); ++i) {
+            const LayerDef& d = L[i];
+            if (d.kind == kImagePool || d.kind == kLogits) continue;
+            const long long M = static_cast<long long>(N) * d.out_h * d.out_w;
+            if (dev_alloc(&p->buf[i].g, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
+            if (d.residual >= 0) { if (dev_alloc(&p->buf[i].gz, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1; }
+            else p->buf[i].gz = p->buf[i].g;
+            if (d.kind == kDepthwise) {
+                Conv2dGeom g{N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+                red_ws = std::max(red_ws, dw_bwd_workspace_floats(g));
+            }
+            if (d.kind == kStem) red_ws = std::max(red_ws, stem_bwd_workspace_floats(N, d.out_h, d.out_w));
+            if (d.kind == kConv1x1) red_ws = std::max(red_ws, wgrad_workspace_floats(d.k_rows, d.cout, M, net->num_sms));
+        }
+        red_ws = std::max(red_ws, wgrad_workspace_floats(lg.cin, lg.cout, M16, net->num_sms));
+        if (dev_alloc(&p->red_ws, red_ws, &p->allocations)) return -1;
+        p->red_ws_floats = red_ws;
+        for (size_t i = 0; i < L.size(); ++i) {
+            const LayerDef& d = L[i];
+            if (d.kind != kConv1x1 && d.kind != kLogits) continue;
+            const long long M = static_cast<long long>(N) * d.out_h * d.out_w;
+            // weight gradient: dW[k_rows][cout] = A^T * dz
+            WgradDesc w;
+            w.X = p->buf[d.input].y; w.ldx = L[d.input].cout; w.Cin = d.k_rows;
+            if (d.kind == kLogits) { w.dZ = p->dlogits_bf16; w.ldz = 32; }
+            else { w.dZ = p->buf[i].gz; w.ldz = d.cout; }
+            w.Cout = d.cout; w.M = M;
+            w.dW = net->grads + d.w_off + static_cast<long long>(d.k_rows0) * d.cout; w.lddw = d.cout;
+            w.workspace = p->red_ws; w.workspace_floats = p->red_ws_floats;
+            if (wgrad_plan(w, net->num_sms, &p->wgrad[i])) return -1;
+            p->has_wgrad[i] = 1;
+            // data gradient: g[input] = dz * W^T (+ skip gradient / image-pool gradient)
+            GemmDesc g;
+            if (d.kind == kLogits) { g.A = p->dlogits_bf16; g.lda = 32; g.K = 32; }
+            else { g.A = p->buf[i].gz; g.lda = d.cout; g.K = d.cout; }
+            g.B = net->wpool + d.wbwd_off; g.ldb = d.ld_bwd;
+            g.M = static_cast<int>(M); g.N = d.k_rows;
+            g.out = p->buf[d.input].g; g.ldc = L[d.input].cout;
+            // expand conv of a residual block: the block input also receives the block output's gradient
+            if (i + 2 < L.size() && L[i + 2].kind == kConv1x1 && L[i + 2].residual == d.input && L[i + 1].kind == kDepthwise) {
+                g.residual = p->buf[i + 2].g; g.ldr = L[i + 2].cout;
+            }
+            if (d.name == "aspp0") { g.rowbias = p->dfeat_rowbias; g.rows_per_image = d.out_h * d.out_w; }
+            if (gemm_plan(g, net->num_sms, &p->dgrad[i])) return -1;
+            p->has_dgrad[i] = 1;
+        }
+        p->have_backward = true;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- weights
+int net_prepare_weights(Net* net, bool frozen) {
+    if (net->weights_dirty) {
+        if (cast_weights(net->cast_table, net->cast_layers, net->cast_max, net->stream)) return -1;
+        net->weights_dirty = false;
+    }
+    if (frozen && net->fold_dirty) {
+        for (const LayerDef& d : net->layers) {
+            if (!d.has_bn || d.kind == kImagePool) continue;
+            if (bn_fold_frozen(net->params + d.gamma_off, net->params + d.beta_off, net->moving + d.mm_off,
+                               net->moving + d.mv_off, d.eps, fscale(net, d), fshift(net, d), d.cout, net->stream)) return -1;
+        }
+        net->fold_dirty = false;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- forward
+static ImgPoolFwd imgpool_desc(Net* net, Plan* p, bool frozen, bool update_moving) {
+    const auto& L = net->layers;
+    const LayerDef& d = L[L.size() - 4];
+    const LayerDef& cp = L[L.size() - 2];
+    ImgPoolFwd a;
+    a.N = p->N; a.HW = L[d.input].out_h * L[d.input].out_w; a.Cin = d.cin; a.Cmid = d.cout; a.Cout = cp.cout;
+    a.feat = p->buf[d.input].y;
+    a.w_pool = net->params + d.w_off;
+    a.w_proj_top = net->params + cp.w_off;
+    a.bn = bn_layer(net, d, p->N);
+    a.frozen = frozen; a.update_moving = update_moving;
+    a.pooled = p->pooled; a.z = p->ip_z; a.act = p->ip_act; a.bias_img = p->bias_img;
+    return a;
+}
+
+int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
+    const auto& L = net->layers;
+    const ams_config& c = net->cfg;
+    const bool frozen = (bn_mode == AMS_BN_MOVING);
+    cudaStream_t s = net->stream;
+    if (net_prepare_weights(net, frozen)) return -1;
+    for (size_t i = 0; i < L.size(); ++i) {
+        const LayerDef& d = L[i];
+        const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
+        LayerBuf& b = p->buf[i];
+        if (d.kind == kImagePool) {
+            if (imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s)) return -1;
+            continue;
+        }
+        if (d.kind == kLogits) {
+            if (gemm_launch(p->fwd_frozen[i], s)) return -1;
+            continue;
+        }
+        bf16* conv_out = frozen ? b.y : b.z;
+        const float* sc = frozen ? fscale(net, d) : nullptr;
+        const float* sh = frozen ? fshift(net, d) : nullptr;
+        if (d.kind == kStem) {
+            if (stem_conv_fwd(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w, d.out_h,
+                              d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, net->params + d.w_off,
+                              sc, sh, conv_out, s)) return -1;
+        } else if (d.kind == kDepthwise) {
+            Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+            if (dw_conv_fwd(p->buf[d.input].y, net->params + d.w_off, g, sc, sh, d.act, conv_out, s)) return -1;
+        } else {
+            if (gemm_launch(frozen ? p->fwd_frozen[i] : p->fwd_train[i], s)) return -1;
+        }
+        if (!frozen) {
+            BnLayer bl = bn_layer(net, d, M);
+            if (bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s)) return -1;
+            if (bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s)) return -1;
+        }
+    }
+    p->last_was_train = !frozen;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+int net_backward(Net* net, Plan* p, bool normalize) {
+    const auto& L = net->layers;
+    const ams_config& c = net->cfg;
+    cudaStream_t s = net->stream;
+    const int nl = static_cast<int>(L.size());
+    // head: loss + d low-res logits
+    HeadGeom hg = net->head; hg.N = p->N; hg.normalize = normalize ? 1 : 0;
+    if (head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s)) return -1;
+    const LayerDef& lg = L[nl - 1];
+    const long long M16 = static_cast<long long>(p->N) * lg.out_h * lg.out_w;
+    if (colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, net->grads + lg.bias_off, s)) return -1;
+    if (wgrad_launch(p->wgrad[nl - 1], s)) return -1;
+    if (gemm_launch(p->dgrad[nl - 1], s)) return -1;
+    for (int i = nl - 2; i >= 0; --i) {
+        const LayerDef& d = L[i];
+        if (d.kind == kImagePool) continue;          // handled together with concat_projection
+        const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
+        LayerBuf& b = p->buf[i];
+        BnLayer bl = bn_layer(net, d, M);
+        if (bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s)) return -1;
+        if (d.kind == kConv1x1) {
+            if (wgrad_launch(p->wgrad[i], s)) return -1;
+            if (d.name == "concat_projection") {
+                const LayerDef& ipd = L[nl - 4];
+                ImgPoolBwd ib;
+                ib.f = imgpool_desc(net, p, false, false);
+                ib.dz_proj = b.gz;
+                ib.dbias = p->ip_dbias;
+                ib.d_w_proj_top = net->grads + d.w_off;
+                ib.d_w_pool = net->grads + ipd.w_off;
+                ib.d_gamma = net->grads + ipd.gamma_off; ib.d_beta = net->grads + ipd.beta_off;
+                ib.dfeat_rowbias = p->dfeat_rowbias;
+                if (imgpool_backward(ib, s)) return -1;
+            }
+            if (gemm_launch(p->dgrad[i], s)) return -1;
+        } else if (d.kind == kDepthwise) {
+            Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+            if (dw_conv_bwd_filter(p->buf[d.input].y, b.gz, g, net->grads + d.w_off, p->red_ws, p->red_ws_floats, s)) return -1;
+            if (dw_conv_bwd_data(b.gz, net->params + d.w_off, g, p->buf[d.input].g, s)) return -1;
+        } else if (d.kind == kStem) {
+            if (stem_conv_bwd_filter(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w,
+                                     d.out_h, d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, b.gz,
+                                     net->grads + d.w_off, p->red_ws, p->red_ws_floats, s)) return -1;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- queue
+int net_dequeue(Net* net, Plan** plan_out, bool need_backward) {
+    int slot = -1;
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        AMS_REQUIRE(!net->filled.empty(), "input queue is empty: call ams_enqueue first");
+        slot = net->filled.front();
+        net->filled.pop_front();
+    }
+    QueueSlot& q = net->slots[slot];
+    Plan* p = net_get_plan(net, q.n, need_backward);
+    if (!p) return -1;
+    const size_t px = static_cast<size_t>(q.n) * net->cfg.height * net->cfg.width;
+    const size_t fbytes = px * 3 * (q.dtype == AMS_FRAMES_U8 ? 1 : 4);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(p->in_frames, q.frames, fbytes, cudaMemcpyDeviceToDevice, net->stream));
+    if (q.has_labels) AMS_CUDA_CHECK(cudaMemcpyAsync(p->in_labels, q.labels, px, cudaMemcpyDeviceToDevice, net->stream));
+    else AMS_CUDA_CHECK(cudaMemsetAsync(p->in_labels, 255, px, net->stream));
+    p->in_dtype = q.dtype;
+    p->in_has_labels = q.has_labels;
+    AMS_CUDA_CHECK(cudaEventRecord(q.consumed, net->stream));
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        q.consumed_pending = true;
+        net->free_slots.push_back(slot);
+    }
+    net->qcv.notify_all();
+    net->last_n = q.n;
+    *plan_out = p;
+    return 0;
+}
+
+}  // namespace ams

@@ -1,0 +1,113 @@
+// The network handle behind the C ABI: topology (restated from the shipped model.meta, checked against
+// ams_b200/graphs/*.json by tests/test_layout.py), flat parameter arenas, per-batch-size execution plans.
+#pragma once
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ams_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace ams {
+
+enum LayerKind { kStem = 0, kConv1x1 = 1, kDepthwise = 2, kImagePool = 3, kLogits = 4 };
+
+struct VarInfo {
+    std::string name;
+    int shape[4] = {0, 0, 0, 0};
+    int ndim = 0;
+    bool trainable = false;
+    long long offset = 0;      // floats into the trainable arena (trainable) or the moving arena
+    long long count = 0;
+};
+
+struct LayerDef {
+    std::string name;
+    int kind = 0;
+    int cin = 0, cout = 0, stride = 1, dil = 1, act = 0;
+    bool has_bn = true;
+    float eps = 0.f, one_minus_decay = 0.f;
+    int input = -1;            // producer layer (-1 = frame)
+    int residual = -1;         // layer whose output is added after BN (-1 = none)
+    // parameter offsets (floats): trainable arena / moving arena
+    long long w_off = -1, gamma_off = -1, beta_off = -1, bias_off = -1, mm_off = -1, mv_off = -1;
+    long long bn_off = -1;     // offset into the per-layer BN vector pool (units of floats, 6 vectors of cout)
+    // bf16 weight copies (elements into the bf16 pool), 1x1 layers only
+    long long wfwd_off = -1, wbwd_off = -1;
+    int ld_fwd = 0, ld_bwd = 0, k_rows0 = 0, k_rows = 0;   // HWIO row window used by the GEMM (concat_projection: 256..511)
+    // geometry at the configured frame size (per image)
+    int in_h = 0, in_w = 0, out_h = 0, out_w = 0, pad_top = 0, pad_left = 0;
+};
+
+struct LayerBuf { bf16* z = nullptr; bf16* y = nullptr; bf16* g = nullptr; bf16* gz = nullptr; };
+
+struct Plan {
+    int N = 0;
+    std::vector<LayerBuf> buf;
+    std::vector<void*> allocations;
+    void* in_frames = nullptr; uint8_t* in_labels = nullptr; int in_dtype = 0; bool in_has_labels = false;
+    float* logits = nullptr;          // [N*h*w][32] fp32
+    float* dlogits_f32 = nullptr; bf16* dlogits_bf16 = nullptr; float* rowbuf = nullptr;
+    int32_t* pred = nullptr;
+    float* loss_dev = nullptr;
+    // image pooling scratch
+    float *pooled = nullptr, *ip_z = nullptr, *ip_act = nullptr, *bias_img = nullptr, *ip_dbias = nullptr, *dfeat_rowbias = nullptr;
+    double* bn_ws = nullptr;
+    float* red_ws = nullptr; size_t red_ws_floats = 0;
+    std::vector<GemmPlan> fwd_frozen, fwd_train, dgrad;
+    std::vector<WgradPlan> wgrad;
+    std::vector<char> has_fwd, has_dgrad, has_wgrad;
+    bool have_backward = false;
+    bool last_was_train = false;
+};
+
+struct QueueSlot {
+    void* frames = nullptr; size_t frames_cap = 0;
+    uint8_t* labels = nullptr; size_t labels_cap = 0;
+    int n = 0, dtype = 0; bool has_labels = false;
+    cudaEvent_t consumed = nullptr; bool consumed_pending = false;
+};
+
+struct Net {
+    ams_config cfg{};
+    int num_sms = kNumSMs;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    std::vector<VarInfo> vars;
+    std::unordered_map<std::string, int> var_index;
+    std::vector<int> trainable_order;       // indices into vars, tf.trainable_variables() order
+    std::vector<LayerDef> layers;
+    long long n_train = 0, n_moving = 0, n_bnpool = 0, n_bf16 = 0;
+    float *params = nullptr, *moving = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr, *before = nullptr;
+    float* delta_scratch = nullptr;
+    uint8_t* mask = nullptr; bool mask_all_ones = true;
+    float beta1_power = 0.9f, beta2_power = 0.999f;
+    float* bnpool = nullptr;                // per layer: scale, shift, mean, rstd (training) + fscale, fshift (frozen)
+    bf16* wpool = nullptr;
+    WeightCast* cast_table = nullptr; int cast_layers = 0, cast_max = 0;
+    VarSeg* segs_dev = nullptr; long long mask_bytes = 0;
+    SelectScratch* select_sc = nullptr;
+    HeadStats* head_st = nullptr;
+    uint8_t* pack_bits = nullptr; __half* pack_vals = nullptr; unsigned int* pack_counts = nullptr; unsigned long long* pack_kept = nullptr;
+    bool weights_dirty = true, fold_dirty = true;
+    HeadGeom head{};
+    std::map<int, std::unique_ptr<Plan>> plans;
+    // input queue
+    std::mutex qmu; std::condition_variable qcv;
+    std::vector<QueueSlot> slots; std::deque<int> filled; std::deque<int> free_slots;
+    int last_n = 0;
+};
+
+int net_build_topology(Net* net);
+Plan* net_get_plan(Net* net, int N, bool need_backward);
+int net_prepare_weights(Net* net, bool frozen);
+int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving);
+int net_backward(Net* net, Plan* p, bool normalize);
+int net_dequeue(Net* net, Plan** plan_out, bool need_backward);
+
+}  // namespace ams

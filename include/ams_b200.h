@@ -1,0 +1,153 @@
+/* libams_b200 -- C ABI of the B200-native AMS student hot path.
+ *
+ * The reference (modelstreaming/ams) has no FFI: its boundary is `tf.Session.run` underneath the Python
+ * class `SemanticNetwork`.  Each entry point below replaces one *role* of sess.run on that path; the
+ * citation after each prototype is the reference call site (file:line in /root/reference) it stands in
+ * for.  Plain pointers and sizes only; all `host` pointers are caller-owned host memory, device memory is
+ * owned by the handle.  Every function returning int returns 0 on success; on failure a message is
+ * available from ams_last_error() (thread-local).
+ *
+ * Threading: ams_enqueue() may be called from another thread concurrently with ams_train_step() /
+ * ams_infer*() (reference: `_fill_queue` thread vs trainer thread, SemanticNetwork.py:230-231, :701 vs :260);
+ * every other entry point assumes the caller serialises (reference `process_lock`, SemanticNetwork.py:70).
+ */
+#ifndef AMS_B200_H_
+#define AMS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ams_net ams_net;
+
+#define AMS_MAX_CLASSES 32
+#define AMS_BN_MOVING 0  /* frozen client graph: inference-mode BN on moving statistics */
+#define AMS_BN_BATCH 1   /* graph as shipped: FusedBatchNormV3(is_training=True), batch statistics */
+#define AMS_FRAMES_U8 0
+#define AMS_FRAMES_F32 1
+
+typedef struct ams_config {
+    int num_classes;                      /* logits channels of the graph: 19 (Cityscapes) or 21 (PASCAL VOC) */
+    int graph_variant;                    /* 0 = deeplabv3_mobilenetv2_cityscapes, 1 = ..._pascalvoc2012 (BN decay table) */
+    int height, width;                    /* frame size fed to the network (reference: width = 2*height, run.py:71) */
+    int device;                           /* CUDA ordinal (reference: gpu_id -> visible_device_list, SemanticNetwork.py:74) */
+    int class_count;                      /* number of selected classes (class_weights_exp == 1, SemanticNetwork.py:48-52) */
+    int class_indices[AMS_MAX_CLASSES];   /* their logits channels, ascending (np.where(class_weights == 1)[0]) */
+    int label_depth;                      /* one_hot depth for teacher labels: 19 (utils/graph_utils.py:15, :392) */
+    int queue_capacity;                   /* staged input batches (reference FIFOQueue capacity 200); 0 = default 4 */
+} ams_config;
+
+const char* ams_last_error(void);
+int ams_abi_version(void);
+
+/* build: import graph + add heads/loss/Adam + create session -- SemanticNetwork.py:121-150, utils/graph_utils.py:338-533 */
+ams_net* ams_create(const ams_config* cfg);
+/* sess.close() -- SemanticNetwork.py:716-717 */
+void ams_destroy(ams_net* net);
+/* run all kernels of this handle on the caller's CUDA stream (cudaStream_t); NULL = the handle's own stream */
+int ams_set_stream(ams_net* net, void* cuda_stream);
+int ams_synchronize(ams_net* net);
+
+/* ---- checkpoint variable layout: SaveHelper, utils/utils.py:10-49; names are TF variable names with ':0' */
+int ams_num_tensors(const ams_net* net);
+/* i-th variable in `tf.global_variables()` order of the shipped graph; shape4 zero-padded to 4 dims */
+int ams_tensor_info(const ams_net* net, int index, char* name, int name_capacity, int shape4[4], int* ndim,
+                    int* trainable, long long* arena_offset);
+/* restore_vars feed of one variable -- utils/utils.py:44-47; KeyError semantics: unknown name fails */
+int ams_set_tensor(ams_net* net, const char* name, const float* host, long long count);
+/* save_vars fetch of one variable -- utils/utils.py:20-28; also serves '<var>/Adam:0', '<var>/Adam_1:0',
+ * 'beta1_power:0', 'beta2_power:0' (the optimizer slots SemanticNetwork.get_vars returns) */
+int ams_get_tensor(ams_net* net, const char* name, float* host, long long count);
+/* whole trainable arena in tf.trainable_variables() order (2,113,043 floats for Cityscapes) in one copy */
+long long ams_trainable_count(const ams_net* net);
+int ams_get_trainable(ams_net* net, float* host);
+int ams_set_trainable(ams_net* net, const float* host);
+/* tf.global_variables_initializer for the Adam slots only (test hook; the reference never resets them) */
+int ams_reset_optimizer(ams_net* net);
+
+/* ---- input queue: sess.run(fill_input_buffer, feed) -- SemanticNetwork.py:176, :204, :701.
+ * frames: [n,height,width,3] u8 or f32 (values 0..255); labels: [n,height,width] u8 teacher ids (ids outside the
+ * selected classes, e.g. 255, are ignored pixels), NULL = all-ignored (predict_input enqueues zeros, :178).
+ * Copies before returning; callable concurrently with ams_train_step / ams_infer*. */
+int ams_enqueue(ams_net* net, const void* frames, int frames_dtype, const uint8_t* labels, int n);
+int ams_queue_size(ams_net* net);
+
+/* ---- inference on the oldest queued batch.
+ * sess.run(predictions) -- SemanticNetwork.py:173 (frozen), :179 (batch statistics).  out_labels int32 [n,H,W] */
+int ams_infer(ams_net* net, int bn_mode, int32_t* out_labels);
+/* reset_conf_mat + sess.run([predictions, update_op, loss]) -- SemanticNetwork.py:198-208.
+ * out_confmat int64 [class_count*class_count], rows = teacher labels, cols = predictions; out_loss may be NaN */
+int ams_infer_metric(ams_net* net, int bn_mode, int32_t* out_labels, int64_t* out_confmat, float* out_loss);
+/* reset_conf_mat + sess.run(cross_update_op) -- SemanticNetwork.py:188-189 (ASR phi-score) */
+int ams_confmat_labels(ams_net* net, const uint8_t* labels_before, const uint8_t* labels_after, long long n,
+                       int64_t* out_confmat);
+
+/* ---- distillation step on the oldest queued batch: sess.run({train_node, loss}) -- SemanticNetwork.py:260.
+ * forward (batch-stat BN) + backward + BN moving-average update + TF1 Adam on every coordinate; when masked != 0
+ * only coordinates with mask==1 are written back (backup -> minimize -> where(mask, new, backup),
+ * utils/graph_utils.py:483-493).  out_loss = pre-update loss. */
+int ams_train_step(ams_net* net, float lr, int masked, float* out_loss);
+/* feed of the 164 mask placeholders (SemanticNetwork.py:255-257) as ONE byte map in trainable-arena order;
+ * NULL = all ones */
+int ams_set_mask(ams_net* net, const uint8_t* host_mask);
+int ams_get_mask(ams_net* net, uint8_t* host_mask);
+/* `_before = save_vars(...)` of get_train_mask -- SemanticNetwork.py:304: snapshot kept on the device */
+int ams_snapshot_before(ams_net* net);
+/* coord_desc_auto selection after iteration 0 -- SemanticNetwork.py:266-288: delta = |after - before|,
+ * thr = np.percentile(delta, 100*(1-coord_frac)) (NumPy 1.19 semantics), mask = delta > thr, unselected
+ * coordinates reverted to `before`; the mask becomes the current mask. */
+int ams_select_topk(ams_net* net, double coord_frac, long long* out_kept, float* out_threshold);
+/* model delta wire format -- run.py:316-328: per variable np.packbits(mask), then per variable
+ * params[mask].astype(float16).  Returns the byte length (and fills out_buf when capacity suffices). */
+int ams_pack_delta(ams_net* net, uint8_t* out_buf, long long capacity, long long* out_len);
+
+/* ---- data-parallel hooks (no reference counterpart: the reference is single-GPU) */
+/* forward+backward only; gradients stay in the device gradient arena as sums over the LOCAL valid pixels
+ * (not divided by n_valid) so that ranks can be summed; out_n_valid / out_loss_sum are the local terms */
+int ams_train_forward_backward(ams_net* net, long long* out_n_valid, double* out_loss_sum);
+/* device pointer + length (floats) of the gradient arena, for an NCCL allreduce issued by the host plumbing */
+void* ams_gradient_arena(ams_net* net, long long* count);
+/* Adam + mask with gradients scaled by grad_scale (= 1 / global n_valid) */
+int ams_apply_optimizer(ams_net* net, float lr, int masked, float grad_scale);
+
+/* ---- parity hooks */
+int ams_get_logits(ams_net* net, float* host, long long count);       /* low-res `semantic` [n,h,w,num_classes] of the last run */
+int ams_get_gradients(ams_net* net, float* host);                     /* trainable-arena order, last train step */
+int ams_num_layers(const ams_net* net);
+int ams_layer_info(const ams_net* net, int index, char* name, int name_capacity, int* kind, int* cin, int* cout,
+                   int* stride, int* dilation, int* act, float* bn_eps, float* bn_one_minus_decay, int* residual_from);
+/* activation of conv layer `index` from the last run: which = 0 post-BN/act output, 1 raw conv output (training) */
+int ams_get_activation(ams_net* net, int index, int which, uint16_t* host_bf16, long long count);
+
+/* ---- op-level entry points on raw DEVICE pointers (kernel unit tests; see tests/test_ops_gpu.py) */
+int ams_op_conv1x1(const void* a_bf16, const void* w_bf16 /*[N][K]*/, int M, int N, int K, const float* scale,
+                   const float* shift, const float* rowbias, int rows_per_image, const void* residual_bf16, int act,
+                   void* out, int out_fp32, int ldc, void* stream);
+int ams_op_wgrad(const void* x_bf16, int cin, const void* dz_bf16, int cout, long long M, float* dw, void* stream);
+int ams_op_depthwise(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
+                     const float* scale, const float* shift, int act, void* out_bf16, void* stream);
+int ams_op_depthwise_bwd(const void* x_bf16, const void* dz_bf16, const float* w, int n, int h, int w_, int c, int stride,
+                         int dilation, void* dx_bf16, float* dw, void* stream);
+int ams_op_stem(const void* frames, int frames_dtype, int n, int h, int w_, const float* w, const float* scale,
+                const float* shift, void* out_bf16, void* stream);
+int ams_op_stem_bwd(const void* frames, int frames_dtype, int n, int h, int w_, const void* dz_bf16, float* dw, void* stream);
+int ams_op_bn_train(const void* z_bf16, long long M, int C, const float* gamma, const float* beta, float eps, int act,
+                    const void* residual_bf16, void* y_bf16, float* mean, float* rstd, void* stream);
+int ams_op_bn_backward(const void* dy_bf16, const void* z_bf16, long long M, int C, const float* gamma, const float* beta,
+                       float eps, int act, void* dz_bf16, float* dgamma, float* dbeta, void* stream);
+int ams_op_head_infer(const float* logits, int n, int h, int w_, int ldl, int H, int W, int class_count,
+                      const int* class_indices, int label_depth, const uint8_t* labels, int32_t* pred, int64_t* confmat,
+                      double* loss_sum, long long* n_valid, void* stream);
+int ams_op_head_backward(const float* logits, int n, int h, int w_, int H, int W, int class_count, const int* class_indices,
+                         int label_depth, const uint8_t* labels, float* dlogits /*[n,h,w,32]*/, float* loss, void* stream);
+int ams_op_select(float* after, const float* before, long long n, double coord_frac, uint8_t* mask, long long* kept,
+                  float* threshold, void* stream);
+int ams_op_adam(float* p, const float* g, float* m, float* v, const uint8_t* mask, long long n, float lr, float beta1_power,
+                float beta2_power, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMS_B200_H_ */
