@@ -61,6 +61,10 @@ _SIGNATURES = {
     'ams_num_layers': (_i, [_vp]),
     'ams_layer_info': (_i, [_vp, _i, C.c_char_p, _i] + [C.POINTER(_i)] * 6 + [C.POINTER(_f)] * 2 + [C.POINTER(_i)]),
     'ams_get_activation': (_i, [_vp, _i, _i, _vp, _ll]),
+    'ams_layout_num_tensors': (_i, [_i, _i]),
+    'ams_layout_tensor_info': (_i, [_i, _i, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll)]),
+    'ams_layout_num_layers': (_i, [_i, _i]),
+    'ams_layout_layer_info': (_i, [_i, _i, _i, C.c_char_p, _i] + [C.POINTER(_i)] * 6 + [C.POINTER(_f)] * 2 + [C.POINTER(_i)]),
     'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
@@ -107,3 +111,25 @@ def check(rc, what=''):
         if msg.startswith('KeyError'):
             raise KeyError(msg[len('KeyError: '):])
         raise NativeError('%s failed: %s' % (what or 'libams_b200 call', msg))
+
+
+def layout(num_classes, graph_variant):
+    """Host-only: (variables, layers) tables of the restated graph -- no device needed."""
+    L = lib()
+    name = C.create_string_buffer(256)
+    shape = (C.c_int * 4)()
+    nd, tr, off = C.c_int(), C.c_int(), C.c_longlong()
+    variables = []
+    for i in range(L.ams_layout_num_tensors(num_classes, graph_variant)):
+        check(L.ams_layout_tensor_info(num_classes, graph_variant, i, name, 256, shape, C.byref(nd), C.byref(tr), C.byref(off)))
+        variables.append(dict(name=name.value.decode(), shape=list(shape[:nd.value]), trainable=bool(tr.value), offset=off.value))
+    layers = []
+    iv = [C.c_int() for _ in range(7)]
+    fv = [C.c_float(), C.c_float()]
+    for i in range(L.ams_layout_num_layers(num_classes, graph_variant)):
+        check(L.ams_layout_layer_info(num_classes, graph_variant, i, name, 256, *[C.byref(v) for v in iv[:6]],
+                                      C.byref(fv[0]), C.byref(fv[1]), C.byref(iv[6])))
+        layers.append(dict(name=name.value.decode(), kind=iv[0].value, cin=iv[1].value, cout=iv[2].value, stride=iv[3].value,
+                           dilation=iv[4].value, act=iv[5].value, eps=fv[0].value, one_minus_decay=fv[1].value,
+                           residual=iv[6].value))
+    return variables, layers

@@ -501,6 +501,41 @@ int ams_get_activation(ams_net* h, int index, int which, uint16_t* host, long lo
     return 0;
 }
 
+// =============================================================================================== host-only layout
+static Net* layout_net(int num_classes, int variant) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, std::unique_ptr<Net>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(num_classes, variant);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::unique_ptr<Net> n(new Net());
+        n->cfg.num_classes = num_classes; n->cfg.graph_variant = variant; n->cfg.height = 512; n->cfg.width = 1024;
+        if (net_build_topology(n.get())) return nullptr;
+        it = cache.emplace(key, std::move(n)).first;
+    }
+    return it->second.get();
+}
+int ams_layout_num_tensors(int nc, int variant) {
+    Net* n = layout_net(nc, variant);
+    return n ? static_cast<int>(n->vars.size()) : -1;
+}
+int ams_layout_tensor_info(int nc, int variant, int index, char* name, int cap, int shape4[4], int* ndim, int* trainable, long long* off) {
+    Net* n = layout_net(nc, variant);
+    if (!n) return -1;
+    return ams_tensor_info(reinterpret_cast<const ams_net*>(n), index, name, cap, shape4, ndim, trainable, off);
+}
+int ams_layout_num_layers(int nc, int variant) {
+    Net* n = layout_net(nc, variant);
+    return n ? static_cast<int>(n->layers.size()) : -1;
+}
+int ams_layout_layer_info(int nc, int variant, int index, char* name, int cap, int* kind, int* cin, int* cout, int* stride,
+                          int* dil, int* act, float* eps, float* k, int* residual_from) {
+    Net* n = layout_net(nc, variant);
+    if (!n) return -1;
+    return ams_layer_info(reinterpret_cast<const ams_net*>(n), index, name, cap, kind, cin, cout, stride, dil, act, eps, k, residual_from);
+}
+
 // =============================================================================================== op-level hooks
 int ams_op_conv1x1(const void* a, const void* w, int M, int N, int K, const float* scale, const float* shift,
                    const float* rowbias, int rows_per_image, const void* residual, int act, void* out, int out_fp32, int ldc,

@@ -121,6 +121,16 @@ int ams_layer_info(const ams_net* net, int index, char* name, int name_capacity,
 /* activation of conv layer `index` from the last run: which = 0 post-BN/act output, 1 raw conv output (training) */
 int ams_get_activation(ams_net* net, int index, int which, uint16_t* host_bf16, long long count);
 
+/* ---- host-only layout queries (no device needed): the variable / layer tables a handle with this graph would
+ * have.  Lets a maintainer (and tests/test_layout.py) check the restated topology against model.meta. */
+int ams_layout_num_tensors(int num_classes, int graph_variant);
+int ams_layout_tensor_info(int num_classes, int graph_variant, int index, char* name, int name_capacity, int shape4[4],
+                           int* ndim, int* trainable, long long* arena_offset);
+int ams_layout_num_layers(int num_classes, int graph_variant);
+int ams_layout_layer_info(int num_classes, int graph_variant, int index, char* name, int name_capacity, int* kind, int* cin,
+                          int* cout, int* stride, int* dilation, int* act, float* bn_eps, float* bn_one_minus_decay,
+                          int* residual_from);
+
 /* ---- op-level entry points on raw DEVICE pointers (kernel unit tests; see tests/test_ops_gpu.py) */
 int ams_op_conv1x1(const void* a_bf16, const void* w_bf16 /*[N][K]*/, int M, int N, int K, const float* scale,
                    const float* shift, const float* rowbias, int rows_per_image, const void* residual_bf16, int act,
