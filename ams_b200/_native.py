@@ -30,6 +30,7 @@ _vp, _i, _ll, _f, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
 _SIGNATURES = {
     'ams_last_error': (C.c_char_p, []),
     'ams_abi_version': (_i, []),
+    'ams_launch_count': (_ll, []),
     'ams_create': (_vp, [C.POINTER(AmsConfig)]),
     'ams_destroy': (None, [_vp]),
     'ams_set_stream': (_i, [_vp, _vp]),
@@ -61,6 +62,8 @@ _SIGNATURES = {
     'ams_num_layers': (_i, [_vp]),
     'ams_layer_info': (_i, [_vp, _i, C.c_char_p, _i] + [C.POINTER(_i)] * 6 + [C.POINTER(_f)] * 2 + [C.POINTER(_i)]),
     'ams_get_activation': (_i, [_vp, _i, _i, _vp, _ll]),
+    'ams_profile_enable': (_i, [_vp, _i]),
+    'ams_profile_report': (_i, [_vp, C.c_char_p, _i]),
     'ams_layout_num_tensors': (_i, [_i, _i]),
     'ams_layout_tensor_info': (_i, [_i, _i, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll)]),
     'ams_layout_num_layers': (_i, [_i, _i]),

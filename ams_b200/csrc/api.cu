@@ -1,4 +1,5 @@
 // extern "C" surface of libams_b200 (see include/ams_b200.h for the reference call site each entry replaces).
+#include <atomic>
 #include <cmath>
 #include <cstring>
 
@@ -7,6 +8,8 @@
 namespace ams {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace ams
 
 using namespace ams;
@@ -57,6 +60,7 @@ extern "C" {
 
 const char* ams_last_error(void) { return g_last_error.c_str(); }
 int ams_abi_version(void) { return 1; }
+long long ams_launch_count(void) { return g_launches.load(); }
 
 ams_net* ams_create(const ams_config* cfg) {
     if (!cfg) { set_last_error("null config"); return nullptr; }
@@ -279,6 +283,7 @@ int ams_enqueue(ams_net* h, const void* frames, int dtype, const uint8_t* labels
         std::unique_lock<std::mutex> lk(net->qmu);
         net->filled.push_back(slot);
     }
+    net->qcv.notify_all();
     return 0;
 }
 int ams_queue_size(ams_net* h) {
@@ -294,7 +299,14 @@ static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels,
     HeadGeom hg = net->head; hg.N = p->N;
     HeadStats hs;
     if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
-    if (head_infer(p->logits, hg, metric ? p->in_labels : nullptr, p->pred, net->head_st, net->stream)) return -1;
+    {
+        cudaStream_t s = net->stream;
+        const double px_ = static_cast<double>(p->N) * net->cfg.height * net->cfg.width;
+        net->prof.begin(s, "head_infer", px_ * (metric ? 5.0 : 4.0) + 4.0 * p->N * hg.h * hg.w * 32);
+        const int rc = head_infer(p->logits, hg, metric ? p->in_labels : nullptr, p->pred, net->head_st, s);
+        net->prof.end(s);
+        if (rc) return -1;
+    }
     const size_t px = static_cast<size_t>(p->N) * net->cfg.height * net->cfg.width;
     if (out_labels) AMS_CUDA_CHECK(cudaMemcpyAsync(out_labels, p->pred, px * sizeof(int32_t), cudaMemcpyDeviceToHost, net->stream));
     if (metric) AMS_CUDA_CHECK(cudaMemcpyAsync(&hs, net->head_st, sizeof(HeadStats), cudaMemcpyDeviceToHost, net->stream));
@@ -340,8 +352,11 @@ static int apply_optimizer(Net* net, float lr, int masked, float grad_scale) {
     // TF1 Adam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), all in fp32
     const float alpha = lr * std::sqrt(1.0f - net->beta2_power) / (1.0f - net->beta1_power);
     const uint8_t* mask = (masked && !net->mask_all_ones) ? net->mask : nullptr;
-    if (adam_masked(net->params, net->grads, grad_scale, net->adam_m, net->adam_v, mask, net->n_train, alpha,
-                    1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, net->stream)) return -1;
+    net->prof.begin(net->stream, "adam_masked", (mask ? 29.0 : 28.0) * net->n_train);
+    const int rc_adam = adam_masked(net->params, net->grads, grad_scale, net->adam_m, net->adam_v, mask, net->n_train, alpha,
+                                    1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, net->stream);
+    net->prof.end(net->stream);
+    if (rc_adam) return -1;
     net->beta1_power *= 0.9f;
     net->beta2_power *= 0.999f;
     net->weights_dirty = true; net->fold_dirty = true;
@@ -499,6 +514,29 @@ int ams_get_activation(ams_net* h, int index, int which, uint16_t* host, long lo
     AMS_CUDA_CHECK(cudaMemcpyAsync(host, src, count * 2, cudaMemcpyDeviceToHost, net->stream));
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
     return 0;
+}
+
+// =============================================================================================== profiler
+int ams_profile_enable(ams_net* h, int on) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->prof.reset();
+    net->prof.enabled = on != 0;
+    return 0;
+}
+int ams_profile_report(ams_net* h, char* buf, int cap) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->prof.collect();
+    std::string out;
+    for (const std::string& tag : net->prof.order) {
+        const ProfAgg& a = net->prof.agg[tag];
+        char line[256];
+        snprintf(line, sizeof(line), "%s %lld %.6f %.0f\n", tag.c_str(), a.launches, a.ms, a.algo_bytes);
+        out += line;
+    }
+    if (buf && cap > 0) { std::strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
+    return static_cast<int>(out.size());
 }
 
 // =============================================================================================== host-only layout

@@ -29,7 +29,12 @@ void set_last_error(const std::string& msg);
             return -2;                                                                           \
         }                                                                                        \
     } while (0)
-#define AMS_LAUNCH_CHECK() AMS_CUDA_CHECK(cudaGetLastError())
+void count_launch();
+#define AMS_LAUNCH_CHECK()                      \
+    do {                                        \
+        ams::count_launch();                    \
+        AMS_CUDA_CHECK(cudaGetLastError());     \
+    } while (0)
 
 constexpr int kNumSMs = 148;   // B200; grids of the persistent kernels are sized from the runtime value
 

@@ -4,6 +4,7 @@
 #include "net.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -35,6 +36,46 @@ int dev_alloc(T** p, size_t count, std::vector<void*>* track = nullptr) {
 }
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------- profiler
+cudaEvent_t Profiler::get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void Profiler::begin(cudaStream_t s, const char* tag, double algo_bytes) {
+    if (!enabled) return;
+    ProfEntry e;
+    e.tag = tag; e.algo_bytes = algo_bytes; e.e0 = get_event(); e.e1 = get_event();
+    cudaEventRecord(e.e0, s);
+    pending.push_back(e);
+}
+void Profiler::end(cudaStream_t s) {
+    if (!enabled || pending.empty()) return;
+    cudaEventRecord(pending.back().e1, s);
+}
+void Profiler::collect() {
+    for (ProfEntry& e : pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.e0, e.e1) == cudaSuccess) {
+            if (!agg.count(e.tag)) order.push_back(e.tag);
+            ProfAgg& a = agg[e.tag];
+            a.launches += 1; a.ms += ms; a.algo_bytes += e.algo_bytes;
+        }
+        pool.push_back(e.e0); pool.push_back(e.e1);
+    }
+    pending.clear();
+}
+void Profiler::reset() { collect(); agg.clear(); order.clear(); }
+
+#define PROF(tag, bytes, call)                                   \
+    do {                                                         \
+        net->prof.begin(s, tag, static_cast<double>(bytes));     \
+        const int _rc = (call);                                  \
+        net->prof.end(s);                                        \
+        if (_rc) return -1;                                      \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------------- topology
 int net_build_topology(Net* net) {
@@ -330,31 +371,37 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
         const LayerDef& d = L[i];
         const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
         LayerBuf& b = p->buf[i];
+        const double out_bytes = 2.0 * M * d.cout;
         if (d.kind == kImagePool) {
-            if (imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s)) return -1;
+            PROF("imgpool_fwd", 2.0 * p->N * L[d.input].out_h * L[d.input].out_w * d.cin, imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s));
             continue;
         }
         if (d.kind == kLogits) {
-            if (gemm_launch(p->fwd_frozen[i], s)) return -1;
+            PROF("gemm_logits", 2.0 * M * d.cin + 4.0 * M * 32, gemm_launch(p->fwd_frozen[i], s));
             continue;
         }
         bf16* conv_out = frozen ? b.y : b.z;
         const float* sc = frozen ? fscale(net, d) : nullptr;
         const float* sh = frozen ? fshift(net, d) : nullptr;
         if (d.kind == kStem) {
-            if (stem_conv_fwd(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w, d.out_h,
-                              d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, net->params + d.w_off,
-                              sc, sh, conv_out, s)) return -1;
+            const double in_bytes = static_cast<double>(p->N) * c.height * c.width * 3 * (p->in_dtype == AMS_FRAMES_U8 ? 1 : 4);
+            PROF("stem_fwd", in_bytes + out_bytes,
+                 stem_conv_fwd(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w, d.out_h,
+                               d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, net->params + d.w_off,
+                               sc, sh, conv_out, s));
         } else if (d.kind == kDepthwise) {
             Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
-            if (dw_conv_fwd(p->buf[d.input].y, net->params + d.w_off, g, sc, sh, d.act, conv_out, s)) return -1;
+            PROF("dw_fwd", 2.0 * p->N * d.in_h * d.in_w * d.cin + out_bytes,
+                 dw_conv_fwd(p->buf[d.input].y, net->params + d.w_off, g, sc, sh, d.act, conv_out, s));
         } else {
-            if (gemm_launch(frozen ? p->fwd_frozen[i] : p->fwd_train[i], s)) return -1;
+            const double gb = 2.0 * M * d.k_rows + 2.0 * d.k_rows * d.cout + out_bytes + ((frozen && d.residual >= 0) ? out_bytes : 0.0);
+            PROF("gemm_fwd", gb, gemm_launch(frozen ? p->fwd_frozen[i] : p->fwd_train[i], s));
         }
         if (!frozen) {
             BnLayer bl = bn_layer(net, d, M);
-            if (bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s)) return -1;
-            if (bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s)) return -1;
+            PROF("bn_stats", out_bytes, bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s));
+            PROF("bn_apply", (d.residual >= 0 ? 3.0 : 2.0) * out_bytes,
+                 bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s));
         }
     }
     p->last_was_train = !frozen;
@@ -369,21 +416,24 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     const int nl = static_cast<int>(L.size());
     // head: loss + d low-res logits
     HeadGeom hg = net->head; hg.N = p->N; hg.normalize = normalize ? 1 : 0;
-    if (head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s)) return -1;
     const LayerDef& lg = L[nl - 1];
     const long long M16 = static_cast<long long>(p->N) * lg.out_h * lg.out_w;
-    if (colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, net->grads + lg.bias_off, s)) return -1;
-    if (wgrad_launch(p->wgrad[nl - 1], s)) return -1;
-    if (gemm_launch(p->dgrad[nl - 1], s)) return -1;
+    PROF("head_loss_bwd", static_cast<double>(p->N) * c.height * c.width + 4.0 * M16 * 32 * 2,
+         head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s));
+    PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, net->grads + lg.bias_off, s));
+    PROF("gemm_wgrad", 2.0 * M16 * (lg.cin + 32), wgrad_launch(p->wgrad[nl - 1], s));
+    PROF("gemm_dgrad", 2.0 * M16 * (lg.cin + 32), gemm_launch(p->dgrad[nl - 1], s));
     for (int i = nl - 2; i >= 0; --i) {
         const LayerDef& d = L[i];
         if (d.kind == kImagePool) continue;          // handled together with concat_projection
         const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
         LayerBuf& b = p->buf[i];
         BnLayer bl = bn_layer(net, d, M);
-        if (bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s)) return -1;
+        const double tb = 2.0 * M * d.cout;
+        // reduce pass reads dy,z; apply pass reads dy,z and writes dz
+        PROF("bn_bwd", 5.0 * tb, bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s));
         if (d.kind == kConv1x1) {
-            if (wgrad_launch(p->wgrad[i], s)) return -1;
+            PROF("gemm_wgrad", 2.0 * M * d.k_rows + tb, wgrad_launch(p->wgrad[i], s));
             if (d.name == "concat_projection") {
                 const LayerDef& ipd = L[nl - 4];
                 ImgPoolBwd ib;
@@ -394,17 +444,19 @@ int net_backward(Net* net, Plan* p, bool normalize) {
                 ib.d_w_pool = net->grads + ipd.w_off;
                 ib.d_gamma = net->grads + ipd.gamma_off; ib.d_beta = net->grads + ipd.beta_off;
                 ib.dfeat_rowbias = p->dfeat_rowbias;
-                if (imgpool_backward(ib, s)) return -1;
+                PROF("imgpool_bwd", tb, imgpool_backward(ib, s));
             }
-            if (gemm_launch(p->dgrad[i], s)) return -1;
+            PROF("gemm_dgrad", tb + 2.0 * M * d.k_rows + 2.0 * d.k_rows * d.cout, gemm_launch(p->dgrad[i], s));
         } else if (d.kind == kDepthwise) {
             Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
-            if (dw_conv_bwd_filter(p->buf[d.input].y, b.gz, g, net->grads + d.w_off, p->red_ws, p->red_ws_floats, s)) return -1;
-            if (dw_conv_bwd_data(b.gz, net->params + d.w_off, g, p->buf[d.input].g, s)) return -1;
+            const double ib = 2.0 * p->N * d.in_h * d.in_w * d.cin;
+            PROF("dw_bwd_filter", ib + tb, dw_conv_bwd_filter(p->buf[d.input].y, b.gz, g, net->grads + d.w_off, p->red_ws, p->red_ws_floats, s));
+            PROF("dw_bwd_data", ib + tb, dw_conv_bwd_data(b.gz, net->params + d.w_off, g, p->buf[d.input].g, s));
         } else if (d.kind == kStem) {
-            if (stem_conv_bwd_filter(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w,
-                                     d.out_h, d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, b.gz,
-                                     net->grads + d.w_off, p->red_ws, p->red_ws_floats, s)) return -1;
+            PROF("stem_bwd_filter", tb + static_cast<double>(p->N) * c.height * c.width * 3,
+                 stem_conv_bwd_filter(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w,
+                                      d.out_h, d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, b.gz,
+                                      net->grads + d.w_off, p->red_ws, p->red_ws_floats, s));
         }
     }
     return 0;
@@ -414,8 +466,11 @@ int net_backward(Net* net, Plan* p, bool normalize) {
 int net_dequeue(Net* net, Plan** plan_out, bool need_backward) {
     int slot = -1;
     {
+        // TF's QueueDequeueV2 blocks until a batch is there (the reference's feeder thread runs concurrently);
+        // give up after 60 s so that a missing ams_enqueue is an error, not a hang
         std::unique_lock<std::mutex> lk(net->qmu);
-        AMS_REQUIRE(!net->filled.empty(), "input queue is empty: call ams_enqueue first");
+        const bool got = net->qcv.wait_for(lk, std::chrono::seconds(60), [&] { return !net->filled.empty(); });
+        AMS_REQUIRE(got, "input queue stayed empty for 60 s: call ams_enqueue first");
         slot = net->filled.front();
         net->filled.pop_front();
     }

@@ -67,6 +67,22 @@ struct Plan {
     bool last_was_train = false;
 };
 
+// Per-launch-group device timing (CUDA events on the launching stream), aggregated by tag.  Off by default.
+struct ProfEntry { std::string tag; double algo_bytes = 0; cudaEvent_t e0 = nullptr, e1 = nullptr; };
+struct ProfAgg { long long launches = 0; double ms = 0, algo_bytes = 0; };
+struct Profiler {
+    bool enabled = false;
+    std::vector<ProfEntry> pending;
+    std::vector<cudaEvent_t> pool;
+    std::map<std::string, ProfAgg> agg;
+    std::vector<std::string> order;
+    cudaEvent_t get_event();
+    void begin(cudaStream_t s, const char* tag, double algo_bytes);
+    void end(cudaStream_t s);
+    void collect();          // after a stream sync: fold pending pairs into agg
+    void reset();
+};
+
 struct QueueSlot {
     void* frames = nullptr; size_t frames_cap = 0;
     uint8_t* labels = nullptr; size_t labels_cap = 0;
@@ -101,6 +117,7 @@ struct Net {
     std::mutex qmu; std::condition_variable qcv;
     std::vector<QueueSlot> slots; std::deque<int> filled; std::deque<int> free_slots;
     int last_n = 0;
+    Profiler prof;
 };
 
 int net_build_topology(Net* net);

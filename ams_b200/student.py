@@ -216,6 +216,20 @@ class Student:
     def apply_optimizer(self, lr, masked, grad_scale):
         nat.check(self._L.ams_apply_optimizer(self._h, float(lr), 1 if masked else 0, float(grad_scale)))
 
+    # ------------------------------------------------------------------ profiling
+    def profile_enable(self, on=True):
+        nat.check(self._L.ams_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self):
+        """{tag: dict(launches, ms, algo_bytes)} accumulated since profile_enable(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._L.ams_profile_report(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, n, ms, b = line.split()
+            out[tag] = dict(launches=int(n), ms=float(ms), algo_bytes=float(b))
+        return out
+
     # ------------------------------------------------------------------ parity hooks
     def get_logits(self, n):
         h, w = self.low_res

@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- AMS student hot path on B200.
+
+Workload (BASELINE.json configs[1], "C2"): one online-distillation PHASE of K iterations, batch 8 @ 512x1024,
+7 selected classes (reference experiment 12), lr 1e-3, strategy coord_desc_auto with coord_fraction 0.05 --
+exactly what `SemanticNetwork.train_with_deque` + the delta writer of run.py:309-336 do:
+   iteration 0 : snapshot, full Adam step, |delta| percentile selection of 5 % of the 2,113,043 coordinates
+   iterations 1..K-1 : forward/backward/BN-moving-average/Adam with the masked parameter write
+   end of phase : pack the model delta (packbits(mask) + fp16 values)
+A "step" is one iteration; `value` = K / (device time of the whole phase) in steps/s with the K input batches
+already resident in HBM; `e2e` = the same phase driven from pinned HOST buffers (H2D of every batch by a feeder
+thread through ams_enqueue, D2H of every loss and of the delta) in steps/s.
+Secondary block `infer`: frozen-client frames/s (C1/C3 shape, batch 8, argmax + confusion matrix).
+
+N > 1 (torchrun): data parallel, 8 frames per GPU (weak scaling), NCCL allreduce of the 8.45 MB gradient arena and
+of n_valid, per-replica BatchNorm statistics.  `--impl reference` times the CPU oracle (the port of the
+reference's TF1 path; TensorFlow 1.15 cannot be installed here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, BATCH = 512, 1024, 8
+CLASSES = [0, 1, 2, 8, 10, 11, 13]          # reference experiment 12 (exp_configs.py:44-47)
+COORD_FRAC = 0.05
+LR = 1e-3
+ALGO_BYTES_STEP = 8.14e9                    # layer-boundary bf16 traffic of one b8 step
+ALGO_BYTES_FRAME = 343.1e6
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def pinned(shape, dtype):
+    import torch
+    t = torch.empty(shape, dtype=dtype).pin_memory()
+    return t, t.numpy()
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import torch
+    import student_oracle as so
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    spec = so.load_spec('cityscapes')
+    V = so.synthetic_variables(spec, 1)
+    sample_b = 2
+    frames = so.synthetic_frames(sample_b, H, W, 0).astype(np.float32)
+    labels = so.synthetic_labels(sample_b, H, W, 0)
+    ts = so.TrainState(spec, V)
+    budget_s = 240.0
+    times = []
+    t_start = time.time()
+    for it in range(args.warmup + args.steps):
+        t0 = time.time()
+        ts.step(frames, labels, np.array(CLASSES), LR)
+        dt = time.time() - t0
+        if it >= args.warmup:
+            times.append(dt)
+        if time.time() - t_start > budget_s and len(times) >= 1:
+            break
+    t_step = float(np.mean(times)) * (BATCH / sample_b)
+    value = 1.0 / t_step
+    sample = ('%d of %d steps measured, each on %d of the %d frames of a step (fwd+bwd+BN update+Adam, fp32, torch-CPU oracle '
+              '= port of the TF1 graph); steps/s scaled by %d/%d' % (len(times), args.steps, sample_b, BATCH, sample_b, BATCH))
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'distill_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * t_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'C2 distillation step, batch 8 @ 512x1024, 7 classes, CPU oracle'},
+        'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+def cpu_baseline():
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import torch
+    import student_oracle as so
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    spec = so.load_spec('cityscapes')
+    V = so.synthetic_variables(spec, 1)
+    b = 2
+    frames = so.synthetic_frames(b, H, W, 0).astype(np.float32)
+    labels = so.synthetic_labels(b, H, W, 0)
+    ts = so.TrainState(spec, V)
+    ts.step(frames[:1], labels[:1], np.array(CLASSES), LR)          # warm-up
+    t0 = time.time()
+    n = 0
+    while n < 3 and time.time() - t0 < 25.0:
+        ts.step(frames, labels, np.array(CLASSES), LR)
+        n += 1
+    t_step = (time.time() - t0) / n * (BATCH / b)
+    # frozen inference, batch 1
+    params = {k: torch.tensor(v) for k, v in V.items()}
+    t1 = time.time()
+    m = 0
+    with torch.no_grad():
+        while m < 5 and time.time() - t1 < 8.0:
+            s, _ = so.forward(spec, params, frames[:1])
+            so.head(so.full_res_logits(s, H, W), labels[:1], np.array(CLASSES), need_loss=False)
+            m += 1
+    fps = m / (time.time() - t1)
+    return {'value': 1.0 / t_step, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d oracle steps on %d of the 8 frames of a step, scaled by %d/8 (torch-CPU fp32 port of the TF1 graph; '
+                      'TF 1.15 itself is not installable here)' % (n, b, b),
+            'infer_frames_per_sec': fps}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from ams_b200 import _native as nat
+    from ams_b200.student import Student
+    from ams_b200.synthetic import synthetic_checkpoint, synthetic_frames, synthetic_labels
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    K, Wm = args.steps, args.warmup
+    st = Student(19, H, W, CLASSES, device=local_rank, queue_capacity=K + 2)
+    stream = torch.cuda.current_stream()
+    st.set_stream(stream.cuda_stream)
+    for k, v in synthetic_checkpoint('cityscapes', 1).items():
+        st.set_tensor(k, v)
+    # 4 distinct synthetic batches per rank, cycled
+    nb = 4
+    host = []
+    for i in range(nb):
+        ft, fa = pinned((BATCH, H, W, 3), torch.uint8)
+        lt, la = pinned((BATCH, H, W), torch.uint8)
+        fa[...] = synthetic_frames(BATCH, H, W, seed=100 * rank + i)
+        la[...] = synthetic_labels(BATCH, H, W, seed=100 * rank + i)
+        host.append((ft, fa, lt, la))
+    h2d_step = BATCH * H * W * 4
+
+    grad_t = None
+    if world > 1:
+        ptr, n = st.gradient_arena()
+
+        class _Arena:
+            __cuda_array_interface__ = {'shape': (n,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+        grad_t = torch.as_tensor(_Arena(), device='cuda')
+        nv_t = torch.zeros(1, dtype=torch.float64, device='cuda')
+
+    def step(masked):
+        if world == 1:
+            return st.train_step(LR, masked)
+        nv, ls = st.train_forward_backward()
+        nv_t[0] = nv
+        dist.all_reduce(grad_t)
+        dist.all_reduce(nv_t)
+        tot = float(nv_t.item())
+        st.apply_optimizer(LR, masked, 1.0 / max(tot, 1.0))
+        return ls / max(nv, 1)
+
+    def phase(feed_from_host):
+        """one distillation phase of K iterations; returns (delta bytes, kept)"""
+        feeder = None
+        if feed_from_host:
+            def feed():
+                for i in range(K):
+                    _, fa, _, la = host[i % nb]
+                    st.enqueue(fa, la)
+            feeder = threading.Thread(target=feed, daemon=True)
+            feeder.start()
+        st.set_mask(None)
+        st.snapshot_before()
+        step(True)
+        kept, _ = st.select_topk(COORD_FRAC)
+        for _ in range(K - 1):
+            step(True)
+        blob = st.pack_delta()
+        if feeder is not None:
+            feeder.join()
+        return len(blob), kept
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also builds the plan, the TMA descriptors and sets the smem attributes)
+    for i in range(Wm):
+        _, fa, _, la = host[i % nb]
+        st.enqueue(fa, la)
+        step(False)
+    torch.cuda.synchronize()
+
+    # ---- timed: device-resident inputs
+    for i in range(K):
+        _, fa, _, la = host[i % nb]
+        st.enqueue(fa, la)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = nat.lib().ams_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    delta_len, kept = phase(False)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = nat.lib().ams_launch_count() - launches0
+    # ---- timed: end to end from pinned host memory
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    f0.record(stream)
+    delta_len2, _ = phase(True)
+    f1.record(stream)
+    barrier()
+    ms_e2e = max(f0.elapsed_time(f1), 1000.0 * (time.time() - t_wall0))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- per-kernel-group device times (separate short pass so the events do not perturb the numbers above)
+    prof = None
+    infer = None
+    if rank == 0:
+        st.profile_enable(True)
+        for i in range(3):
+            _, fa, _, la = host[i % nb]
+            st.enqueue(fa, la)
+            st.train_step(LR, True)
+        prof = st.profile_report()
+        st.profile_enable(False)
+        # ---- secondary: frozen-client inference, batch 8, argmax + confusion matrix
+        n_inf = 10
+        for i in range(3):
+            st.enqueue(host[i % nb][1], host[i % nb][3])
+            st.infer_metric(BATCH, nat.BN_MOVING)
+        for i in range(n_inf):
+            st.enqueue(host[i % nb][1], host[i % nb][3])
+        out = np.empty((BATCH, H, W), dtype=np.int32)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record(stream)
+        for i in range(n_inf):
+            st.infer_metric(BATCH, nat.BN_MOVING)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        ms_inf = g0.elapsed_time(g1) / n_inf
+        st.profile_enable(True)
+        for i in range(3):
+            st.enqueue(host[i % nb][1], host[i % nb][3])
+            st.infer_metric(BATCH, nat.BN_MOVING)
+        prof_inf = st.profile_report()
+        st.profile_enable(False)
+        infer = {'frames_per_sec': BATCH / (ms_inf / 1000.0), 'ms_per_batch8': ms_inf, 'includes': 'D2H of int32 label maps + confusion matrix',
+                 'roofline_frac_layer_boundary': (BATCH / (ms_inf / 1000.0)) * ALGO_BYTES_FRAME / (peaks()[0] * 1e9),
+                 'kernel_groups_ms_per_batch': {k: round(v['ms'] / 3, 4) for k, v in sorted(prof_inf.items(), key=lambda kv: -kv[1]['ms'])}}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        steps_s = K * world / (ms / 1000.0)
+        e2e_s = K * world / (ms_e2e / 1000.0)
+        top = max(prof.items(), key=lambda kv: kv[1]['ms'])
+        t_ms = top[1]['ms'] / top[1]['launches']
+        a_gbs = top[1]['algo_bytes'] / top[1]['launches'] / (t_ms * 1e-3) / 1e9
+        step_ms_prof = sum(v['ms'] for v in prof.values()) / 3
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(top[0])
+            except Exception:
+                traffic = None
+        line = {
+            'metric': 'distill_steps_per_sec', 'value': steps_s, 'unit': 'steps/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': 'C2: AMS online distillation phase (K iterations), batch 8/GPU @ 512x1024, 7 classes, '
+                                   'coord_desc_auto 5 % selection at iteration 0 + masked Adam + delta pack at the end',
+                       'global_batch': BATCH * world, 'parallelism': 'dp%d' % world if world > 1 else 'single',
+                       'l2': 'no explicit flush: each step streams ~3 GB of activations (>> 126 MB L2) and batches are distinct',
+                       'delta_bytes': delta_len, 'kept_coordinates': kept},
+            'e2e': {'value': e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d_step, 'd2h_bytes_per_step': 4 + delta_len2 // K,
+                    'ms_per_step': ms_e2e / K},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {'bound': 'hbm', 'kernel': top[0], 'achieved': a_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': a_gbs / peak,
+                         'traffic': traffic, 'peak_source': peak_src, 'avg_launch_ms': t_ms,
+                         'share_of_step': top[1]['ms'] / 3 / step_ms_prof,
+                         'whole_step_frac_layer_boundary': (K / (ms / 1000.0)) * ALGO_BYTES_STEP / (peak * 1e9),
+                         'kernel_groups_ms_per_step': {k: round(v['ms'] / 3, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])},
+                         'kernel_groups_gbs': {k: round(v['algo_bytes'] / (v['ms'] * 1e-3) / 1e9, 1) for k, v in prof.items() if v['ms'] > 0}},
+            'infer': infer,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline()
+        print(json.dumps(line))
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    args.steps = max(args.steps, 2)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

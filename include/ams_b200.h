@@ -41,6 +41,8 @@ typedef struct ams_config {
 
 const char* ams_last_error(void);
 int ams_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long ams_launch_count(void);
 
 /* build: import graph + add heads/loss/Adam + create session -- SemanticNetwork.py:121-150, utils/graph_utils.py:338-533 */
 ams_net* ams_create(const ams_config* cfg);
@@ -120,6 +122,11 @@ int ams_layer_info(const ams_net* net, int index, char* name, int name_capacity,
                    int* stride, int* dilation, int* act, float* bn_eps, float* bn_one_minus_decay, int* residual_from);
 /* activation of conv layer `index` from the last run: which = 0 post-BN/act output, 1 raw conv output (training) */
 int ams_get_activation(ams_net* net, int index, int which, uint16_t* host_bf16, long long count);
+
+/* ---- per-kernel-group device timing (CUDA events on the launching stream), for bench.py's roofline line.
+ * report: one line per group "<tag> <launches> <total_ms> <algorithmic_bytes>"; returns the text length */
+int ams_profile_enable(ams_net* net, int on);
+int ams_profile_report(ams_net* net, char* buf, int capacity);
 
 /* ---- host-only layout queries (no device needed): the variable / layer tables a handle with this graph would
  * have.  Lets a maintainer (and tests/test_layout.py) check the restated topology against model.meta. */
