@@ -13,10 +13,10 @@ constexpr int kRedThreads = 256;
 constexpr int kFlush = 16;          // fp32 run length before flushing into fp64
 
 int red_chunks(long long M, int C) {
-    // enough blocks to fill the machine, each with at least ~64 rows per thread-row
+    // enough blocks to fill the machine (4 per SM) while every thread still walks >= 8 rows
     const int c8 = C / 8;
-    const int rows_per_block = std::max(1, kRedThreads / c8);
-    long long want = std::max<long long>(1, std::min<long long>(4 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 32)));
+    const int rows_per_block = std::max(1, kRedThreads / std::min(c8, kRedThreads));
+    long long want = std::max<long long>(1, std::min<long long>(4 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8)));
     return static_cast<int>(want);
 }
 
@@ -36,16 +36,30 @@ bn_stats_kernel(const bf16* __restrict__ z, long long M, int C, long long rows_p
         for (int q = 0; q < 8; ++q) { ds[q] = 0.0; dq[q] = 0.0; }
         if (lr < rows_in_block) {
             long long r = r_begin + lr;
+            const long long RB = rows_in_block;
             while (r < r_end) {
                 float fs[8], fq[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { fs[q] = 0.f; fq[q] = 0.f; }
-#pragma unroll 4
-                for (int i = 0; i < kFlush && r < r_end; ++i, r += rows_in_block) {
-                    float v[8];
-                    unpack8(ldg_stream(z + r * C + c8 * 8), v);
+                // 4 x 4 rows per fp32 run; 4 independent 128-bit loads in flight per thread
+                for (int it = 0; it < kFlush / 4 && r < r_end; ++it) {
+                    uint4 raw[4];
+                    int nv = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { fs[q] += v[q]; fq[q] = fmaf(v[q], v[q], fq[q]); }
+                    for (int u = 0; u < 4; ++u) {
+                        const long long rr = r + u * RB;
+                        if (rr < r_end) { raw[u] = ldg_stream(z + rr * C + c8 * 8); nv = u + 1; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (u < nv) {
+                            float v[8];
+                            unpack8(raw[u], v);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) { fs[q] += v[q]; fq[q] = fmaf(v[q], v[q], fq[q]); }
+                        }
+                    }
+                    r += 4 * RB;
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { ds[q] += fs[q]; dq[q] += fq[q]; }
@@ -65,14 +79,19 @@ bn_stats_kernel(const bf16* __restrict__ z, long long M, int C, long long rows_p
     }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, int update_moving) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lanes stride over the chunk partials (fixed assignment + fixed shuffle tree => deterministic)
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, int update_moving) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= L.C) return;
     double s = 0.0, q = 0.0;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = lane; k < chunks; k += 32) {
         s += partial[static_cast<long long>(k) * 2 * L.C + c];
         q += partial[static_cast<long long>(k) * 2 * L.C + L.C + c];
     }
+    s = warp_sum_d(s);
+    q = warp_sum_d(q);
+    if (lane != 0) return;
     const double n = static_cast<double>(L.M);
     const double mean = s / n;
     double var = q / n - mean * mean;
@@ -150,27 +169,45 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
         for (int q = 0; q < 8; ++q) { ds[q] = 0.0; dq[q] = 0.0; sc[q] = scale[c8 * 8 + q]; sh[q] = shift[c8 * 8 + q]; }
         if (lr < rows_in_block) {
             long long r = r_begin + lr;
+            const long long RB = rows_in_block;
             while (r < r_end) {
                 float fs[8], fq[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { fs[q] = 0.f; fq[q] = 0.f; }
-#pragma unroll 2
-                for (int i = 0; i < kFlush && r < r_end; ++i, r += rows_in_block) {
-                    float g[8], v[8];
-                    unpack8(ldg_stream(dy + r * C + c8 * 8), g);
-                    if (dy2) {
-                        float g2[8];
-                        unpack8(ldg_stream(dy2 + r * C + c8 * 8), g2);
+                for (int it = 0; it < kFlush / 2 && r < r_end; ++it) {
+                    uint4 rg[2], rz[2], rg2[2];
+                    int nv = 0;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) g[q] += g2[q];
+                    for (int u = 0; u < 2; ++u) {
+                        const long long rr = r + u * RB;
+                        if (rr < r_end) {
+                            rg[u] = ldg_stream(dy + rr * C + c8 * 8);
+                            rz[u] = ldg_stream(z + rr * C + c8 * 8);
+                            if (dy2) rg2[u] = ldg_stream(dy2 + rr * C + c8 * 8);
+                            nv = u + 1;
+                        }
                     }
-                    unpack8(ldg_stream(z + r * C + c8 * 8), v);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float gm = act_mask(g[q], fmaf(v[q], sc[q], sh[q]), act);
-                        fs[q] += gm;
-                        fq[q] = fmaf(gm, v[q], fq[q]);
+                    for (int u = 0; u < 2; ++u) {
+                        if (u < nv) {
+                            float g[8], v[8];
+                            unpack8(rg[u], g);
+                            unpack8(rz[u], v);
+                            if (dy2) {
+                                float g2[8];
+                                unpack8(rg2[u], g2);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) g[q] += g2[q];
+                            }
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float gm = act_mask(g[q], fmaf(v[q], sc[q], sh[q]), act);
+                                fs[q] += gm;
+                                fq[q] = fmaf(gm, v[q], fq[q]);
+                            }
+                        }
                     }
+                    r += 2 * RB;
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { ds[q] += fs[q]; dq[q] += fq[q]; }
@@ -191,15 +228,18 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 }
 
 // coef[0][c]=A, [1][c]=B, [2][c]=Cc with dz = A*g + B*z + Cc ; also d_gamma, d_beta
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, float* d_gamma,
-                                       float* d_beta, float* coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, float* d_gamma, float* d_beta, float* coef) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= L.C) return;
     double s1 = 0.0, sz = 0.0;
-    for (int k = 0; k < chunks; ++k) {
+    for (int k = lane; k < chunks; k += 32) {
         s1 += partial[static_cast<long long>(k) * 2 * L.C + c];
         sz += partial[static_cast<long long>(k) * 2 * L.C + L.C + c];
     }
+    s1 = warp_sum_d(s1);
+    sz = warp_sum_d(sz);
+    if (lane != 0) return;
     const double mean = L.mean[c], rstd = L.rstd[c], gamma = L.gamma[c];
     const double n = static_cast<double>(L.M);
     const double s2 = rstd * (sz - mean * s1);           // sum g * xhat
@@ -238,133 +278,132 @@ bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __
 }
 
 // ------------------------------------------------------------------------------------ generic column sums
-// out[g][c] = sum over rows [g*rpg, (g+1)*rpg) of x[row][c]; one block per (group, 64-channel slab); fixed order
+// partial[g][split][c] = sum over the split's rows of group g of x[row][c]; thread = (row lane, channel), 64 channels
+// per block; a second tiny kernel adds the splits in fixed order (deterministic).
+constexpr int kColsumSplits = 32;
 __global__ void __launch_bounds__(256)
-colsum_groups_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb, int ld, long long rpg, int C,
-                     float* __restrict__ out) {
+colsum_partial_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb, int ld, long long rpg, int C,
+                      double* __restrict__ partial) {
     __shared__ double s_red[4][64];
-    const int g = blockIdx.x;
+    const int g = blockIdx.x, split = blockIdx.z;
     const int c = blockIdx.y * 64 + (threadIdx.x & 63);
     const int lr = threadIdx.x >> 6;
+    const long long rows_per_split = (rpg + kColsumSplits - 1) / kColsumSplits;
+    const long long r0 = static_cast<long long>(g) * rpg + split * rows_per_split;
+    const long long r1 = min(r0 + rows_per_split, static_cast<long long>(g + 1) * rpg);
     double acc = 0.0;
     if (c < C) {
-        const long long r0 = static_cast<long long>(g) * rpg;
-        for (long long r = r0 + lr; r < r0 + rpg; r += 4)
-            acc += xf ? static_cast<double>(xf[r * ld + c]) : static_cast<double>(__bfloat162float(xb[r * ld + c]));
+        float run = 0.f;
+        int cnt = 0;
+        for (long long r = r0 + lr; r < r1; r += 4) {
+            run += xf ? xf[r * ld + c] : __bfloat162float(xb[r * ld + c]);
+            if (++cnt == 32) { acc += run; run = 0.f; cnt = 0; }
+        }
+        acc += run;
     }
     s_red[lr][threadIdx.x & 63] = acc;
     __syncthreads();
     if (lr == 0 && c < C)
-        out[static_cast<long long>(g) * C + c] = static_cast<float>(s_red[0][threadIdx.x] + s_red[1][threadIdx.x] +
-                                                                    s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+        partial[(static_cast<long long>(g) * kColsumSplits + split) * C + c] =
+            s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
+}
+__global__ void colsum_final_kernel(const double* __restrict__ partial, int groups, int C, float scale, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups * C) return;
+    const int g = i / C, c = i % C;
+    double acc = 0.0;
+    for (int s = 0; s < kColsumSplits; ++s) acc += partial[(static_cast<long long>(g) * kColsumSplits + s) * C + c];
+    out[i] = static_cast<float>(acc) * scale;
 }
 
 // ------------------------------------------------------------------------------------ image pooling branch
-// single block; everything is tiny (N <= 64 images, 320 -> 256 -> 256)
+// Everything here is tiny (N <= 64 images, 320 -> 256 -> 256) and fp32; several small multi-block kernels.
+// out[n][co] = sum_c in[n][c] * w[c][co]      (thread per output, coalesced over co)
 __global__ void __launch_bounds__(256)
-imgpool_fwd_kernel(ImgPoolFwd a) {
-    const int N = a.N, Cin = a.Cin, Cm = a.Cmid, Co = a.Cout;
-    // z[n][co] = sum_c pooled[n][c] * w_pool[c][co]
-    for (int i = threadIdx.x; i < N * Cm; i += blockDim.x) {
-        const int n = i / Cm, co = i % Cm;
-        float acc = 0.f;
-        for (int c = 0; c < Cin; ++c) acc = fmaf(a.pooled[n * Cin + c], a.w_pool[c * Cm + co], acc);
-        a.z[i] = acc;
-    }
-    __syncthreads();
-    for (int co = threadIdx.x; co < Cm; co += blockDim.x) {
-        float sc, sh;
-        if (a.frozen) {
-            sc = a.bn.gamma[co] * rsqrtf(a.bn.moving_var[co] + a.bn.eps);
-            sh = a.bn.beta[co] - a.bn.moving_mean[co] * sc;
-        } else {
-            double s = 0.0, q = 0.0;
-            for (int n = 0; n < N; ++n) { const double v = a.z[n * Cm + co]; s += v; }
-            const double mean = s / N;
-            for (int n = 0; n < N; ++n) { const double d = a.z[n * Cm + co] - mean; q += d * d; }
-            const double var = q / N;
-            const float meanf = static_cast<float>(mean), varf = static_cast<float>(var);
-            const float rstd = rsqrtf(varf + a.bn.eps);
-            sc = a.bn.gamma[co] * rstd;
-            sh = a.bn.beta[co] - meanf * sc;
-            a.bn.mean[co] = meanf;
-            a.bn.rstd[co] = rstd;
-            if (a.update_moving) {
-                const float unb = static_cast<float>(var * (static_cast<double>(N) / fmax(N - 1.0, 1.0)));
-                const float mm = a.bn.moving_mean[co], mv = a.bn.moving_var[co];
-                a.bn.moving_mean[co] = __fsub_rn(mm, __fmul_rn(__fsub_rn(mm, meanf), a.bn.one_minus_decay));
-                a.bn.moving_var[co] = __fsub_rn(mv, __fmul_rn(__fsub_rn(mv, unb), a.bn.one_minus_decay));
-            }
-        }
-        a.bn.scale[co] = sc;
-        a.bn.shift[co] = sh;
-        for (int n = 0; n < N; ++n) a.act[n * Cm + co] = fmaxf(fmaf(a.z[n * Cm + co], sc, sh), 0.f);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < N * Co; i += blockDim.x) {
-        const int n = i / Co, co = i % Co;
-        float acc = 0.f;
-        for (int c = 0; c < Cm; ++c) acc = fmaf(a.act[n * Cm + c], a.w_proj_top[c * Co + co], acc);
-        a.bias_img[i] = acc;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-imgpool_bwd_kernel(ImgPoolBwd b, float* __restrict__ dact /*[N][Cmid] scratch*/) {
-    const ImgPoolFwd& a = b.f;
-    const int N = a.N, Cin = a.Cin, Cm = a.Cmid, Co = a.Cout;
-    // d act[n][c] = sum_co dbias[n][co] * w_proj_top[c][co]
-    for (int i = threadIdx.x; i < N * Cm; i += blockDim.x) {
-        const int n = i / Cm, c = i % Cm;
-        float acc = 0.f;
-        for (int co = 0; co < Co; ++co) acc = fmaf(b.dbias[n * Co + co], a.w_proj_top[c * Co + co], acc);
-        dact[i] = a.act[i] > 0.f ? acc : 0.f;                 // through the ReLU
-    }
-    // d w_proj_top[c][co] = sum_n act[n][c] * dbias[n][co]
-    for (int i = threadIdx.x; i < Cm * Co; i += blockDim.x) {
-        const int c = i / Co, co = i % Co;
-        float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc = fmaf(a.act[n * Cm + c], b.dbias[n * Co + co], acc);
-        b.d_w_proj_top[i] = acc;
-    }
-    __syncthreads();
-    // BN backward over the batch dimension (training statistics): dact -> dz (in place)
-    for (int co = threadIdx.x; co < Cm; co += blockDim.x) {
-        const double mean = a.bn.mean[co], rstd = a.bn.rstd[co], gamma = a.bn.gamma[co];
-        double s1 = 0.0, s2 = 0.0;
-        for (int n = 0; n < N; ++n) {
-            const double g = dact[n * Cm + co];
-            s1 += g;
-            s2 += g * (a.z[n * Cm + co] - mean) * rstd;
-        }
-        b.d_gamma[co] = static_cast<float>(s2);
-        b.d_beta[co] = static_cast<float>(s1);
-        for (int n = 0; n < N; ++n) {
-            const double xh = (a.z[n * Cm + co] - mean) * rstd;
-            dact[n * Cm + co] = static_cast<float>(gamma * rstd * (dact[n * Cm + co] - s1 / N - xh * s2 / N));
-        }
-    }
-    __syncthreads();
-    // d w_pool[c][co] = sum_n pooled[n][c] * dz[n][co]
-    for (int i = threadIdx.x; i < Cin * Cm; i += blockDim.x) {
-        const int c = i / Cm, co = i % Cm;
-        float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc = fmaf(a.pooled[n * Cin + c], dact[n * Cm + co], acc);
-        b.d_w_pool[i] = acc;
-    }
-    // d pooled[n][c] / HW
-    const float inv_hw = 1.f / static_cast<float>(a.HW);
-    for (int i = threadIdx.x; i < N * Cin; i += blockDim.x) {
-        const int n = i / Cin, c = i % Cin;
-        float acc = 0.f;
-        for (int co = 0; co < Cm; ++co) acc = fmaf(dact[n * Cm + co], a.w_pool[c * Cm + co], acc);
-        b.dfeat_rowbias[i] = acc * inv_hw;
-    }
-}
-
-__global__ void scale_rows_kernel(float* x, int n, float s) {
+small_fc_kernel(const float* __restrict__ in, const float* __restrict__ w, int N, int Cin, int Cout, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] *= s;
+    if (i >= N * Cout) return;
+    const int n = i / Cout, co = i % Cout;
+    const float* x = in + n * Cin;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < Cin; ++c) acc = fmaf(x[c], w[c * Cout + co], acc);
+    out[i] = acc;
+}
+// out[n][c] = scale * sum_co g[n][co] * w[c][co]   (warp per output, lanes over co), optional ReLU gate
+__global__ void __launch_bounds__(256)
+small_fc_t_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ gate, int N, int C,
+                  int Cout, float scale, float* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N * C) return;
+    const int n = warp / C, c = warp % C;
+    float acc = 0.f;
+    for (int co = lane; co < Cout; co += 32) acc = fmaf(g[n * Cout + co], w[c * Cout + co], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[warp] = (gate && !(gate[warp] > 0.f)) ? 0.f : acc * scale;
+}
+// out[c][co] = sum_n a[n][c] * b[n][co]
+__global__ void __launch_bounds__(256)
+small_outer_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, int C, int Cout, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * Cout) return;
+    const int c = i / Cout, co = i % Cout;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(a[n * C + c], b[n * Cout + co], acc);
+    out[i] = acc;
+}
+// BN over the batch dimension + ReLU (training statistics or frozen)
+__global__ void __launch_bounds__(256)
+imgpool_bn_kernel(ImgPoolFwd a) {
+    const int co = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = a.N, Cm = a.Cmid;
+    if (co >= Cm) return;
+    float sc, sh;
+    if (a.frozen) {
+        sc = a.bn.gamma[co] * rsqrtf(a.bn.moving_var[co] + a.bn.eps);
+        sh = a.bn.beta[co] - a.bn.moving_mean[co] * sc;
+    } else {
+        double s = 0.0, q = 0.0;
+        for (int n = 0; n < N; ++n) s += a.z[n * Cm + co];
+        const double mean = s / N;
+        for (int n = 0; n < N; ++n) { const double d = a.z[n * Cm + co] - mean; q += d * d; }
+        const double var = q / N;
+        const float meanf = static_cast<float>(mean), varf = static_cast<float>(var);
+        const float rstd = rsqrtf(varf + a.bn.eps);
+        sc = a.bn.gamma[co] * rstd;
+        sh = a.bn.beta[co] - meanf * sc;
+        a.bn.mean[co] = meanf;
+        a.bn.rstd[co] = rstd;
+        if (a.update_moving) {
+            const float unb = static_cast<float>(var * (static_cast<double>(N) / fmax(N - 1.0, 1.0)));
+            const float mm = a.bn.moving_mean[co], mv = a.bn.moving_var[co];
+            a.bn.moving_mean[co] = __fsub_rn(mm, __fmul_rn(__fsub_rn(mm, meanf), a.bn.one_minus_decay));
+            a.bn.moving_var[co] = __fsub_rn(mv, __fmul_rn(__fsub_rn(mv, unb), a.bn.one_minus_decay));
+        }
+    }
+    a.bn.scale[co] = sc;
+    a.bn.shift[co] = sh;
+    for (int n = 0; n < N; ++n) a.act[n * Cm + co] = fmaxf(fmaf(a.z[n * Cm + co], sc, sh), 0.f);
+}
+// BN backward over the batch dimension: dact -> dz in place, d_gamma, d_beta
+__global__ void __launch_bounds__(256)
+imgpool_bn_bwd_kernel(ImgPoolFwd a, float* __restrict__ dact, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    const int co = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = a.N, Cm = a.Cmid;
+    if (co >= Cm) return;
+    const double mean = a.bn.mean[co], rstd = a.bn.rstd[co], gamma = a.bn.gamma[co];
+    double s1 = 0.0, s2 = 0.0;
+    for (int n = 0; n < N; ++n) {
+        const double g = dact[n * Cm + co];
+        s1 += g;
+        s2 += g * (a.z[n * Cm + co] - mean) * rstd;
+    }
+    d_gamma[co] = static_cast<float>(s2);
+    d_beta[co] = static_cast<float>(s1);
+    for (int n = 0; n < N; ++n) {
+        const double xh = (a.z[n * Cm + co] - mean) * rstd;
+        dact[n * Cm + co] = static_cast<float>(gamma * rstd * (dact[n * Cm + co] - s1 / N - xh * s2 / N));
+    }
 }
 
 }  // namespace
@@ -387,7 +426,7 @@ int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double*
     AMS_REQUIRE(smem <= 48 * 1024, "BN reduction shared memory");
     bn_stats_kernel<<<chunks, kRedThreads, smem, s>>>(z, L.M, L.C, rpc, ws);
     AMS_LAUNCH_CHECK();
-    bn_finalize_kernel<<<ceil_div(L.C, 128), 128, 0, s>>>(ws, chunks, L, update_moving);
+    bn_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(ws, chunks, L, update_moving);
     AMS_LAUNCH_CHECK();
     return 0;
 }
@@ -415,7 +454,7 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     float* coef = reinterpret_cast<float*>(ws + static_cast<size_t>(chunks) * 2 * L.C);
     bn_bwd_reduce_kernel<<<chunks, kRedThreads, smem, s>>>(dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     AMS_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<ceil_div(L.C, 128), 128, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
+    bn_bwd_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
     AMS_LAUNCH_CHECK();
     const long long total8 = L.M * L.C / 8;
     bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s>>>(dy, dy2, z, L.scale, L.shift, coef, act, total8, L.C, dz_out);
@@ -423,29 +462,44 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     return 0;
 }
 
-int colsum_groups(const float* xf, const bf16* xb, int ld, long long rows_per_group, int groups, int C, float* out,
-                  cudaStream_t s) {
-    dim3 grid(groups, ceil_div(C, 64));
-    colsum_groups_kernel<<<grid, 256, 0, s>>>(xf, xb, ld, rows_per_group, C, out);
+int colsum_groups(const float* xf, const bf16* xb, int ld, long long rows_per_group, int groups, int C, float scale,
+                  float* out, double* workspace, cudaStream_t s) {
+    dim3 grid(groups, ceil_div(C, 64), kColsumSplits);
+    colsum_partial_kernel<<<grid, 256, 0, s>>>(xf, xb, ld, rows_per_group, C, workspace);
+    AMS_LAUNCH_CHECK();
+    colsum_final_kernel<<<ceil_div(groups * C, 128), 128, 0, s>>>(workspace, groups, C, scale, out);
     AMS_LAUNCH_CHECK();
     return 0;
 }
+size_t colsum_workspace_doubles(int groups, int C) { return static_cast<size_t>(groups) * kColsumSplits * C; }
 
 int imgpool_forward(const ImgPoolFwd& a, cudaStream_t s) {
     // pooled[n][c] = mean over HW of feat
-    if (colsum_groups(nullptr, a.feat, a.Cin, a.HW, a.N, a.Cin, a.pooled, s)) return -1;
-    scale_rows_kernel<<<ceil_div(a.N * a.Cin, 256), 256, 0, s>>>(a.pooled, a.N * a.Cin, 1.f / static_cast<float>(a.HW));
+    if (colsum_groups(nullptr, a.feat, a.Cin, a.HW, a.N, a.Cin, 1.f / static_cast<float>(a.HW), a.pooled, a.ws, s)) return -1;
+    small_fc_kernel<<<ceil_div(a.N * a.Cmid, 256), 256, 0, s>>>(a.pooled, a.w_pool, a.N, a.Cin, a.Cmid, a.z);
     AMS_LAUNCH_CHECK();
-    imgpool_fwd_kernel<<<1, 256, 0, s>>>(a);
+    imgpool_bn_kernel<<<ceil_div(a.Cmid, 256), 256, 0, s>>>(a);
+    AMS_LAUNCH_CHECK();
+    small_fc_kernel<<<ceil_div(a.N * a.Cout, 256), 256, 0, s>>>(a.act, a.w_proj_top, a.N, a.Cmid, a.Cout, a.bias_img);
     AMS_LAUNCH_CHECK();
     return 0;
 }
 
 int imgpool_backward(const ImgPoolBwd& b, cudaStream_t s) {
     const ImgPoolFwd& a = b.f;
-    if (colsum_groups(nullptr, b.dz_proj, a.Cout, a.HW, a.N, a.Cout, b.dbias, s)) return -1;
-    // dact scratch lives right after dbias (caller allocates N*(Cout+Cmid) floats)
-    imgpool_bwd_kernel<<<1, 256, 0, s>>>(b, b.dbias + static_cast<size_t>(a.N) * a.Cout);
+    float* dact = b.dbias + static_cast<size_t>(a.N) * a.Cout;       // caller allocates N*(Cout+Cmid) floats
+    if (colsum_groups(nullptr, b.dz_proj, a.Cout, a.HW, a.N, a.Cout, 1.f, b.dbias, a.ws, s)) return -1;
+    // d act = relu'(act) * dbias * w_proj_top^T ;  d w_proj_top = act^T dbias
+    small_fc_t_kernel<<<ceil_div(a.N * a.Cmid * 32, 256), 256, 0, s>>>(b.dbias, a.w_proj_top, a.act, a.N, a.Cmid, a.Cout, 1.f, dact);
+    AMS_LAUNCH_CHECK();
+    small_outer_kernel<<<ceil_div(a.Cmid * a.Cout, 256), 256, 0, s>>>(a.act, b.dbias, a.N, a.Cmid, a.Cout, b.d_w_proj_top);
+    AMS_LAUNCH_CHECK();
+    imgpool_bn_bwd_kernel<<<ceil_div(a.Cmid, 256), 256, 0, s>>>(a, dact, b.d_gamma, b.d_beta);
+    AMS_LAUNCH_CHECK();
+    small_outer_kernel<<<ceil_div(a.Cin * a.Cmid, 256), 256, 0, s>>>(a.pooled, dact, a.N, a.Cin, a.Cmid, b.d_w_pool);
+    AMS_LAUNCH_CHECK();
+    small_fc_t_kernel<<<ceil_div(a.N * a.Cin * 32, 256), 256, 0, s>>>(dact, a.w_pool, nullptr, a.N, a.Cin, a.Cmid,
+                                                                      1.f / static_cast<float>(a.HW), b.dfeat_rowbias);
     AMS_LAUNCH_CHECK();
     return 0;
 }

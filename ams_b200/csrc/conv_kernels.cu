@@ -120,12 +120,15 @@ stem_bwd_filter_kernel(const T* __restrict__ in, StemGeom g, const bf16* __restr
     o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int chunks) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// out[i] = sum over chunks of partial[chunk][i]; one warp per output, fixed lane assignment (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int chunks) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     double acc = 0.0;
-    for (int c = 0; c < chunks; ++c) acc += static_cast<double>(partial[static_cast<long long>(c) * n + i]);
-    out[i] = static_cast<float>(acc);
+    for (int c = lane; c < chunks; c += 32) acc += static_cast<double>(partial[static_cast<long long>(c) * n + i]);
+    acc = warp_sum_d(acc);
+    if (lane == 0) out[i] = static_cast<float>(acc);
 }
 
 // ============================================================================================ depthwise
@@ -246,75 +249,99 @@ dw_bwd_data_kernel(const bf16* __restrict__ dz, const float* __restrict__ w, Con
     stg_stream(dx + ((static_cast<long long>(n) * g.H + iy) * g.W + ix) * g.C + c0, pack8(acc));
 }
 
-// dW[ky,kx,c] = sum_{n,oy,ox} x[iy,ix,c] * dz[oy,ox,c].  block = (32 channel-groups) x (8 pixel lanes);
-// each block owns a contiguous run of output pixels, partial [chunk][9][C] reduced in fixed order afterwards.
-constexpr int kDwBwdLanesC = 32, kDwBwdLanesP = 4;
-__global__ void __launch_bounds__(kDwBwdLanesC * kDwBwdLanesP)
+// dW[ky,kx,c] = sum_{n,oy,ox} x[iy,ix,c] * dz[oy,ox,c].
+// thread = one 8-channel group x a strip of TW consecutive output pixels (register sliding window over the input
+// columns the strip touches); a block holds 256/min(C/8,256) strips side by side, each block owns a contiguous run
+// of strips, partial [block][9][C] is reduced in fixed order afterwards (deterministic).
+constexpr int kDwfTW = 4;
+template <int S, int D>
+__global__ void __launch_bounds__(256, 2)
 dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Conv2dGeom g, float* __restrict__ partial,
-                     int pix_per_block) {
-    __shared__ float s_red[kDwBwdLanesP][kDwBwdLanesC][9 * 8 + 1];
+                     int strips_per_block) {
+    extern __shared__ float s_red[];                       // [rows_in_block][tpr][73]
+    constexpr int TW = kDwfTW;
+    constexpr int NCOLS = (TW - 1) * S + 2 * D + 1;
     const int C8 = g.C >> 3;
-    const int lc = threadIdx.x % kDwBwdLanesC, lp = threadIdx.x / kDwBwdLanesC;
-    const int c8 = blockIdx.y * kDwBwdLanesC + lc;
-    const bool c_ok = c8 < C8;
-    const int c0 = c8 * 8;
+    const int tpr = min(C8, 256);
+    const int rows_in_block = 256 / tpr;
+    const int lr = threadIdx.x / tpr, lc = threadIdx.x % tpr;
+    const int WG = (g.Wo + TW - 1) / TW;
+    const long long total = static_cast<long long>(g.N) * g.Ho * WG;
+    const long long s_begin = static_cast<long long>(blockIdx.x) * strips_per_block;
+    const long long s_end = min(s_begin + strips_per_block, total);
+    const int c0 = lc * 8;
     float acc[9][8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[t][q] = 0.f;
-    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
-    const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_block;
-    const long long p_end = min(p_begin + pix_per_block, total);
-    if (c_ok) {
-        for (long long pix = p_begin + lp; pix < p_end; pix += kDwBwdLanesP) {
-            const int ox = static_cast<int>(pix % g.Wo);
-            const int oy = static_cast<int>((pix / g.Wo) % g.Ho);
-            const int n = static_cast<int>(pix / (static_cast<long long>(g.Wo) * g.Ho));
-            float d[8];
-            unpack8(ldg_stream(dz + pix * g.C + c0), d);
+    if (lr < rows_in_block) {
+        for (long long sidx = s_begin + lr; sidx < s_end; sidx += rows_in_block) {
+            const int xg = static_cast<int>(sidx % WG);
+            const int oy = static_cast<int>((sidx / WG) % g.Ho);
+            const int n = static_cast<int>(sidx / (static_cast<long long>(WG) * g.Ho));
+            const int ox0 = xg * TW;
+            float d[TW][8];
+#pragma unroll
+            for (int t = 0; t < TW; ++t) {
+                if (ox0 + t < g.Wo) unpack8(ldg_stream(dz + ((static_cast<long long>(n) * g.Ho + oy) * g.Wo + ox0 + t) * g.C + c0), d[t]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) d[t][q] = 0.f;
+                }
+            }
+            const int ix0 = ox0 * S - g.pad_left;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
-                const int iy = oy * g.stride - g.pad_top + ky * g.dil;
+                const int iy = oy * S - g.pad_top + ky * D;
                 if (iy < 0 || iy >= g.H) continue;
+                const bf16* row = x + ((static_cast<long long>(n) * g.H + iy) * g.W) * g.C + c0;
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = ox * g.stride - g.pad_left + kx * g.dil;
+                for (int j = 0; j < NCOLS; ++j) {
+                    bool used = false;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) used = used || ((j - kx * D) >= 0 && (j - kx * D) % S == 0 && (j - kx * D) / S < TW);
+                    if (!used) continue;
+                    const int ix = ix0 + j;
                     if (ix < 0 || ix >= g.W) continue;
                     float v[8];
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((static_cast<long long>(n) * g.H + iy) * g.W + ix) * g.C + c0)), v);
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * g.C)), v);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[ky * 3 + kx][q] = fmaf(v[q], d[q], acc[ky * 3 + kx][q]);
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int tt = j - kx * D;
+                        if (tt >= 0 && tt % S == 0 && tt / S < TW) {
+                            const int t = tt / S;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) acc[ky * 3 + kx][q] = fmaf(v[q], d[t][q], acc[ky * 3 + kx][q]);
+                        }
+                    }
                 }
             }
         }
+        float* dst = s_red + (static_cast<size_t>(lr) * tpr + lc) * 73;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[t * 8 + q] = acc[t][q];
     }
-#pragma unroll
-    for (int t = 0; t < 9; ++t)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s_red[lp][lc][t * 8 + q] = acc[t][q];
     __syncthreads();
-    // thread (lp, lc): sum the kDwBwdLanesP pixel lanes for 9 of the 72 (tap, q) entries
-    if (c_ok) {
-        for (int e = lp; e < 72; e += kDwBwdLanesP) {
-            float sum = 0.f;
-#pragma unroll
-            for (int l = 0; l < kDwBwdLanesP; ++l) sum += s_red[l][lc][e];
-            const int t = e / 8, q = e % 8;
-            partial[(static_cast<long long>(blockIdx.x) * 9 + t) * g.C + c0 + q] = sum;
-        }
+    for (int e = threadIdx.x; e < tpr * 72; e += 256) {
+        const int cc = e / 72, k = e % 72;
+        float sum = 0.f;
+        for (int l = 0; l < rows_in_block; ++l) sum += s_red[(static_cast<size_t>(l) * tpr + cc) * 73 + k];
+        partial[(static_cast<long long>(blockIdx.x) * 9 + k / 8) * g.C + cc * 8 + (k % 8)] = sum;
     }
 }
 
 int blocks_for(long long total, int threads) { return static_cast<int>((total + threads - 1) / threads); }
 
 constexpr int kStemPixPerBlock = 2048;
-int dw_pix_per_block(const Conv2dGeom& g) {
-    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
-    const int cgroups = ceil_div(g.C / 8, kDwBwdLanesC);
-    long long want_blocks = std::max<long long>(1, (4LL * kNumSMs) / cgroups);
-    long long ppb = std::max<long long>(64, ceil_div_ll(total, want_blocks));
-    return static_cast<int>(ppb);
+int dw_strips_per_block(const Conv2dGeom& g) {
+    const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, kDwfTW);
+    const int rows_in_block = 256 / std::min(g.C / 8, 256);
+    const long long want_blocks = 4LL * kNumSMs;
+    long long spb = std::max<long long>(rows_in_block * 4LL, ceil_div_ll(total, want_blocks));
+    return static_cast<int>(spb);
 }
 
 }  // namespace
@@ -350,7 +377,7 @@ int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int 
     else
         stem_bwd_filter_kernel<float><<<chunks, kStemBwdThreads, 0, s>>>(static_cast<const float*>(in), g, dz, workspace, kStemPixPerBlock);
     AMS_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div(864, 256), 256, 0, s>>>(workspace, dw, 864, chunks);
+    reduce_partials_kernel<<<ceil_div(864 * 32, 256), 256, 0, s>>>(workspace, dw, 864, chunks);
     AMS_LAUNCH_CHECK();
     return 0;
 }
@@ -381,21 +408,32 @@ int dw_conv_bwd_data(const bf16* dz, const float* w, const Conv2dGeom& g, bf16* 
 }
 
 size_t dw_bwd_workspace_floats(const Conv2dGeom& g) {
-    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
-    const int ppb = dw_pix_per_block(g);
-    return static_cast<size_t>(ceil_div_ll(total, ppb)) * 9 * g.C;
+    const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, kDwfTW);
+    return static_cast<size_t>(ceil_div_ll(total, dw_strips_per_block(g))) * 9 * g.C;
 }
 
 int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
                        size_t workspace_floats, cudaStream_t s) {
-    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
-    const int ppb = dw_pix_per_block(g);
-    const int chunks = static_cast<int>(ceil_div_ll(total, ppb));
+    AMS_REQUIRE(g.C % 8 == 0 && g.C / 8 <= 256, "depthwise channels must be a multiple of 8, at most 2048");
+    const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, kDwfTW);
+    const int spb = dw_strips_per_block(g);
+    const int chunks = static_cast<int>(ceil_div_ll(total, spb));
     AMS_REQUIRE(workspace_floats >= static_cast<size_t>(chunks) * 9 * g.C, "depthwise bwd workspace too small");
-    dim3 grid(chunks, ceil_div(g.C / 8, kDwBwdLanesC));
-    dw_bwd_filter_kernel<<<grid, kDwBwdLanesC * kDwBwdLanesP, 0, s>>>(x, dz, g, workspace, ppb);
+    const int tpr = std::min(g.C / 8, 256);
+    const size_t smem = static_cast<size_t>(256 / tpr) * tpr * 73 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_bwd_filter_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_bwd_filter_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_bwd_filter_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        attr = true;
+    }
+    if (g.stride == 1 && g.dil == 1) dw_bwd_filter_kernel<1, 1><<<chunks, 256, smem, s>>>(x, dz, g, workspace, spb);
+    else if (g.stride == 2 && g.dil == 1) dw_bwd_filter_kernel<2, 1><<<chunks, 256, smem, s>>>(x, dz, g, workspace, spb);
+    else if (g.stride == 1 && g.dil == 2) dw_bwd_filter_kernel<1, 2><<<chunks, 256, smem, s>>>(x, dz, g, workspace, spb);
+    else AMS_REQUIRE(false, "unsupported depthwise stride/dilation");
     AMS_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div(9 * g.C, 256), 256, 0, s>>>(workspace, dw, 9 * g.C, chunks);
+    reduce_partials_kernel<<<ceil_div(9 * g.C * 32, 256), 256, 0, s>>>(workspace, dw, 9 * g.C, chunks);
     AMS_LAUNCH_CHECK();
     return 0;
 }

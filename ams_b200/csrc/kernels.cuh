@@ -70,6 +70,7 @@ struct ImgPoolFwd {
     float* z;                    // [N][Cmid]  saved (pre-BN)
     float* act;                  // [N][Cmid]  saved (post relu)
     float* bias_img;             // [N][Cout]  -> rowbias of concat_projection
+    double* ws;                  // colsum_workspace_doubles(N, max(Cin, Cout))
 };
 int imgpool_forward(const ImgPoolFwd& a, cudaStream_t s);
 struct ImgPoolBwd {
@@ -116,7 +117,8 @@ int head_loss_backward(const float* logits, const HeadGeom& g, const uint8_t* la
 // ---- generic reductions
 // colsum[g][c] = sum over rows of group g (rows_per_group consecutive rows) of x[row][c]   (deterministic)
 int colsum_groups(const float* x_f32, const bf16* x_bf16, int ld, long long rows_per_group, int groups, int C,
-                  float* out, cudaStream_t s);
+                  float scale, float* out, double* workspace, cudaStream_t s);
+size_t colsum_workspace_doubles(int groups, int C);
 
 // ---- optimizer / selection / delta
 int adam_masked(float* p, const float* g, float grad_scale, float* m, float* v, const uint8_t* mask, long long n,

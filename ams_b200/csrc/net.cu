@@ -243,6 +243,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
         if (dev_alloc(&p->bias_img, static_cast<size_t>(N) * 256, &p->allocations)) return -1;
         if (dev_alloc(&p->ip_dbias, static_cast<size_t>(N) * (256 + ipd.cout), &p->allocations)) return -1;
         if (dev_alloc(&p->dfeat_rowbias, static_cast<size_t>(N) * ipd.cin, &p->allocations)) return -1;
+        if (dev_alloc(&p->small_ws, colsum_workspace_doubles(std::max(N, 1), 512), &p->allocations)) return -1;
         // forward GEMM plans
         for (size_t i = 0; i < L.size(); ++i) {
             const LayerDef& d = L[i];
@@ -357,7 +358,7 @@ static ImgPoolFwd imgpool_desc(Net* net, Plan* p, bool frozen, bool update_movin
     a.w_proj_top = net->params + cp.w_off;
     a.bn = bn_layer(net, d, p->N);
     a.frozen = frozen; a.update_moving = update_moving;
-    a.pooled = p->pooled; a.z = p->ip_z; a.act = p->ip_act; a.bias_img = p->bias_img;
+    a.pooled = p->pooled; a.z = p->ip_z; a.act = p->ip_act; a.bias_img = p->bias_img; a.ws = p->small_ws;
     return a;
 }
 
@@ -420,7 +421,7 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     const long long M16 = static_cast<long long>(p->N) * lg.out_h * lg.out_w;
     PROF("head_loss_bwd", static_cast<double>(p->N) * c.height * c.width + 4.0 * M16 * 32 * 2,
          head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s));
-    PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, net->grads + lg.bias_off, s));
+    PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
     PROF("gemm_wgrad", 2.0 * M16 * (lg.cin + 32), wgrad_launch(p->wgrad[nl - 1], s));
     PROF("gemm_dgrad", 2.0 * M16 * (lg.cin + 32), gemm_launch(p->dgrad[nl - 1], s));
     for (int i = nl - 2; i >= 0; --i) {

@@ -58,7 +58,7 @@ struct Plan {
     float* loss_dev = nullptr;
     // image pooling scratch
     float *pooled = nullptr, *ip_z = nullptr, *ip_act = nullptr, *bias_img = nullptr, *ip_dbias = nullptr, *dfeat_rowbias = nullptr;
-    double* bn_ws = nullptr;
+    double* bn_ws = nullptr; double* small_ws = nullptr;
     float* red_ws = nullptr; size_t red_ws_floats = 0;
     std::vector<GemmPlan> fwd_frozen, fwd_train, dgrad;
     std::vector<WgradPlan> wgrad;
