@@ -13,11 +13,13 @@ constexpr int kRedThreads = 256;
 constexpr int kFlush = 16;          // fp32 run length before flushing into fp64
 
 int red_chunks(long long M, int C) {
-    // enough blocks to fill the machine (4 per SM) while every thread still walks >= 8 rows
+    // enough blocks to fill the machine while every thread still walks >= 8 rows; the partial matrix
+    // (chunks x 2C doubles) is kept small so that the one-warp-per-channel finalize stays cheap
     const int c8 = C / 8;
     const int rows_per_block = std::max(1, kRedThreads / std::min(c8, kRedThreads));
-    long long want = std::max<long long>(1, std::min<long long>(4 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8)));
-    return static_cast<int>(want);
+    long long want = std::min<long long>(4 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8));
+    want = std::min<long long>(want, std::max<long long>(kNumSMs, 65536 / C));
+    return static_cast<int>(std::max<long long>(1, want));
 }
 
 // partial[chunk][0][c] = sum z, partial[chunk][1][c] = sum z^2 over the rows of the chunk
@@ -117,7 +119,7 @@ bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, con
                 const bf16* __restrict__ residual, bf16* __restrict__ y, long long total8, int C) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total8) return;
-    const int c0 = static_cast<int>((i * 8) % C);
+    const int c0 = static_cast<int>(i % (C >> 3)) * 8;
     float v[8];
     unpack8(ldg_stream(z + i * 8), v);
     const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
@@ -253,26 +255,34 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L
     coef[2 * L.C + c] = static_cast<float>(Cc);
 }
 
+__device__ __forceinline__ void load8f(const float* p, float* o) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
                     int act, long long total8, int C, bf16* dz_out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total8) return;
-    const int c0 = static_cast<int>((i * 8) % C);
-    float g[8], v[8];
+    const int c8n = C >> 3;
+    const int c0 = static_cast<int>(i % c8n) * 8;
+    float g[8], v[8], sc[8], sh[8], ca[8], cb[8], cc[8];
     unpack8(*reinterpret_cast<const uint4*>(dy + i * 8), g);      // may alias dz_out: plain load
+    unpack8(ldg_stream(z + i * 8), v);
+    load8f(scale + c0, sc); load8f(shift + c0, sh);
+    load8f(coef + c0, ca); load8f(coef + C + c0, cb); load8f(coef + 2 * C + c0, cc);
     if (dy2) {
         float g2[8];
         unpack8(ldg_stream(dy2 + i * 8), g2);
 #pragma unroll
         for (int q = 0; q < 8; ++q) g[q] += g2[q];
     }
-    unpack8(ldg_stream(z + i * 8), v);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const float gm = act_mask(g[q], fmaf(v[q], scale[c0 + q], shift[c0 + q]), act);
-        g[q] = fmaf(coef[c0 + q], gm, fmaf(coef[C + c0 + q], v[q], coef[2 * C + c0 + q]));
+        const float gm = act_mask(g[q], fmaf(v[q], sc[q], sh[q]), act);
+        g[q] = fmaf(ca[q], gm, fmaf(cb[q], v[q], cc[q]));
     }
     stg_stream(dz_out + i * 8, pack8(g));
 }

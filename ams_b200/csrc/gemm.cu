@@ -355,13 +355,29 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int lddw,
-                                    int splits, long long split_stride) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= static_cast<long long>(Cin) * Cout) return;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[s * split_stride + i];     // fixed order => deterministic
-    dw[(i / Cout) * lddw + (i % Cout)] = acc;
+// 4 consecutive outputs per thread (float4 loads of the split-K partials), fixed split order => deterministic
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int lddw, int splits,
+                    long long split_stride) {
+    const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    const long long n = static_cast<long long>(Cin) * Cout;
+    if (i4 >= n) return;
+    if ((Cout & 3) == 0) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int s = 0; s < splits; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(ws + s * split_stride + i4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float* o = dw + (i4 / Cout) * lddw + (i4 % Cout);
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
+    } else {
+        for (long long i = i4; i < min(i4 + 4, n); ++i) {
+            float acc = 0.f;
+            for (int s = 0; s < splits; ++s) acc += ws[s * split_stride + i];
+            dw[(i / Cout) * lddw + (i % Cout)] = acc;
+        }
+    }
 }
 
 }  // namespace
@@ -477,7 +493,7 @@ int wgrad_launch(const WgradPlan& pl, cudaStream_t stream) {
     AMS_LAUNCH_CHECK();
     if (pl.splits > 1) {
         const long long n = static_cast<long long>(d.Cin) * d.Cout;
-        wgrad_reduce_kernel<<<int(ceil_div_ll(n, 256)), 256, 0, stream>>>(d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
+        wgrad_reduce_kernel<<<int(ceil_div_ll(n, 1024)), 256, 0, stream>>>(d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
                                                                           pl.splits, p.split_stride);
         AMS_LAUNCH_CHECK();
     }
