@@ -420,7 +420,9 @@ imgpool_bn_bwd_kernel(ImgPoolFwd a, float* __restrict__ dact, float* __restrict_
 
 // ============================================================================================ host
 size_t bn_workspace_doubles(long long M, int C) {
-    return static_cast<size_t>(red_chunks(M, C)) * 2 * C + 3 * static_cast<size_t>(C);   // partials + coef (as floats inside)
+    // partials (reduction chunks, or one slab per CTA of a producer kernel with fused statistics) + coef
+    const size_t chunks = std::max<size_t>(red_chunks(M, C), 2 * kNumSMs);
+    return chunks * 2 * C + 3 * static_cast<size_t>(C);
 }
 
 static size_t red_smem(int C) {
@@ -437,6 +439,12 @@ int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double*
     bn_stats_kernel<<<chunks, kRedThreads, smem, s>>>(z, L.M, L.C, rpc, ws);
     AMS_LAUNCH_CHECK();
     bn_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(ws, chunks, L, update_moving);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, int update_moving, cudaStream_t s) {
+    bn_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(partial, chunks, L, update_moving);
     AMS_LAUNCH_CHECK();
     return 0;
 }

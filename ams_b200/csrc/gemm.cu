@@ -17,6 +17,7 @@
 
 #include <cudaTypedefs.h>
 #include <algorithm>
+#include <cstdlib>
 
 namespace ams {
 namespace {
@@ -233,6 +234,225 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // =============================================================================================
+//                     K-major GEMM v2: shared-memory staged epilogue, TMA store, fused BN statistics
+// =============================================================================================
+// 10 warps: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue (two warps per TMEM
+// lane quarter, alternating 16-column chunks).  The bf16 output tile is staged in shared memory in the
+// SWIZZLE_128B layout of the output tensor map (bank-conflict-free 16-byte writes), optionally reduced column-wise
+// for the BatchNorm batch statistics, and written with cp.async.bulk.tensor (full-line coalesced HBM writes, M/N
+// tails clipped by the TMA unit).
+constexpr int kGemm2Threads = 320;
+constexpr int kEpiThreads = 256;
+
+struct Gemm2Params {
+    int M, N, K;
+    int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc, stage_bufs, nboxes;
+    uint32_t tmem_cols;
+    const float* scale; const float* shift; const float* rowbias; int rows_per_image;
+    const __nv_bfloat16* residual; int ldr;
+    int act;
+    double* stats_partial;
+};
+
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_a = BLOCK_M * BLOCK_K * 2;
+    const int stage_b = p.block_n * BLOCK_K * 2;
+    const int cbuf_bytes = p.nboxes * BLOCK_M * 128;                  // one staging buffer: nboxes x [128 rows][128 B]
+    uint8_t* smA = smem;
+    uint8_t* smB = smA + p.stages * stage_a;
+    uint8_t* smC = smB + p.stages * stage_b;                          // 1024-aligned (stage sizes are multiples of 2 KB)
+    float* s_scale = reinterpret_cast<float*>(smC + p.stage_bufs * cbuf_bytes);
+    float* s_shift = s_scale + p.n_alloc;
+    double* s_run = reinterpret_cast<double*>(s_shift + p.n_alloc);   // [2][n_alloc] running column sums of this CTA
+    float2* s_part = reinterpret_cast<float2*>(s_run + 2 * p.n_alloc);   // [16 slices][block_n]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + 16 * p.block_n);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        t5::tma_prefetch_desc(&tmA);
+        t5::tma_prefetch_desc(&tmB);
+        t5::tma_prefetch_desc(&tmC);
+        for (int s = 0; s < p.stages; ++s) { t5::mbar_init(&full_bar[s], 1); t5::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { t5::mbar_init(&tfull_bar[s], 1); t5::mbar_init(&tempty_bar[s], kEpiThreads); }
+        t5::fence_barrier_init();
+    }
+    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
+    for (int n = threadIdx.x; n < p.n_alloc; n += kGemm2Threads) {
+        s_scale[n] = (n < p.N) ? (p.scale ? p.scale[n] : 1.f) : 0.f;
+        s_shift[n] = (n < p.N && p.shift) ? p.shift[n] : 0.f;
+        s_run[n] = 0.0;
+        s_run[p.n_alloc + n] = 0.0;
+    }
+    t5::fence_before_thread_sync();
+    __syncthreads();
+    t5::fence_after_thread_sync();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
+                for (int kb = 0; kb < p.k_blocks; ++kb) {
+                    t5::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + stage_b);
+                    t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+                    t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+            t5::mbar_wait(&tempty_bar[as], aphase ^ 1);
+            t5::fence_after_thread_sync();
+            const uint32_t tmem_d = tmem_base + as * p.block_n;
+            for (int kb = 0; kb < p.k_blocks; ++kb) {
+                t5::mbar_wait(&full_bar[stage], phase);
+                t5::fence_after_thread_sync();
+                if (lane == 0) {
+                    const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
+                    const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                        t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
+                    }
+                    t5::mma_commit(&empty_bar[stage]);
+                    if (kb == p.k_blocks - 1) t5::mma_commit(&tfull_bar[as]);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        const int et = threadIdx.x - 64;              // 0..255
+        const int q = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;             // which of the two warps of this quarter
+        const int row = q * 32 + lane;
+        const int nchunks = p.block_n >> 4;
+        // statistics slicing: nslices * block_n <= 256 threads, nslices a power of two <= 16
+        int nslices = 1;
+        while (nslices < 16 && nslices * 2 * p.block_n <= kEpiThreads) nslices <<= 1;
+        const int rows_per_slice = BLOCK_M / nslices;
+        int it = 0, buf = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
+            const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+            uint8_t* cbuf = smC + buf * cbuf_bytes;
+            // the TMA store that last read this staging buffer must have finished reading it
+            if (et == 0) { if (p.stage_bufs == 2) t5::tma_store_wait_read<1>(); else t5::tma_store_wait_read<0>(); }
+            t5::named_barrier_sync(1, kEpiThreads);
+            t5::mbar_wait(&tfull_bar[as], aphase);
+            t5::fence_after_thread_sync();
+            const long long m = static_cast<long long>(m_tile) * BLOCK_M + row;
+            const bool row_ok = m < p.M;
+            const float* rb = nullptr;
+            if (p.rowbias && row_ok) rb = p.rowbias + (m / p.rows_per_image) * p.N;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.block_n;
+            for (int j = half; j < nchunks; j += 2) {
+                const int c0 = j << 4;
+                uint32_t r[16];
+                t5::tmem_ld16(taddr0 + c0, r);
+                t5::tmem_ld_wait();
+                const int n0 = n_tile * p.block_n + c0;
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = row_ok ? __uint_as_float(r[k]) : 0.f;
+                if (rb) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) if (n0 + k < p.N) v[k] += rb[n0 + k];
+                }
+                if (p.scale || p.shift || p.act) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = act_apply(fmaf(v[k], s_scale[n0 + k], s_shift[n0 + k]), p.act);
+                }
+                if (p.residual && row_ok) {
+                    const __nv_bfloat16* rp = p.residual + m * p.ldr + n0;
+                    float f[8];
+                    if (n0 < p.N) {
+                        unpack8(ldg_stream(rp), f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] += f[k];
+                    }
+                    if (n0 + 8 < p.N) {
+                        unpack8(ldg_stream(rp + 8), f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[8 + k] += f[k];
+                    }
+                }
+                // swizzled staging write: box = 64 columns, 16-byte chunk index XOR (row & 7)
+                uint8_t* rowp = cbuf + (c0 >> 6) * (BLOCK_M * 128) + row * 128;
+                const int ci = (c0 & 63) >> 3;
+                *reinterpret_cast<uint4*>(rowp + ((ci ^ (row & 7)) << 4)) = pack8(v);
+                *reinterpret_cast<uint4*>(rowp + (((ci + 1) ^ (row & 7)) << 4)) = pack8(v + 8);
+            }
+            t5::fence_before_thread_sync();
+            t5::mbar_arrive(&tempty_bar[as]);                    // TMEM stage free for the next MMAs
+            t5::fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA unit
+            t5::named_barrier_sync(2, kEpiThreads);
+            if (p.stats_partial) {
+                // column statistics of the stored bf16 tile: thread = (slice of rows, column)
+                const int c = et % p.block_n, slice = et / p.block_n;
+                if (slice < nslices) {
+                    const uint8_t* colp = cbuf + (c >> 6) * (BLOCK_M * 128) + (c & 7) * 2;
+                    const int ci = (c & 63) >> 3;
+                    float s = 0.f, sq = 0.f;
+                    const int r0 = slice * rows_per_slice;
+#pragma unroll 8
+                    for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
+                        const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((ci ^ (rr & 7)) << 4)));
+                        s += x;
+                        sq = fmaf(x, x, sq);
+                    }
+                    s_part[slice * p.block_n + c] = make_float2(s, sq);
+                }
+                t5::named_barrier_sync(3, kEpiThreads);
+                if (et < p.block_n) {
+                    double s = 0.0, sq = 0.0;
+                    for (int sl = 0; sl < nslices; ++sl) { const float2 v2 = s_part[sl * p.block_n + et]; s += v2.x; sq += v2.y; }
+                    s_run[n_tile * p.block_n + et] += s;
+                    s_run[p.n_alloc + n_tile * p.block_n + et] += sq;
+                }
+            }
+            if (et == 0) {
+                for (int b = 0; b < p.nboxes; ++b)
+                    t5::tma_store_2d(&tmC, cbuf + b * (BLOCK_M * 128), n_tile * p.block_n + b * 64, m_tile * BLOCK_M);
+                t5::tma_store_commit();
+            }
+            if (p.stage_bufs == 2) buf ^= 1;
+        }
+        if (et == 0) t5::tma_store_wait_all<0>();
+        if (p.stats_partial) {
+            t5::named_barrier_sync(1, kEpiThreads);
+            double* dst = p.stats_partial + static_cast<long long>(blockIdx.x) * 2 * p.N;
+            for (int n = et; n < p.N; n += kEpiThreads) { dst[n] = s_run[n]; dst[p.N + n] = s_run[p.n_alloc + n]; }
+        }
+    }
+    t5::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) {
+        t5::fence_after_thread_sync();
+        t5::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+// =============================================================================================
 //                                   MN-major split-K GEMM (wgrad)
 // =============================================================================================
 struct WgradKParams {
@@ -383,6 +603,12 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Ci
 }  // namespace
 
 // ============================================================================================= host
+static bool use_v1() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("AMS_GEMM_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
 int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     AMS_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "empty GEMM");
     AMS_REQUIRE(d.lda % 8 == 0 && d.ldb % 8 == 0, "bf16 operand strides must be multiples of 8 elements");
@@ -390,28 +616,44 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     AMS_REQUIRE(!d.out_fp32 || d.ldc % 4 == 0, "fp32 output needs ldc multiple of 4");
     AMS_REQUIRE(!d.residual || d.ldr % 8 == 0, "residual stride must be a multiple of 8");
     plan->d = d;
-    const int npad = ceil_div(d.N, 16) * 16;
-    int t = ceil_div(npad, 256);
-    while (npad % (16 * t) != 0) ++t;
-    plan->block_n = npad / t;
-    plan->n_tiles = t;
+    plan->v2 = (!d.out_fp32 && !use_v1()) ? 1 : 0;
+    AMS_REQUIRE(plan->v2 || !d.stats_partial, "fused statistics need the bf16 (v2) epilogue");
+    int npad = ceil_div(d.N, 16) * 16;
+    if (npad <= 256) {
+        plan->block_n = npad;
+        plan->n_tiles = 1;
+    } else {
+        // several N tiles: whole 64-column TMA boxes per tile (the last tile is clipped by the tensor extent)
+        const int t = ceil_div(npad, 256);
+        plan->block_n = ceil_div(ceil_div(npad, t), 64) * 64;
+        plan->n_tiles = ceil_div(npad, plan->block_n);
+    }
+    npad = plan->block_n * plan->n_tiles;                       // = n_alloc of the kernels
     plan->m_tiles = ceil_div(d.M, BLOCK_M);
     plan->k_blocks = ceil_div(d.K, BLOCK_K);
     plan->tmem_cols = tmem_cols_for(2 * plan->block_n);
     AMS_REQUIRE(plan->tmem_cols <= 512, "TMEM overflow");
     const size_t stage_bytes = size_t(BLOCK_M) * BLOCK_K * 2 + size_t(plan->block_n) * BLOCK_K * 2;
-    const size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 4) * 8 + 16;
+    size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 4) * 8 + 16;
+    if (plan->v2) {
+        const int nboxes = ceil_div(plan->block_n, 64);
+        plan->stage_bufs = (nboxes <= 2) ? 2 : 1;
+        fixed += size_t(plan->stage_bufs) * nboxes * BLOCK_M * 128 + size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8;
+    }
     int stages = int((kSmemBudget - fixed) / stage_bytes);
     stages = std::max(2, std::min(stages, kMaxStages));
     plan->stages = stages;
     plan->smem_bytes = fixed + stages * stage_bytes;
+    AMS_REQUIRE(plan->smem_bytes <= 227 * 1024, "GEMM shared memory overflow");
     const int tiles = plan->m_tiles * plan->n_tiles;
     plan->grid = std::min(tiles, num_sms);
     if (encode_2d_bf16(&plan->tmA, d.A, d.K, d.M, size_t(d.lda) * 2, BLOCK_K, BLOCK_M)) return -1;
     if (encode_2d_bf16(&plan->tmB, d.B, d.K, d.N, size_t(d.ldb) * 2, BLOCK_K, plan->block_n)) return -1;
+    if (plan->v2 && encode_2d_bf16(&plan->tmC, d.out, d.N, d.M, size_t(d.ldc) * 2, 64, BLOCK_M)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
         AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     return 0;
@@ -419,6 +661,19 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
 
 int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
     const GemmDesc& d = pl.d;
+    if (pl.v2) {
+        Gemm2Params p;
+        p.M = d.M; p.N = d.N; p.K = d.K;
+        p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;
+        p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.n_alloc = pl.n_tiles * pl.block_n;
+        p.stage_bufs = pl.stage_bufs; p.nboxes = ceil_div(pl.block_n, 64);
+        p.tmem_cols = pl.tmem_cols;
+        p.scale = d.scale; p.shift = d.shift; p.rowbias = d.rowbias; p.rows_per_image = d.rows_per_image;
+        p.residual = d.residual; p.ldr = d.ldr; p.act = d.act; p.stats_partial = d.stats_partial;
+        gemm_kmajor_v2_kernel<<<pl.grid, kGemm2Threads, pl.smem_bytes, stream>>>(pl.tmA, pl.tmB, pl.tmC, p);
+        AMS_LAUNCH_CHECK();
+        return 0;
+    }
     GemmKParams p;
     p.M = d.M; p.N = d.N; p.K = d.K;
     p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;

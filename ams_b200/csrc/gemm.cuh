@@ -20,12 +20,16 @@ struct GemmDesc {
     int rows_per_image = 1;
     const __nv_bfloat16* residual = nullptr; int ldr = 0;
     int act = 0;                       // 0 none, 1 relu, 2 relu6
+    // optional BatchNorm batch statistics of the STORED (bf16-rounded) output, fused into the epilogue:
+    // stats_partial[cta][0][N] = column sums, [cta][1][N] = column sums of squares (one slab per CTA of the grid)
+    double* stats_partial = nullptr;
 };
 
 // A prepared launch: tensor maps encoded once, reused every step (buffers are static in the plan).
 struct GemmPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmC;
     GemmDesc d;
+    int v2 = 0, stage_bufs = 1;
     int block_n = 0, n_tiles = 0, m_tiles = 0, k_blocks = 0, stages = 0, tmem_cols = 0;
     size_t smem_bytes = 0;
     int grid = 0;

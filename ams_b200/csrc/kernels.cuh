@@ -47,6 +47,8 @@ struct BnLayer {            // device pointers into the parameter / state arenas
 size_t bn_workspace_doubles(long long M, int C);
 // batch statistics of z (bf16 [M,C]) -> scale/shift/mean/rstd (+ moving-average update)
 int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double* workspace, cudaStream_t s);
+// same, from per-chunk partial sums a producer kernel already wrote: partial[chunk][0][C] = sum, [chunk][1][C] = sum sq
+int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, int update_moving, cudaStream_t s);
 // y = act(z*scale+shift) (+ residual)
 int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y,
              long long M, int C, cudaStream_t s);

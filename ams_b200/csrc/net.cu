@@ -265,6 +265,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
                 if (gemm_plan(f, net->num_sms, &p->fwd_frozen[i])) return -1;
                 GemmDesc t = g;
                 t.out = p->buf[i].z; t.ldc = d.cout;
+                t.stats_partial = p->bn_ws;                  // BatchNorm batch statistics fused into the epilogue
                 if (gemm_plan(t, net->num_sms, &p->fwd_train[i])) return -1;
             }
             p->has_fwd[i] = 1;
@@ -400,7 +401,10 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
         }
         if (!frozen) {
             BnLayer bl = bn_layer(net, d, M);
-            PROF("bn_stats", out_bytes, bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s));
+            if (d.kind == kConv1x1 && p->fwd_train[i].d.stats_partial)
+                PROF("bn_finalize", 16.0 * p->fwd_train[i].grid * d.cout, bn_finalize_partials(p->bn_ws, p->fwd_train[i].grid, bl, update_moving ? 1 : 0, s));
+            else
+                PROF("bn_stats", out_bytes, bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s));
             PROF("bn_apply", (d.residual >= 0 ? 3.0 : 2.0) * out_bytes,
                  bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s));
         }
