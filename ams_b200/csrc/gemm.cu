@@ -43,18 +43,20 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 // 2-D bf16 tensor [outer][inner] with a 128B-swizzled box; out-of-bounds elements read as zero.
 int encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                   uint32_t box_inner, uint32_t box_outer) {
+                   uint32_t box_inner, uint32_t box_outer, int swizzle_bytes = 128) {
     auto fn = get_encode_fn();
     AMS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
     AMS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
     AMS_REQUIRE(row_stride_bytes % 16 == 0, "TMA row stride must be a multiple of 16 bytes");
-    AMS_REQUIRE(box_inner * 2 <= 128 && box_outer <= 256, "TMA box too large");
+    AMS_REQUIRE(box_inner * 2 <= static_cast<uint32_t>(swizzle_bytes) && box_outer <= 256, "TMA box too large");
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     AMS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
     return 0;
@@ -246,7 +248,9 @@ constexpr int kEpiThreads = 256;
 
 struct Gemm2Params {
     int M, N, K;
-    int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc, stage_bufs, nboxes;
+    int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc, stage_bufs, nboxes, acc_stages, block_k;
+    int linear_out, pitch, cbuf_bytes;          // linear_out: dense padded staging + coalesced copy-out (n_tiles == 1)
+    __nv_bfloat16* out; int ldc;
     uint32_t tmem_cols;
     const float* scale; const float* shift; const float* rowbias; int rows_per_image;
     const __nv_bfloat16* residual; int ldr;
@@ -254,14 +258,22 @@ struct Gemm2Params {
     double* stats_partial;
 };
 
-__global__ void __launch_bounds__(kGemm2Threads, 1)
+enum : int { kEpiAffine = 1, kEpiResidual = 2, kEpiRowBias = 4, kEpiStats = 8 };
+
+__device__ __forceinline__ void lds8(const float* p, float* o) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+template <int F>
+__global__ void __launch_bounds__(kGemm2Threads, 2)
 gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_a = BLOCK_M * BLOCK_K * 2;
-    const int stage_b = p.block_n * BLOCK_K * 2;
-    const int cbuf_bytes = p.nboxes * BLOCK_M * 128;                  // one staging buffer: nboxes x [128 rows][128 B]
+    const int stage_a = BLOCK_M * p.block_k * 2;
+    const int stage_b = p.block_n * p.block_k * 2;
+    const int cbuf_bytes = p.cbuf_bytes;    // TMA mode: nboxes x [128 rows][128 B] swizzled; linear mode: [128 rows][pitch]
     uint8_t* smA = smem;
     uint8_t* smB = smA + p.stages * stage_a;
     uint8_t* smC = smB + p.stages * stage_b;                          // 1024-aligned (stage sizes are multiples of 2 KB)
@@ -306,8 +318,8 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     t5::mbar_wait(&empty_bar[stage], phase ^ 1);
                     t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + stage_b);
-                    t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
-                    t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+                    t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * p.block_k, m_tile * BLOCK_M);
+                    t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * p.block_k, n_tile * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -316,7 +328,8 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
         int stage = 0; uint32_t phase = 0; int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-            const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+            const int as = (p.acc_stages == 2) ? (it & 1) : 0;
+            const uint32_t aphase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
             t5::mbar_wait(&tempty_bar[as], aphase ^ 1);
             t5::fence_after_thread_sync();
             const uint32_t tmem_d = tmem_base + as * p.block_n;
@@ -326,10 +339,11 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (lane == 0) {
                     const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
                     const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
-#pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-                        const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
+                    // K-major swizzled rows of block_k*2 bytes (128/64/32-byte swizzle): 8-row groups SBO apart
+                    const uint32_t sbo = 16u * p.block_k, ltype = p.block_k == 64 ? 2u : (p.block_k == 32 ? 4u : 6u);
+                    for (int k = 0; k < p.block_k / UMMA_K; ++k) {
+                        const uint64_t da = t5::make_smem_desc(a_addr + k * UMMA_K * 2, 16, sbo, ltype);
+                        const uint64_t db = t5::make_smem_desc(b_addr + k * UMMA_K * 2, 16, sbo, ltype);
                         t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
                     }
                     t5::mma_commit(&empty_bar[stage]);
@@ -353,72 +367,119 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         int it = 0, buf = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
-            const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+            const int as = (p.acc_stages == 2) ? (it & 1) : 0;
+            const uint32_t aphase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
             uint8_t* cbuf = smC + buf * cbuf_bytes;
             // the TMA store that last read this staging buffer must have finished reading it
-            if (et == 0) { if (p.stage_bufs == 2) t5::tma_store_wait_read<1>(); else t5::tma_store_wait_read<0>(); }
+            if (!p.linear_out && et == 0) { if (p.stage_bufs == 2) t5::tma_store_wait_read<1>(); else t5::tma_store_wait_read<0>(); }
             t5::named_barrier_sync(1, kEpiThreads);
             t5::mbar_wait(&tfull_bar[as], aphase);
             t5::fence_after_thread_sync();
             const long long m = static_cast<long long>(m_tile) * BLOCK_M + row;
             const bool row_ok = m < p.M;
             const float* rb = nullptr;
-            if (p.rowbias && row_ok) rb = p.rowbias + (m / p.rows_per_image) * p.N;
+            if ((F & kEpiRowBias) && row_ok) rb = p.rowbias + (m / p.rows_per_image) * p.N;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.block_n;
-            for (int j = half; j < nchunks; j += 2) {
+            const float act_lo = p.act ? 0.f : -INFINITY, act_hi = (p.act == 2) ? 6.f : INFINITY;
+            auto process = [&](const uint32_t* r, int j) {
                 const int c0 = j << 4;
-                uint32_t r[16];
-                t5::tmem_ld16(taddr0 + c0, r);
-                t5::tmem_ld_wait();
                 const int n0 = n_tile * p.block_n + c0;
                 float v[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) v[k] = row_ok ? __uint_as_float(r[k]) : 0.f;
-                if (rb) {
+                for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(r[k]);
+                if (row_ok) {
+                    if (F & kEpiRowBias) {
+                        if (n0 + 16 <= p.N) {
+                            float b[8];
+                            lds8(rb + n0, b);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) if (n0 + k < p.N) v[k] += rb[n0 + k];
-                }
-                if (p.scale || p.shift || p.act) {
+                            for (int k = 0; k < 8; ++k) v[k] += b[k];
+                            lds8(rb + n0 + 8, b);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = act_apply(fmaf(v[k], s_scale[n0 + k], s_shift[n0 + k]), p.act);
-                }
-                if (p.residual && row_ok) {
-                    const __nv_bfloat16* rp = p.residual + m * p.ldr + n0;
-                    float f[8];
-                    if (n0 < p.N) {
-                        unpack8(ldg_stream(rp), f);
+                            for (int k = 0; k < 8; ++k) v[8 + k] += b[k];
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] += f[k];
+                            for (int k = 0; k < 16; ++k) if (n0 + k < p.N) v[k] += rb[n0 + k];
+                        }
                     }
-                    if (n0 + 8 < p.N) {
-                        unpack8(ldg_stream(rp + 8), f);
+                    if (F & kEpiAffine) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[8 + k] += f[k];
+                        for (int h8 = 0; h8 < 16; h8 += 8) {
+                            float sc[8], sh[8];
+                            lds8(s_scale + n0 + h8, sc);
+                            lds8(s_shift + n0 + h8, sh);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[h8 + k] = fminf(fmaxf(fmaf(v[h8 + k], sc[k], sh[k]), act_lo), act_hi);
+                        }
                     }
+                    if (F & kEpiResidual) {
+                        const __nv_bfloat16* rp = p.residual + m * p.ldr + n0;
+                        float f[8];
+                        if (n0 < p.N) {
+                            unpack8(ldg_stream(rp), f);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] += f[k];
+                        }
+                        if (n0 + 8 < p.N) {
+                            unpack8(ldg_stream(rp + 8), f);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[8 + k] += f[k];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = 0.f;
                 }
                 // swizzled staging write: box = 64 columns, 16-byte chunk index XOR (row & 7)
-                uint8_t* rowp = cbuf + (c0 >> 6) * (BLOCK_M * 128) + row * 128;
-                const int ci = (c0 & 63) >> 3;
-                *reinterpret_cast<uint4*>(rowp + ((ci ^ (row & 7)) << 4)) = pack8(v);
-                *reinterpret_cast<uint4*>(rowp + (((ci + 1) ^ (row & 7)) << 4)) = pack8(v + 8);
+                if (p.linear_out) {
+                    // dense rows of `pitch` bytes (pitch/16 odd => 8 consecutive rows hit 8 different 16-byte bank groups)
+                    uint8_t* rowp = cbuf + row * p.pitch + c0 * 2;
+                    if (c0 < p.N) *reinterpret_cast<uint4*>(rowp) = pack8(v);
+                    if (c0 + 8 < p.N) *reinterpret_cast<uint4*>(rowp + 16) = pack8(v + 8);
+                } else {
+                    uint8_t* rowp = cbuf + (c0 >> 6) * (BLOCK_M * 128) + row * 128;
+                    const int ci = (c0 & 63) >> 3;
+                    *reinterpret_cast<uint4*>(rowp + ((ci ^ (row & 7)) << 4)) = pack8(v);
+                    *reinterpret_cast<uint4*>(rowp + (((ci + 1) ^ (row & 7)) << 4)) = pack8(v + 8);
+                }
+            };
+            for (int j = half; j < nchunks; j += 4) {
+                // two TMEM loads in flight per wait
+                uint32_t r0[16], r1[16];
+                const bool two = (j + 2) < nchunks;
+                t5::tmem_ld16(taddr0 + (j << 4), r0);
+                if (two) t5::tmem_ld16(taddr0 + ((j + 2) << 4), r1);
+                t5::tmem_ld_wait();
+                process(r0, j);
+                if (two) process(r1, j + 2);
             }
             t5::fence_before_thread_sync();
             t5::mbar_arrive(&tempty_bar[as]);                    // TMEM stage free for the next MMAs
-            t5::fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA unit
+            if (!p.linear_out) t5::fence_proxy_async_smem();     // generic-proxy writes -> visible to the TMA unit
             t5::named_barrier_sync(2, kEpiThreads);
-            if (p.stats_partial) {
+            if (F & kEpiStats) {
                 // column statistics of the stored bf16 tile: thread = (slice of rows, column)
                 const int c = et % p.block_n, slice = et / p.block_n;
                 if (slice < nslices) {
-                    const uint8_t* colp = cbuf + (c >> 6) * (BLOCK_M * 128) + (c & 7) * 2;
-                    const int ci = (c & 63) >> 3;
                     float s = 0.f, sq = 0.f;
                     const int r0 = slice * rows_per_slice;
+                    if (p.linear_out) {
+                        const uint8_t* colp = cbuf + c * 2;
 #pragma unroll 8
-                    for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
-                        const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((ci ^ (rr & 7)) << 4)));
-                        s += x;
-                        sq = fmaf(x, x, sq);
+                        for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
+                            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * p.pitch));
+                            s += x;
+                            sq = fmaf(x, x, sq);
+                        }
+                    } else {
+                        const uint8_t* colp = cbuf + (c >> 6) * (BLOCK_M * 128) + (c & 7) * 2;
+                        const int ci = (c & 63) >> 3;
+#pragma unroll 8
+                        for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
+                            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((ci ^ (rr & 7)) << 4)));
+                            s += x;
+                            sq = fmaf(x, x, sq);
+                        }
                     }
                     s_part[slice * p.block_n + c] = make_float2(s, sq);
                 }
@@ -430,7 +491,17 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     s_run[p.n_alloc + n_tile * p.block_n + et] += sq;
                 }
             }
-            if (et == 0) {
+            if (p.linear_out) {
+                // the tile is one contiguous run of global memory (all N columns, ldc == N): fully coalesced 16-byte stores
+                const int cpr = p.N >> 3;                                   // 16-byte chunks per row
+                const int rows_valid = static_cast<int>(min(static_cast<long long>(BLOCK_M), p.M - static_cast<long long>(m_tile) * BLOCK_M));
+                const int total = rows_valid * cpr;
+                uint4* gdst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(m_tile) * BLOCK_M * p.ldc);
+                for (int i = et; i < total; i += kEpiThreads) {
+                    const int rr = i / cpr, cc = i - rr * cpr;
+                    stg_stream(gdst + i, *reinterpret_cast<const uint4*>(cbuf + rr * p.pitch + (cc << 4)));
+                }
+            } else if (et == 0) {
                 for (int b = 0; b < p.nboxes; ++b)
                     t5::tma_store_2d(&tmC, cbuf + b * (BLOCK_M * 128), n_tile * p.block_n + b * 64, m_tile * BLOCK_M);
                 t5::tma_store_commit();
@@ -438,7 +509,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (p.stage_bufs == 2) buf ^= 1;
         }
         if (et == 0) t5::tma_store_wait_all<0>();
-        if (p.stats_partial) {
+        if (F & kEpiStats) {
             t5::named_barrier_sync(1, kEpiThreads);
             double* dst = p.stats_partial + static_cast<long long>(blockIdx.x) * 2 * p.N;
             for (int n = et; n < p.N; n += kEpiThreads) { dst[n] = s_run[n]; dst[p.N + n] = s_run[p.n_alloc + n]; }
@@ -630,30 +701,42 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     }
     npad = plan->block_n * plan->n_tiles;                       // = n_alloc of the kernels
     plan->m_tiles = ceil_div(d.M, BLOCK_M);
-    plan->k_blocks = ceil_div(d.K, BLOCK_K);
-    plan->tmem_cols = tmem_cols_for(2 * plan->block_n);
-    AMS_REQUIRE(plan->tmem_cols <= 512, "TMEM overflow");
-    const size_t stage_bytes = size_t(BLOCK_M) * BLOCK_K * 2 + size_t(plan->block_n) * BLOCK_K * 2;
+    // small-K layers: a TMA box as wide as the row (32/64-byte swizzle) instead of a mostly out-of-bounds 128-byte box
+    plan->block_k = (plan->v2 && d.K <= 16) ? 16 : ((plan->v2 && d.K <= 32) ? 32 : BLOCK_K);
+    plan->k_blocks = ceil_div(d.K, plan->block_k);
+    // v2 runs two CTAs per SM (more epilogue warps in flight): each gets <= 256 TMEM columns and <= ~110 KB smem
+    plan->acc_stages = (!plan->v2 || 2 * plan->block_n <= 256) ? 2 : 1;
+    plan->tmem_cols = tmem_cols_for(plan->acc_stages * plan->block_n);
+    AMS_REQUIRE(plan->tmem_cols <= (plan->v2 ? 256u : 512u), "TMEM overflow");
+    const size_t stage_bytes = size_t(BLOCK_M) * plan->block_k * 2 + size_t(plan->block_n) * plan->block_k * 2;
     size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 4) * 8 + 16;
+    size_t budget = kSmemBudget;
     if (plan->v2) {
         const int nboxes = ceil_div(plan->block_n, 64);
-        plan->stage_bufs = (nboxes <= 2) ? 2 : 1;
-        fixed += size_t(plan->stage_bufs) * nboxes * BLOCK_M * 128 + size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8;
+        plan->linear_out = (plan->n_tiles == 1 && d.ldc == d.N) ? 1 : 0;
+        plan->pitch = d.N * 2 + (((d.N / 8) % 2 == 0) ? 16 : 0);
+        plan->cbuf_bytes = plan->linear_out ? ((BLOCK_M * plan->pitch + 1023) / 1024) * 1024 : nboxes * BLOCK_M * 128;
+        plan->stage_bufs = (plan->cbuf_bytes <= 16 * 1024) ? 2 : 1;
+        fixed += size_t(plan->stage_bufs) * plan->cbuf_bytes + size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8;
+        budget = 110 * 1024;
     }
-    int stages = int((kSmemBudget - fixed) / stage_bytes);
+    int stages = budget > fixed ? int((budget - fixed) / stage_bytes) : 0;
     stages = std::max(2, std::min(stages, kMaxStages));
     plan->stages = stages;
     plan->smem_bytes = fixed + stages * stage_bytes;
     AMS_REQUIRE(plan->smem_bytes <= 227 * 1024, "GEMM shared memory overflow");
     const int tiles = plan->m_tiles * plan->n_tiles;
-    plan->grid = std::min(tiles, num_sms);
-    if (encode_2d_bf16(&plan->tmA, d.A, d.K, d.M, size_t(d.lda) * 2, BLOCK_K, BLOCK_M)) return -1;
-    if (encode_2d_bf16(&plan->tmB, d.B, d.K, d.N, size_t(d.ldb) * 2, BLOCK_K, plan->block_n)) return -1;
+    plan->grid = std::min(tiles, (plan->v2 && plan->smem_bytes <= 113 * 1024) ? 2 * num_sms : num_sms);
+    if (encode_2d_bf16(&plan->tmA, d.A, d.K, d.M, size_t(d.lda) * 2, plan->block_k, BLOCK_M, plan->block_k * 2)) return -1;
+    if (encode_2d_bf16(&plan->tmB, d.B, d.K, d.N, size_t(d.ldb) * 2, plan->block_k, plan->block_n, plan->block_k * 2)) return -1;
     if (plan->v2 && encode_2d_bf16(&plan->tmC, d.out, d.N, d.M, size_t(d.ldc) * 2, 64, BLOCK_M)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
         AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define AMS_G2A(FL) AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_v2_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AMS_G2A(0) AMS_G2A(1) AMS_G2A(2) AMS_G2A(3) AMS_G2A(4) AMS_G2A(5) AMS_G2A(6) AMS_G2A(7)
+        AMS_G2A(8) AMS_G2A(9) AMS_G2A(10) AMS_G2A(11) AMS_G2A(12) AMS_G2A(13) AMS_G2A(14) AMS_G2A(15)
+#undef AMS_G2A
         attr_set = true;
     }
     return 0;
@@ -666,11 +749,20 @@ int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
         p.M = d.M; p.N = d.N; p.K = d.K;
         p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;
         p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.n_alloc = pl.n_tiles * pl.block_n;
-        p.stage_bufs = pl.stage_bufs; p.nboxes = ceil_div(pl.block_n, 64);
+        p.stage_bufs = pl.stage_bufs; p.nboxes = ceil_div(pl.block_n, 64); p.acc_stages = pl.acc_stages; p.block_k = pl.block_k;
+        p.linear_out = pl.linear_out; p.pitch = pl.pitch; p.cbuf_bytes = pl.cbuf_bytes;
+        p.out = static_cast<__nv_bfloat16*>(d.out); p.ldc = d.ldc;
         p.tmem_cols = pl.tmem_cols;
         p.scale = d.scale; p.shift = d.shift; p.rowbias = d.rowbias; p.rows_per_image = d.rows_per_image;
         p.residual = d.residual; p.ldr = d.ldr; p.act = d.act; p.stats_partial = d.stats_partial;
-        gemm_kmajor_v2_kernel<<<pl.grid, kGemm2Threads, pl.smem_bytes, stream>>>(pl.tmA, pl.tmB, pl.tmC, p);
+        const int flags = ((d.scale || d.shift || d.act) ? kEpiAffine : 0) | (d.residual ? kEpiResidual : 0) |
+                          (d.rowbias ? kEpiRowBias : 0) | (d.stats_partial ? kEpiStats : 0);
+        switch (flags) {
+#define AMS_G2(FL) case FL: gemm_kmajor_v2_kernel<FL><<<pl.grid, kGemm2Threads, pl.smem_bytes, stream>>>(pl.tmA, pl.tmB, pl.tmC, p); break;
+            AMS_G2(0) AMS_G2(1) AMS_G2(2) AMS_G2(3) AMS_G2(4) AMS_G2(5) AMS_G2(6) AMS_G2(7)
+            AMS_G2(8) AMS_G2(9) AMS_G2(10) AMS_G2(11) AMS_G2(12) AMS_G2(13) AMS_G2(14) AMS_G2(15)
+#undef AMS_G2
+        }
         AMS_LAUNCH_CHECK();
         return 0;
     }
