@@ -249,6 +249,7 @@ constexpr int kEpiThreads = 256;
 struct Gemm2Params {
     int M, N, K;
     int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc, stage_bufs, nboxes, acc_stages, block_k;
+    int b_resident;                              // single B tile (k_blocks == 1, n_tiles == 1): loaded once per CTA
     int linear_out, pitch, cbuf_bytes;          // linear_out: dense padded staging + coalesced copy-out (n_tiles == 1)
     __nv_bfloat16* out; int ldc;
     uint32_t tmem_cols;
@@ -276,7 +277,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int cbuf_bytes = p.cbuf_bytes;    // TMA mode: nboxes x [128 rows][128 B] swizzled; linear mode: [128 rows][pitch]
     uint8_t* smA = smem;
     uint8_t* smB = smA + p.stages * stage_a;
-    uint8_t* smC = smB + p.stages * stage_b;                          // 1024-aligned (stage sizes are multiples of 2 KB)
+    uint8_t* smC = smB + (p.b_resident ? 1 : p.stages) * stage_b;                          // 1024-aligned (stage sizes are multiples of 2 KB)
     float* s_scale = reinterpret_cast<float*>(smC + p.stage_bufs * cbuf_bytes);
     float* s_shift = s_scale + p.n_alloc;
     double* s_run = reinterpret_cast<double*>(s_shift + p.n_alloc);   // [2][n_alloc] running column sums of this CTA
@@ -285,7 +286,8 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* bres_bar = tempty_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -296,6 +298,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         t5::tma_prefetch_desc(&tmC);
         for (int s = 0; s < p.stages; ++s) { t5::mbar_init(&full_bar[s], 1); t5::mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { t5::mbar_init(&tfull_bar[s], 1); t5::mbar_init(&tempty_bar[s], kEpiThreads); }
+        t5::mbar_init(bres_bar, 1);
         t5::fence_barrier_init();
     }
     if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
@@ -313,13 +316,18 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
+            if (p.b_resident) {
+                t5::mbar_arrive_expect_tx(bres_bar, stage_b);
+                t5::tma_load_2d(smB, &tmB, bres_bar, 0, 0);
+            }
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     t5::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + stage_b);
+                    t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + (p.b_resident ? 0 : stage_b));
                     t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * p.block_k, m_tile * BLOCK_M);
-                    t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * p.block_k, n_tile * p.block_n);
+                    if (!p.b_resident)
+                        t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * p.block_k, n_tile * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -327,6 +335,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
         int stage = 0; uint32_t phase = 0; int it = 0;
+        if (p.b_resident) t5::mbar_wait(bres_bar, 0);
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int as = (p.acc_stages == 2) ? (it & 1) : 0;
             const uint32_t aphase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
@@ -338,7 +347,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 t5::fence_after_thread_sync();
                 if (lane == 0) {
                     const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
-                    const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
+                    const uint32_t b_addr = t5::smem_u32(smB + (p.b_resident ? 0 : stage) * stage_b);
                     // K-major swizzled rows of block_k*2 bytes (128/64/32-byte swizzle): 8-row groups SBO apart
                     const uint32_t sbo = 16u * p.block_k, ltype = p.block_k == 64 ? 2u : (p.block_k == 32 ? 4u : 6u);
                     for (int k = 0; k < p.block_k / UMMA_K; ++k) {
@@ -708,8 +717,10 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     plan->acc_stages = (!plan->v2 || 2 * plan->block_n <= 256) ? 2 : 1;
     plan->tmem_cols = tmem_cols_for(plan->acc_stages * plan->block_n);
     AMS_REQUIRE(plan->tmem_cols <= (plan->v2 ? 256u : 512u), "TMEM overflow");
-    const size_t stage_bytes = size_t(BLOCK_M) * plan->block_k * 2 + size_t(plan->block_n) * plan->block_k * 2;
-    size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 4) * 8 + 16;
+    plan->b_resident = (plan->v2 && plan->k_blocks == 1 && plan->n_tiles == 1) ? 1 : 0;
+    const size_t b_tile = size_t(plan->block_n) * plan->block_k * 2;
+    const size_t stage_bytes = size_t(BLOCK_M) * plan->block_k * 2 + (plan->b_resident ? 0 : b_tile);
+    size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 6) * 8 + 16 + (plan->b_resident ? b_tile : 0);
     size_t budget = kSmemBudget;
     if (plan->v2) {
         const int nboxes = ceil_div(plan->block_n, 64);
@@ -749,7 +760,7 @@ int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
         p.M = d.M; p.N = d.N; p.K = d.K;
         p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;
         p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.n_alloc = pl.n_tiles * pl.block_n;
-        p.stage_bufs = pl.stage_bufs; p.nboxes = ceil_div(pl.block_n, 64); p.acc_stages = pl.acc_stages; p.block_k = pl.block_k;
+        p.stage_bufs = pl.stage_bufs; p.nboxes = ceil_div(pl.block_n, 64); p.acc_stages = pl.acc_stages; p.block_k = pl.block_k; p.b_resident = pl.b_resident;
         p.linear_out = pl.linear_out; p.pitch = pl.pitch; p.cbuf_bytes = pl.cbuf_bytes;
         p.out = static_cast<__nv_bfloat16*>(d.out); p.ldc = d.ldc;
         p.tmem_cols = pl.tmem_cols;

@@ -29,7 +29,7 @@ struct GemmDesc {
 struct GemmPlan {
     CUtensorMap tmA, tmB, tmC;
     GemmDesc d;
-    int v2 = 0, stage_bufs = 1, acc_stages = 2, block_k = 64, linear_out = 0, pitch = 0, cbuf_bytes = 0;
+    int v2 = 0, stage_bufs = 1, acc_stages = 2, block_k = 64, linear_out = 0, pitch = 0, cbuf_bytes = 0, b_resident = 0;
     int block_n = 0, n_tiles = 0, m_tiles = 0, k_blocks = 0, stages = 0, tmem_cols = 0;
     size_t smem_bytes = 0;
     int grid = 0;
