@@ -185,25 +185,15 @@ def run_ours(args, rank, world, local_rank):
         host.append((ft, fa, lt, la))
     h2d_step = BATCH * H * W * 4
 
-    grad_t = None
+    dp = None
     if world > 1:
-        ptr, n = st.gradient_arena()
-
-        class _Arena:
-            __cuda_array_interface__ = {'shape': (n,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
-        grad_t = torch.as_tensor(_Arena(), device='cuda')
-        nv_t = torch.zeros(1, dtype=torch.float64, device='cuda')
+        from ams_b200.parallel import DataParallelStudent
+        dp = DataParallelStudent(st)
 
     def step(masked):
-        if world == 1:
+        if dp is None:
             return st.train_step(LR, masked)
-        nv, ls = st.train_forward_backward()
-        nv_t[0] = nv
-        dist.all_reduce(grad_t)
-        dist.all_reduce(nv_t)
-        tot = float(nv_t.item())
-        st.apply_optimizer(LR, masked, 1.0 / max(tot, 1.0))
-        return ls / max(nv, 1)
+        return dp.train_step(LR, masked)
 
     def phase(feed_from_host):
         """one distillation phase of K iterations; returns (delta bytes, kept)"""

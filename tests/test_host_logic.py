@@ -1,0 +1,103 @@
+"""CPU tests of the host-side mirror of the reference interface (utils, exp_configs, mask strategy tables)."""
+import random
+from collections import deque
+
+import numpy as np
+import pytest
+
+import student_oracle as so
+from ams_b200 import exp_configs
+from ams_b200.SemanticNetwork import _MASK_TABLES
+from ams_b200.student import load_graph_spec, _low_res
+from ams_b200.synthetic import synthetic_checkpoint
+from ams_b200.utils.utils import calculate_miou, choose_frames, colormap, mini_batch
+
+
+def test_calculate_miou_matches_oracle_and_options():
+    rng = np.random.default_rng(0)
+    cm = rng.integers(0, 50, size=(6, 6)).astype(np.float64)
+    cm[:, 4] = 0
+    cm[4, :] = 0
+    a = calculate_miou(cm, nan=True)
+    b = so.calculate_miou(cm)
+    assert np.array_equal(np.array(a), np.array(b), equal_nan=True) and np.isnan(a[4])
+    assert calculate_miou(cm)[4] == 'Not predicted/present'
+    iou, pop, fn, fp = calculate_miou(cm, population=True, detailed=True)
+    assert abs(pop.sum() - 1) < 1e-12 and fn[4] == 0 and len(fp) == 6
+
+
+def test_choose_frames_equally_spaced():
+    items = [(i, -i) for i in range(30)]
+    f, l = choose_frames(items, 0.1)
+    assert f == [9, 19, 29] and l == [-9, -19, -29]
+    assert choose_frames(items, 1.0)[0] == list(range(30))
+    assert choose_frames(items, 0.0) == ([], [])
+
+
+def test_mini_batch_shapes_dtype_and_rng_order():
+    frames = deque(np.full((8, 16, 3), i, np.uint8) for i in range(5))
+    labels = deque(np.full((8, 16), i, np.uint8) for i in range(5))
+    np.random.seed(3); random.seed(3)
+    img, lab = mini_batch(frames, labels, [8, 16], [1], 4, 2)
+    assert img.shape == (2, 4, 8, 16, 3) and lab.shape == (2, 4, 8, 16) and img.dtype == np.float64
+    assert np.array_equal(img[..., 0, 0, 0], lab[..., 0, 0])           # image and label drawn from the same frame
+    np.random.seed(3); random.seed(3)
+    picks = []
+    for _ in range(8):
+        picks.append(np.random.choice(5)); random.randint(0, 0); random.randint(0, 0); random.randint(0, 0)
+    assert list(lab[..., 0, 0].reshape(-1)) == picks                    # same RNG call order as the reference
+
+
+def test_exp_configs_tables():
+    w = exp_configs.class_weights(12)
+    assert w.shape == (19, 1) and w.dtype == np.float32 and list(np.where(w == 1)[0]) == [0, 1, 2, 8, 10, 11, 13]
+    assert exp_configs.num_classes(40) == 21 and exp_configs.class_weights(40).shape == (21, 1)
+    assert exp_configs.is_coco(40) and not exp_configs.is_coco(12)
+    assert exp_configs.test_length(12) == 900
+    with pytest.raises(ValueError):
+        exp_configs.class_weights(0)
+    assert exp_configs.coco_class_converter().shape == (81,) and exp_configs.coco_class_converter()[1] == 15
+
+
+def test_mask_strategy_tables_reference_real_variables():
+    names = {v['name'] for v in load_graph_spec('cityscapes')['trainable_variables']}
+    assert len(_MASK_TABLES) == 15
+    for (strategy, frac), (substr, exact, bern) in _MASK_TABLES.items():
+        assert strategy in ('coord_desc_last', 'coord_desc_first', 'coord_desc_both') and frac in (0.1, 0.05, 0.01, 0.2, 0.02)
+        for k in list(exact) + list(bern):
+            assert k in names, (strategy, frac, k)
+        for s in substr:
+            assert any(s in n for n in names), (strategy, frac, s)
+        for p in bern.values():
+            assert 0 < p < 1
+
+
+def test_mask_tables_hit_the_advertised_fraction():
+    """Each hard-coded strategy was tuned by the reference authors to train ~coord_frac of the coordinates."""
+    spec = load_graph_spec('cityscapes')
+    sizes = {v['name']: int(np.prod(v['shape'])) for v in spec['trainable_variables']}
+    total = sum(sizes.values())
+    for (strategy, frac), (substr, exact, bern) in _MASK_TABLES.items():
+        expected = 0.0
+        for n, sz in sizes.items():
+            if any(s in n for s in substr) or n in exact:
+                expected += sz
+            elif n in bern:
+                expected += sz * bern[n]
+        # two reference quirks kept verbatim (SemanticNetwork.py:600-625): 'last' @ 0.02 draws concat_projection/weights
+        # with P(True)=0.7187 (4.7 % of the model), 'first' @ 0.02 lands on 2.14 %
+        tol = {('coord_desc_last', 0.02): 0.03, ('coord_desc_first', 0.02): 0.002}.get((strategy, frac), 0.0005)
+        assert abs(expected / total - frac) < tol, (strategy, frac, expected / total)
+
+
+def test_synthetic_checkpoint_layout():
+    ck = synthetic_checkpoint('cityscapes', 1)
+    spec = load_graph_spec('cityscapes')
+    assert list(ck) == [v['name'] for v in spec['variables']]
+    assert all(ck[v['name']].shape == tuple(v['shape']) and ck[v['name']].dtype == np.float32 for v in spec['variables'])
+    assert sum(a.size for a in ck.values()) * 4 == 8584524              # the byte size of the reference's TF shard
+
+
+def test_low_res_and_colormap():
+    assert (_low_res(512), _low_res(1024), _low_res(256)) == (33, 65, 17)
+    assert colormap().shape == (256, 3) and list(colormap()[13]) == [0, 0, 142]

@@ -1,0 +1,182 @@
+"""CPU tests pinning the oracle (no GPU): (1) the hand-written restatement equals, bit for bit in fp32, what
+oracle/metagraph_interp.py computed by executing the reference's shipped model.meta (tests/golden/*.npz, generated
+by oracle/make_golden.py); (2) closed-form unit cases for every restated TF op (the reference has no tests or
+golden vectors of its own: SURVEY.md section 4)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import student_oracle as so
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'interp_*.npz')))
+
+
+def test_golden_fixtures_exist():
+    assert len(GOLDEN) >= 3
+
+
+@pytest.mark.parametrize('path', GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_restatement_matches_model_meta_interpreter(path):
+    g = np.load(path)
+    tag = os.path.basename(path).split('_')[1]
+    spec = so.load_spec(tag)
+    V = so.synthetic_variables(spec, seed=int(g['seed']), conditioned=bool(int(g['conditioned'])))
+    frames = g['frames']
+    n, h, w, _ = frames.shape
+    params = {k: torch.tensor(v) for k, v in V.items()}
+    for mode in ('moving', 'batch'):
+        keep = {}
+        with torch.no_grad():
+            sem, stats = so.forward(spec, params, frames.astype(np.float32), bn_mode=mode, keep=keep)
+            full = so.full_res_logits(sem, h, w)
+        assert np.array_equal(sem.numpy(), g[mode + '/semantic'])
+        assert np.array_equal(full.argmax(3).numpy().astype(np.uint8), g[mode + '/student_logits_argmax'])
+        assert np.array_equal(full[:, 0].numpy(), g[mode + '/student_logits_row0'])
+        assert float(keep['MobilenetV2/expanded_conv_14/depthwise'].double().sum()) == float(g[mode + '/expanded_conv_14_depthwise_relu6_sum'])
+        assert float(keep['concat_projection'].double().sum()) == float(g[mode + '/concat_projection_relu_sum'])
+        assert np.array_equal(keep['MobilenetV2/expanded_conv_3/project'].numpy(), g[mode + '/expanded_conv_3_project_bn'])
+    ts = so.TrainState(spec, V)
+    ts.apply_moving_stats(stats)
+    for k in g.files:
+        if k.startswith('update/'):
+            assert np.array_equal(ts.vars[k[len('update/'):]], g[k]), k
+
+
+def test_bn_of_constant_image_is_beta():
+    """FusedBatchNormV3(is_training): zero variance => y == beta; image_pooling at N == 1."""
+    x = torch.full((1, 1, 1, 5), 3.25)
+    gamma, beta = torch.rand(5) + 0.5, torch.randn(5)
+    y, m, v = so.batch_norm(x, gamma, beta, 1e-3, 'batch')
+    assert torch.allclose(y.reshape(-1), beta) and torch.equal(m, torch.full((5,), 3.25)) and float(v.abs().max()) == 0.0
+
+
+def test_bn_unbiased_variance_output():
+    x = torch.randn(2, 3, 4, 6)
+    _, m, v = so.batch_norm(x, torch.ones(6), torch.zeros(6), 1e-3, 'batch')
+    flat = x.reshape(-1, 6)
+    assert torch.allclose(v, flat.var(dim=0, unbiased=True), atol=1e-6) and torch.allclose(m, flat.mean(0), atol=1e-6)
+
+
+def test_same_padding_is_tf_style():
+    # even input, stride 2, k=3: TF pads 0 before / 1 after (torch's symmetric padding would differ)
+    assert so._same_pads(8, 3, 2, 1) == (0, 1)
+    assert so._same_pads(513, 3, 2, 1) == (1, 1)
+    assert so._same_pads(33, 3, 1, 2) == (2, 2)
+    x = torch.arange(16, dtype=torch.float32).reshape(1, 4, 4, 1)
+    w = torch.ones(3, 3, 1, 1)
+    y = so.conv2d_same(x, w, 2, 1, False)
+    assert y.shape == (1, 2, 2, 1) and float(y[0, 0, 0, 0]) == float(x[0, 0:3, 0:3, 0].sum())
+
+
+def test_resize_align_corners_identity_and_corners():
+    x = torch.randn(1, 5, 7, 3)
+    assert torch.equal(so.resize_bilinear_align(x, 5, 7), x)
+    y = so.resize_bilinear_align(x, 64, 128)
+    for (a, b), (c, d) in (((0, 0), (0, 0)), ((63, 127), (4, 6)), ((0, 127), (0, 6)), ((63, 0), (4, 0))):
+        assert torch.equal(y[0, a, b], x[0, c, d])
+    lo, hi, l = so.resize_weights(33, 512)
+    assert lo[0] == 0 and hi[-1] == 32 and lo[-1] == 32 and float(l[-1]) == 0.0 and np.all(hi - lo <= 1)
+
+
+def test_confusion_matrix_and_miou_hand_case():
+    labels = np.array([[0, 0, 1, 1, 2, 255]])
+    pred = np.array([[0, 1, 1, 1, 0, 2]])
+    fl, w = so.reduce_labels(labels, [0, 1, 2])
+    cm = so.confusion_matrix(fl, pred, w, 3)
+    assert np.array_equal(cm, np.array([[1, 1, 0], [0, 2, 0], [1, 0, 0]], dtype=np.float64))
+    iou = so.calculate_miou(cm)
+    assert iou[0] == 1 / 3 and iou[1] == 2 / 3 and iou[2] == 0.0
+    # class neither present nor predicted => NaN, ignored by nanmean (SemanticNetwork.py:210-211)
+    cm2 = so.confusion_matrix(*so.reduce_labels(np.array([[0, 0]]), [0, 5])[:1], np.array([[0, 0]]), np.ones((1, 2)), 2)
+    assert np.isnan(so.calculate_miou(cm2)[1])
+
+
+def test_reduce_labels_class_subset_and_out_of_range():
+    cls = [0, 2, 13]
+    fl, w = so.reduce_labels(np.array([0, 1, 2, 13, 18, 19, 200, 255]), cls)
+    assert list(w) == [1, 0, 1, 1, 0, 0, 0, 0] and list(fl[:4]) == [0, 0, 1, 2]
+    # one_hot depth is 19 even for the 21-class graph
+    fl, w = so.reduce_labels(np.array([19, 20]), [19, 20])
+    assert list(w) == [0, 0]
+
+
+def test_loss_is_mean_over_valid_and_nan_when_empty():
+    logits = torch.zeros(1, 2, 2, 19)
+    h = so.head(logits, np.array([[[0, 255], [3, 3]]]), np.arange(19))
+    assert h['n_valid'] == 3 and abs(float(h['loss']) - np.log(19)) < 1e-6
+    h = so.head(logits, np.full((1, 2, 2), 255), np.arange(19))
+    assert np.isnan(float(h['loss'])) and h['conf_mat'].sum() == 0
+
+
+def test_adam_first_step_closed_form():
+    """From fresh state TF1 Adam moves every coordinate by lr*g/(|g| + eps/sqrt(1-beta2))."""
+    spec = {'trainable_variables': [{'name': 'v', 'shape': [5]}], 'convs': []}
+    st = so.TrainState.__new__(so.TrainState)
+    st.spec, st.trainable = spec, ['v']
+    st.vars = {'v': np.zeros(5, np.float32)}
+    st.m = {'v': np.zeros(5, np.float32)}
+    st.v = {'v': np.zeros(5, np.float32)}
+    st.beta1_power, st.beta2_power = so.BETA1, so.BETA2
+    g = np.array([1e-3, -2.0, 5e-6, 0.0, 7.0], np.float32)
+    st.adam_apply({'v': g}, 1e-3)
+    expect = -1e-3 * g / (np.abs(g) + 1e-8 / np.sqrt(1 - 0.999))
+    assert np.allclose(st.vars['v'], expect, rtol=2e-4, atol=1e-12)
+    assert st.beta1_power == np.float32(0.9) * np.float32(0.9)
+
+
+def test_masked_adam_keeps_unselected_but_updates_slots():
+    spec = {'trainable_variables': [{'name': 'v', 'shape': [4]}], 'convs': []}
+    st = so.TrainState.__new__(so.TrainState)
+    st.spec, st.trainable = spec, ['v']
+    st.vars = {'v': np.ones(4, np.float32)}
+    st.m = {'v': np.zeros(4, np.float32)}
+    st.v = {'v': np.zeros(4, np.float32)}
+    st.beta1_power, st.beta2_power = so.BETA1, so.BETA2
+    st.adam_apply({'v': np.ones(4, np.float32)}, 1e-3, {'v': np.array([True, False, True, False])})
+    assert st.vars['v'][1] == 1.0 and st.vars['v'][0] < 1.0 and np.all(st.m['v'] > 0) and np.all(st.v['v'] > 0)
+
+
+def test_percentile_selection_numpy119_semantics():
+    rng = np.random.default_rng(0)
+    a = rng.random(2113043).astype(np.float32)
+    thr, lo, w_hi = so.percentile_threshold_np119(a, 0.05)
+    assert lo == 2007389 and abs(w_hi - 0.9) < 1e-6                    # virtual index 2,007,389.9
+    srt = np.sort(a)
+    assert thr == np.float32(np.float64(srt[lo]) * (1 - w_hi) + np.float64(srt[lo + 1]) * w_hi)
+    assert int((a > thr).sum()) == 105653                               # k = 105,653 kept when there are no ties
+    # massive ties: strict '>' can select nothing
+    t = np.full(1000, 1e-3, np.float32)
+    thr, _, _ = so.percentile_threshold_np119(t, 0.1)
+    assert int((t > thr).sum()) == 0
+
+
+def test_pack_delta_wire_format():
+    masks = [np.array([[1, 0, 0, 0, 0, 0, 0, 1], [1, 1, 0, 0, 0, 0, 0, 0]], bool), np.array([0, 1, 1], bool)]
+    params = [np.arange(16, dtype=np.float32).reshape(2, 8), np.array([0.5, 1.5, 65536.0], np.float32)]
+    blob = so.pack_delta(masks, params)
+    assert blob[:3] == bytes([0b10000001, 0b11000000, 0b01100000])
+    vals = np.frombuffer(blob[3:], dtype=np.float16)
+    assert list(vals[:5]) == [0.0, 7.0, 8.0, 9.0, 1.5] and np.isinf(vals[5])
+
+
+def test_teacher_forcing_is_value_neutral():
+    spec = so.load_spec('cityscapes')
+    V = so.synthetic_variables(spec, 3)
+    fr = so.synthetic_frames(1, 32, 48, 1).astype(np.float32)
+    lab = so.synthetic_labels(1, 32, 48, 1, block=8)
+    ts = so.TrainState(spec, V, precision='bf16')
+    keep = {}
+    with torch.no_grad():
+        so.forward(spec, {k: torch.tensor(v) for k, v in V.items()}, fr, bn_mode='batch', precision='bf16', keep=keep)
+    forced = {}
+    for c in spec['convs']:
+        if c['name'] in ('image_pooling', 'logits/semantic'):
+            continue
+        forced[c['name'] + '/z'] = keep[c['name'] + '/z']
+        forced[c['name']] = keep[c['residual_add_name']] if c['residual_from'] else keep[c['name']]
+    l1, g1, _, _ = ts.loss_and_grads(fr, lab, np.arange(19))
+    l2, g2, _, _ = ts.loss_and_grads(fr, lab, np.arange(19), forced=forced)
+    assert l1 == l2 and all(np.array_equal(g1[k], g2[k]) for k in g1)
