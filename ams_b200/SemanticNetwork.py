@@ -77,7 +77,11 @@ _MASK_TABLES = {
 
 
 def load_frozen(path):
-    with np.load(path, allow_pickle=False) as z:
+    try:
+        z = np.load(path, allow_pickle=False)
+    except Exception:
+        raise ValueError('%s is not an ams_b200 frozen model (a TF GraphDef .pb cannot be loaded)' % path)
+    with z:
         if FROZEN_MAGIC not in z.files:
             raise ValueError('%s is not an ams_b200 frozen model (a TF GraphDef .pb cannot be loaded)' % path)
         return OrderedDict((k, z[k]) for k in z.files if k != FROZEN_MAGIC)

@@ -111,8 +111,8 @@ def last_error():
 def check(rc, what=''):
     if rc != 0:
         msg = last_error()
-        if msg.startswith('KeyError'):
-            raise KeyError(msg[len('KeyError: '):])
+        if 'KeyError: ' in msg:                      # unknown variable name: same exception as utils/utils.py:41
+            raise KeyError(msg.split('KeyError: ', 1)[1].split(' at ')[0])
         raise NativeError('%s failed: %s' % (what or 'libams_b200 call', msg))
 
 
