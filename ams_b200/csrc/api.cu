@@ -1,5 +1,6 @@
 // extern "C" surface of libams_b200 (see include/ams_b200.h for the reference call site each entry replaces).
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -266,7 +267,9 @@ int ams_enqueue(ams_net* h, const void* frames, int dtype, const uint8_t* labels
     int slot = -1;
     {
         std::unique_lock<std::mutex> lk(net->qmu);
-        net->qcv.wait(lk, [&] { return !net->free_slots.empty(); });
+        // FIFOQueue semantics: block while the queue is full -- but a full queue nobody drains is an error, not a hang
+        const bool got = net->qcv.wait_for(lk, std::chrono::seconds(60), [&] { return !net->free_slots.empty(); });
+        AMS_REQUIRE(got, "input queue stayed full for 60 s: nothing is consuming it (queue_capacity too small?)");
         slot = net->free_slots.front();
         net->free_slots.pop_front();
     }

@@ -49,6 +49,8 @@ class DataParallelStudent:
         self.grad = torch.as_tensor(_DeviceArena(ptr, n), device='cuda')
 
     def train_step(self, lr, masked):
+        # the library and torch must share one stream (Student.set_stream(torch.cuda.current_stream().cuda_stream)):
+        # the allreduce is ordered after backward and before Adam by stream order alone
         n_valid, loss_sum = self.student.train_forward_backward()
         scale, loss = allreduce_step_terms(self.grad, n_valid, loss_sum, self.group)
         self.student.apply_optimizer(lr, masked, scale)

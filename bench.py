@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+T0 = time.time()
 
 H, W, BATCH = 512, 1024, 8
 CLASSES = [0, 1, 2, 8, 10, 11, 13]          # reference experiment 12 (exp_configs.py:44-47)
@@ -168,10 +169,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def mark(msg):
+        if args.verbose:
+            print('[rank %d %.1fs] %s' % (rank, time.time() - T0, msg), file=sys.stderr, flush=True)
+
     K, Wm = args.steps, args.warmup
-    st = Student(19, H, W, CLASSES, device=local_rank, queue_capacity=K + 2)
-    stream = torch.cuda.current_stream()
+    N_INF = 10
+    st = Student(19, H, W, CLASSES, device=local_rank, queue_capacity=max(K, N_INF) + 2)
+    # a dedicated (non-default) stream shared by torch (events, NCCL ordering) and the library's kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     st.set_stream(stream.cuda_stream)
+    mark('student created')
     for k, v in synthetic_checkpoint('cityscapes', 1).items():
         st.set_tensor(k, v)
     # 4 distinct synthetic batches per rank, cycled
@@ -226,6 +236,7 @@ def run_ours(args, rank, world, local_rank):
         _, fa, _, la = host[i % nb]
         st.enqueue(fa, la)
         step(False)
+        mark('warm-up step %d done' % i)
     torch.cuda.synchronize()
 
     # ---- timed: device-resident inputs
@@ -242,6 +253,7 @@ def run_ours(args, rank, world, local_rank):
     delta_len, kept = phase(False)
     e1.record(stream)
     barrier()
+    mark('device-resident phase done')
     ms = e0.elapsed_time(e1)
     launches = nat.lib().ams_launch_count() - launches0
     # ---- timed: end to end from pinned host memory
@@ -252,12 +264,15 @@ def run_ours(args, rank, world, local_rank):
     delta_len2, _ = phase(True)
     f1.record(stream)
     barrier()
+    mark('e2e phase done')
     ms_e2e = max(f0.elapsed_time(f1), 1000.0 * (time.time() - t_wall0))
     clocks = sampler.stop() if rank == 0 else None
+    mark('clock sampler stopped')
     if world > 1:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    mark('max over ranks done')
 
     # ---- per-kernel-group device times (separate short pass so the events do not perturb the numbers above)
     prof = None
@@ -270,8 +285,9 @@ def run_ours(args, rank, world, local_rank):
             st.train_step(LR, True)
         prof = st.profile_report()
         st.profile_enable(False)
+        mark('profile pass done')
         # ---- secondary: frozen-client inference, batch 8, argmax + confusion matrix
-        n_inf = 10
+        n_inf = N_INF
         for i in range(3):
             st.enqueue(host[i % nb][1], host[i % nb][3])
             st.infer_metric(BATCH, nat.BN_MOVING)
@@ -292,6 +308,7 @@ def run_ours(args, rank, world, local_rank):
             st.infer_metric(BATCH, nat.BN_MOVING)
         prof_inf = st.profile_report()
         st.profile_enable(False)
+        mark('infer pass done')
         infer = {'frames_per_sec': BATCH / (ms_inf / 1000.0), 'ms_per_batch8': ms_inf, 'includes': 'D2H of int32 label maps + confusion matrix',
                  'roofline_frac_layer_boundary': (BATCH / (ms_inf / 1000.0)) * ALGO_BYTES_FRAME / (peaks()[0] * 1e9),
                  'kernel_groups_ms_per_batch': {k: round(v['ms'] / 3, 4) for k, v in sorted(prof_inf.items(), key=lambda kv: -kv[1]['ms'])}}
@@ -335,8 +352,10 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    mark('closing')
     st.close()
+    mark('closed')
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,6 +367,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--verbose', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     args.steps = max(args.steps, 2)
