@@ -655,29 +655,34 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
-// 4 consecutive outputs per thread (float4 loads of the split-K partials), fixed split order => deterministic
+// Fixed split order => deterministic.  Few splits: one thread per 4 outputs walks the splits; many splits (the
+// high-resolution layers, ~300 splits of a tiny dW): one warp per 4 outputs, lanes stride the splits, fixed shuffle tree.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int lddw, int splits,
-                    long long split_stride) {
-    const long long i4 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+                    long long split_stride, int warp_per_item) {
     const long long n = static_cast<long long>(Cin) * Cout;
+    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long i4 = (warp_per_item ? (tid >> 5) : tid) * 4;
     if (i4 >= n) return;
+    const int s0 = warp_per_item ? lane : 0, ds = warp_per_item ? 32 : 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if ((Cout & 3) == 0) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int s = 0; s < splits; ++s) {
+        for (int s = s0; s < splits; s += ds) {
             const float4 v = *reinterpret_cast<const float4*>(ws + s * split_stride + i4);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
         }
-        float* o = dw + (i4 / Cout) * lddw + (i4 % Cout);
-        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z; o[3] = acc.w;
     } else {
-        for (long long i = i4; i < min(i4 + 4, n); ++i) {
-            float acc = 0.f;
-            for (int s = 0; s < splits; ++s) acc += ws[s * split_stride + i];
-            dw[(i / Cout) * lddw + (i % Cout)] = acc;
-        }
+        for (int s = s0; s < splits; s += ds)
+            for (int k = 0; k < 4; ++k) if (i4 + k < n) acc[k] += ws[s * split_stride + i4 + k];
     }
+    if (warp_per_item) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane != 0) return;
+    }
+    for (int k = 0; k < 4; ++k)
+        if (i4 + k < n) dw[((i4 + k) / Cout) * lddw + ((i4 + k) % Cout)] = acc[k];
 }
 
 }  // namespace
@@ -802,7 +807,7 @@ static void wgrad_shape(int Cin, int Cout, long long M, int num_sms, int* ci_til
     *boxes_b = ceil_div(bn, 64);
     *k_blocks = int(ceil_div_ll(M, BLOCK_K));
     const int tiles = (*ci_tiles) * (*co_tiles);
-    int want = std::max(1, (2 * num_sms) / tiles);
+    int want = std::max(1, num_sms / tiles);               // about one CTA per SM: fewer, longer split-K runs
     int max_splits = std::max(1, *k_blocks / 8);           // at least 8 k-blocks (512 pixels) per CTA
     int s = std::min(want, max_splits);
     *kb_per_split = ceil_div(*k_blocks, s);
@@ -851,8 +856,10 @@ int wgrad_launch(const WgradPlan& pl, cudaStream_t stream) {
     AMS_LAUNCH_CHECK();
     if (pl.splits > 1) {
         const long long n = static_cast<long long>(d.Cin) * d.Cout;
-        wgrad_reduce_kernel<<<int(ceil_div_ll(n, 1024)), 256, 0, stream>>>(d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
-                                                                          pl.splits, p.split_stride);
+        const int wpi = pl.splits > 16 ? 1 : 0;
+        const long long threads = ceil_div_ll(n, 4) * (wpi ? 32 : 1);
+        wgrad_reduce_kernel<<<int(ceil_div_ll(threads, 256)), 256, 0, stream>>>(d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
+                                                                               pl.splits, p.split_stride, wpi);
         AMS_LAUNCH_CHECK();
     }
     return 0;
