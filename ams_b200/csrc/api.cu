@@ -525,6 +525,7 @@ int ams_profile_enable(ams_net* h, int on) {
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
     net->prof.reset();
     net->prof.enabled = on != 0;
+    net->prof.per_layer = on == 2;
     return 0;
 }
 int ams_profile_report(ams_net* h, char* buf, int cap) {
@@ -621,8 +622,35 @@ static Conv2dGeom make_geom(int n, int h, int w, int c, int stride, int dil) {
 
 int ams_op_depthwise(const void* in, const float* w, int n, int h, int w_, int c, int stride, int dil, const float* scale,
                      const float* shift, int act, void* out, void* stream) {
-    return dw_conv_fwd(static_cast<const bf16*>(in), w, make_geom(n, h, w_, c, stride, dil), scale, shift, act,
-                       static_cast<bf16*>(out), as_stream(stream));
+    return dw_conv_fwd_tiled(static_cast<const bf16*>(in), w, make_geom(n, h, w_, c, stride, dil), nullptr, nullptr, 0, scale,
+                             shift, act, static_cast<bf16*>(out), nullptr, nullptr, as_stream(stream));
+}
+
+__global__ void sum_rows_kernel(const double* __restrict__ partial, int rows, int n, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0;
+    for (int r = 0; r < rows; ++r) a += partial[static_cast<long long>(r) * n + i];
+    out[i] = a;
+}
+
+int ams_op_depthwise_fused(const void* in, const float* w, int n, int h, int w_, int c, int stride, int dil,
+                           const float* in_scale, const float* in_shift, int in_act, void* out, double* stats_out,
+                           void* stream) {
+    const Conv2dGeom g = make_geom(n, h, w_, c, stride, dil);
+    double* ws = nullptr;
+    const long long rows = dw_tiled_stats_rows(g);
+    if (stats_out) AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), static_cast<size_t>(rows) * 2 * c * sizeof(double)));
+    int got = 0;
+    int rc = dw_conv_fwd_tiled(static_cast<const bf16*>(in), w, g, in_scale, in_shift, in_act, nullptr, nullptr, 0,
+                               static_cast<bf16*>(out), ws, &got, as_stream(stream));
+    if (!rc && stats_out) {
+        sum_rows_kernel<<<ceil_div(2 * c, 128), 128, 0, as_stream(stream)>>>(ws, got, 2 * c, stats_out);
+        if (cudaGetLastError() != cudaSuccess) rc = -1;
+    }
+    cudaStreamSynchronize(as_stream(stream));
+    if (ws) cudaFree(ws);
+    return rc;
 }
 
 int ams_op_depthwise_bwd(const void* x, const void* dz, const float* w, int n, int h, int w_, int c, int stride, int dil,

@@ -81,19 +81,34 @@ bn_stats_kernel(const bf16* __restrict__ z, long long M, int C, long long rows_p
     }
 }
 
-// one warp per channel: lanes stride over the chunk partials (fixed assignment + fixed shuffle tree => deterministic)
-__global__ void __launch_bounds__(256)
-bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, int update_moving) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= L.C) return;
+// block = 32 channels x kFinRows row-lanes: coalesced reads of the partial rows, fixed lane assignment and a
+// fixed-order shared-memory tree => deterministic
+constexpr int kFinRows = 32;
+__device__ __forceinline__ bool finalize_sums(const double* __restrict__ partial, int chunks, int C, int c, double* s_out,
+                                              double* q_out) {
+    __shared__ double s_s[kFinRows][33], s_q[kFinRows][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     double s = 0.0, q = 0.0;
-    for (int k = lane; k < chunks; k += 32) {
-        s += partial[static_cast<long long>(k) * 2 * L.C + c];
-        q += partial[static_cast<long long>(k) * 2 * L.C + L.C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int k = rl; k < chunks; k += kFinRows) {
+            s += partial[static_cast<long long>(k) * 2 * C + c];
+            q += partial[static_cast<long long>(k) * 2 * C + C + c];
+        }
     }
-    s = warp_sum_d(s);
-    q = warp_sum_d(q);
-    if (lane != 0) return;
+    s_s[rl][cl] = s; s_q[rl][cl] = q;
+    __syncthreads();
+    if (rl != 0 || c >= C) return false;
+    for (int k = 1; k < kFinRows; ++k) { s += s_s[k][cl]; q += s_q[k][cl]; }
+    *s_out = s; *q_out = q;
+    return true;
+}
+
+__global__ void __launch_bounds__(32 * kFinRows)
+bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, int update_moving) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, q;
+    if (!finalize_sums(partial, chunks, L.C, c, &s, &q)) return;
     const double n = static_cast<double>(L.M);
     const double mean = s / n;
     double var = q / n - mean * mean;
@@ -230,18 +245,11 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 }
 
 // coef[0][c]=A, [1][c]=B, [2][c]=Cc with dz = A*g + B*z + Cc ; also d_gamma, d_beta
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kFinRows)
 bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, float* d_gamma, float* d_beta, float* coef) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (c >= L.C) return;
-    double s1 = 0.0, sz = 0.0;
-    for (int k = lane; k < chunks; k += 32) {
-        s1 += partial[static_cast<long long>(k) * 2 * L.C + c];
-        sz += partial[static_cast<long long>(k) * 2 * L.C + L.C + c];
-    }
-    s1 = warp_sum_d(s1);
-    sz = warp_sum_d(sz);
-    if (lane != 0) return;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s1, sz;
+    if (!finalize_sums(partial, chunks, L.C, c, &s1, &sz)) return;
     const double mean = L.mean[c], rstd = L.rstd[c], gamma = L.gamma[c];
     const double n = static_cast<double>(L.M);
     const double s2 = rstd * (sz - mean * s1);           // sum g * xhat
@@ -438,13 +446,13 @@ int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double*
     AMS_REQUIRE(smem <= 48 * 1024, "BN reduction shared memory");
     bn_stats_kernel<<<chunks, kRedThreads, smem, s>>>(z, L.M, L.C, rpc, ws);
     AMS_LAUNCH_CHECK();
-    bn_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(ws, chunks, L, update_moving);
+    bn_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(ws, chunks, L, update_moving);
     AMS_LAUNCH_CHECK();
     return 0;
 }
 
 int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, int update_moving, cudaStream_t s) {
-    bn_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(partial, chunks, L, update_moving);
+    bn_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(partial, chunks, L, update_moving);
     AMS_LAUNCH_CHECK();
     return 0;
 }
@@ -472,7 +480,7 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     float* coef = reinterpret_cast<float*>(ws + static_cast<size_t>(chunks) * 2 * L.C);
     bn_bwd_reduce_kernel<<<chunks, kRedThreads, smem, s>>>(dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     AMS_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<ceil_div(L.C * 32, 256), 256, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
+    bn_bwd_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
     AMS_LAUNCH_CHECK();
     const long long total8 = L.M * L.C / 8;
     bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s>>>(dy, dy2, z, L.scale, L.shift, coef, act, total8, L.C, dz_out);

@@ -33,6 +33,14 @@ int dw_conv_bwd_data(const bf16* dz, const float* w, const Conv2dGeom& g, bf16* 
 int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
                        size_t workspace_floats, cudaStream_t s);
 size_t dw_bwd_workspace_floats(const Conv2dGeom& g);
+// shared-memory tiled forward (dw_tiled.cu): optional BN+act of the PRODUCER applied while staging the input
+// (in_scale/in_shift), optional folded BN + act on the result (out_scale/out_shift), optional per-tile column sums
+// stats[tile][2][C] (sum, sum of squares of the stored bf16 values) for bn_finalize_partials.
+bool dw_tiled_supported(const Conv2dGeom& g);
+long long dw_tiled_stats_rows(const Conv2dGeom& g);
+int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const float* in_scale, const float* in_shift,
+                      int in_act, const float* out_scale, const float* out_shift, int out_act, bf16* out, double* stats,
+                      int* stats_rows, cudaStream_t s);
 
 // ---- BatchNorm, training mode
 struct BnLayer {            // device pointers into the parameter / state arenas, all [C] fp32

@@ -47,7 +47,8 @@ cudaEvent_t Profiler::get_event() {
 void Profiler::begin(cudaStream_t s, const char* tag, double algo_bytes) {
     if (!enabled) return;
     ProfEntry e;
-    e.tag = tag; e.algo_bytes = algo_bytes; e.e0 = get_event(); e.e1 = get_event();
+    e.tag = tag; e.algo_bytes = algo_bytes;
+    if (per_layer && layer) { e.tag += "@"; e.tag += layer; } e.e0 = get_event(); e.e1 = get_event();
     cudaEventRecord(e.e0, s);
     pending.push_back(e);
 }
@@ -234,6 +235,10 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             if (dev_alloc(&p->buf[i].y, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
             if (dev_alloc(&p->buf[i].z, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
             bn_ws = std::max(bn_ws, bn_workspace_doubles(M, d.cout));
+            if (d.kind == kDepthwise) {
+                Conv2dGeom g{N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+                bn_ws = std::max(bn_ws, static_cast<size_t>(dw_tiled_stats_rows(g)) * 2 * d.cout + 3 * static_cast<size_t>(d.cout));
+            }
         }
         if (dev_alloc(&p->bn_ws, bn_ws, &p->allocations)) return -1;
         const LayerDef& ipd = L[L.size() - 4];
@@ -371,6 +376,7 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
     if (net_prepare_weights(net, frozen)) return -1;
     for (size_t i = 0; i < L.size(); ++i) {
         const LayerDef& d = L[i];
+        net->prof.layer = d.name.c_str();
         const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
         LayerBuf& b = p->buf[i];
         const double out_bytes = 2.0 * M * d.cout;
@@ -383,6 +389,7 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
             continue;
         }
         bf16* conv_out = frozen ? b.y : b.z;
+        int dw_rows = 0;
         const float* sc = frozen ? fscale(net, d) : nullptr;
         const float* sh = frozen ? fshift(net, d) : nullptr;
         if (d.kind == kStem) {
@@ -393,8 +400,10 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
                                sc, sh, conv_out, s));
         } else if (d.kind == kDepthwise) {
             Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+            // training: batch statistics of the stored z come out of the same kernel (per-tile partials)
             PROF("dw_fwd", 2.0 * p->N * d.in_h * d.in_w * d.cin + out_bytes,
-                 dw_conv_fwd(p->buf[d.input].y, net->params + d.w_off, g, sc, sh, d.act, conv_out, s));
+                 dw_conv_fwd_tiled(p->buf[d.input].y, net->params + d.w_off, g, nullptr, nullptr, 0, sc, sh, d.act, conv_out,
+                                   frozen ? nullptr : p->bn_ws, &dw_rows, s));
         } else {
             const double gb = 2.0 * M * d.k_rows + 2.0 * d.k_rows * d.cout + out_bytes + ((frozen && d.residual >= 0) ? out_bytes : 0.0);
             PROF("gemm_fwd", gb, gemm_launch(frozen ? p->fwd_frozen[i] : p->fwd_train[i], s));
@@ -403,6 +412,8 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
             BnLayer bl = bn_layer(net, d, M);
             if (d.kind == kConv1x1 && p->fwd_train[i].d.stats_partial)
                 PROF("bn_finalize", 16.0 * p->fwd_train[i].grid * d.cout, bn_finalize_partials(p->bn_ws, p->fwd_train[i].grid, bl, update_moving ? 1 : 0, s));
+            else if (d.kind == kDepthwise)
+                PROF("bn_finalize", 16.0 * dw_rows * d.cout, bn_finalize_partials(p->bn_ws, dw_rows, bl, update_moving ? 1 : 0, s));
             else
                 PROF("bn_stats", out_bytes, bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s));
             PROF("bn_apply", (d.residual >= 0 ? 3.0 : 2.0) * out_bytes,
@@ -423,6 +434,7 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     HeadGeom hg = net->head; hg.N = p->N; hg.normalize = normalize ? 1 : 0;
     const LayerDef& lg = L[nl - 1];
     const long long M16 = static_cast<long long>(p->N) * lg.out_h * lg.out_w;
+    net->prof.layer = lg.name.c_str();
     PROF("head_loss_bwd", static_cast<double>(p->N) * c.height * c.width + 4.0 * M16 * 32 * 2,
          head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s));
     PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
@@ -431,6 +443,7 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     for (int i = nl - 2; i >= 0; --i) {
         const LayerDef& d = L[i];
         if (d.kind == kImagePool) continue;          // handled together with concat_projection
+        net->prof.layer = d.name.c_str();
         const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
         LayerBuf& b = p->buf[i];
         BnLayer bl = bn_layer(net, d, M);

@@ -72,6 +72,8 @@ struct ProfEntry { std::string tag; double algo_bytes = 0; cudaEvent_t e0 = null
 struct ProfAgg { long long launches = 0; double ms = 0, algo_bytes = 0; };
 struct Profiler {
     bool enabled = false;
+    bool per_layer = false;            // tags become "group@layer" (diagnostics: tools/profile_layers.py)
+    const char* layer = nullptr;
     std::vector<ProfEntry> pending;
     std::vector<cudaEvent_t> pool;
     std::map<std::string, ProfAgg> agg;

@@ -218,11 +218,11 @@ class Student:
 
     # ------------------------------------------------------------------ profiling
     def profile_enable(self, on=True):
-        nat.check(self._L.ams_profile_enable(self._h, 1 if on else 0))
+        nat.check(self._L.ams_profile_enable(self._h, int(on)))
 
     def profile_report(self):
         """{tag: dict(launches, ms, algo_bytes)} accumulated since profile_enable(True)."""
-        buf = C.create_string_buffer(1 << 16)
+        buf = C.create_string_buffer(1 << 19)
         self._L.ams_profile_report(self._h, buf, len(buf))
         out = {}
         for line in buf.value.decode().splitlines():

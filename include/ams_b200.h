@@ -145,6 +145,11 @@ int ams_op_conv1x1(const void* a_bf16, const void* w_bf16 /*[N][K]*/, int M, int
 int ams_op_wgrad(const void* x_bf16, int cin, const void* dz_bf16, int cout, long long M, float* dw, void* stream);
 int ams_op_depthwise(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
                      const float* scale, const float* shift, int act, void* out_bf16, void* stream);
+/* tiled depthwise with the producer's BN+act applied while staging the input (in_scale/in_shift may be NULL) and the
+ * batch statistics of the stored output: stats_out[2][c] fp64 DEVICE = column sums (sum, sum of squares) */
+int ams_op_depthwise_fused(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
+                           const float* in_scale, const float* in_shift, int in_act, void* out_bf16, double* stats_out,
+                           void* stream);
 int ams_op_depthwise_bwd(const void* x_bf16, const void* dz_bf16, const float* w, int n, int h, int w_, int c, int stride,
                          int dilation, void* dx_bf16, float* dw, void* stream);
 int ams_op_stem(const void* frames, int frames_dtype, int n, int h, int w_, const float* w, const float* scale,

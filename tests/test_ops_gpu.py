@@ -120,6 +120,32 @@ def test_depthwise_fwd(n, h, w, c, stride, dil):
     assert ok1 and ok2
 
 
+@pytest.mark.parametrize('n,h,w,c,stride,dil', [(2, 33, 65, 32, 1, 1), (1, 65, 129, 96, 2, 1), (2, 17, 33, 960, 1, 2),
+                                                (1, 64, 30, 144, 2, 1), (1, 9, 17, 384, 1, 1), (2, 129, 257, 192, 1, 1)])
+def test_depthwise_fused_bn_on_load_and_stats(n, h, w, c, stride, dil):
+    """Training-mode depthwise: the producer's BN + ReLU6 is applied while the tile is staged (the normalised tensor
+    is never materialised; conv zero padding stays zero AFTER the activation) and the batch statistics of the stored
+    bf16 output come out of the same kernel."""
+    L = nat.lib()
+    z = bf16_round(rnd(n, h, w, c, seed=23, scale=2.0))
+    wt = rnd(3, 3, c, seed=24, scale=0.4)
+    sc = torch.rand(c) + 0.5
+    sh = rnd(c, seed=25, scale=0.5)
+    y = bf16_round(torch.addcmul(sh, z, sc).clamp(0, 6))            # fmaf(z, sc, sh): one rounding like the kernel
+    y = bf16_round((z.double() * sc.double() + sh.double()).float().clamp(0, 6))
+    raw = _dw_ref(y, wt, stride, dil)
+    out = torch.full(raw.shape, float('nan'), dtype=BF, device=DEV)
+    stats = torch.full((2, c), float('nan'), dtype=torch.float64, device=DEV)
+    call(L.ams_op_depthwise_fused, P(z.to(DEV, BF)), P(wt.to(DEV)), n, h, w, c, stride, dil, P(sc.to(DEV)), P(sh.to(DEV)), 2,
+         P(out), P(stats), stream_ptr())
+    torch.cuda.synchronize()
+    ok, _ = err_stats('depthwise fused (BN on load) %s s%d d%d' % ((n, h, w, c), stride, dil), out, raw, ULP, 2e-3)
+    assert ok
+    o = out.float().cpu().double().reshape(-1, c)
+    assert torch.allclose(stats[0].cpu(), o.sum(0), rtol=1e-6, atol=1e-4)
+    assert torch.allclose(stats[1].cpu(), (o * o).sum(0), rtol=1e-6, atol=1e-4)
+
+
 @pytest.mark.parametrize('n,h,w,c,stride,dil', [(2, 33, 65, 32, 1, 1), (1, 65, 129, 96, 2, 1), (2, 17, 33, 960, 1, 2), (1, 64, 30, 144, 2, 1)])
 def test_depthwise_bwd(n, h, w, c, stride, dil):
     L = nat.lib()
