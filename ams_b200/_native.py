@@ -72,6 +72,7 @@ _SIGNATURES = {
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     'ams_op_depthwise_fused': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    'ams_op_depthwise_bwd_fused': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'ams_op_depthwise_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'ams_op_stem': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     'ams_op_stem_bwd': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -513,6 +513,12 @@ int ams_get_activation(ams_net* h, int index, int which, uint16_t* host, long lo
     const bf16* src = which == 0 ? p->buf[index].y : (which == 1 ? p->buf[index].z : p->buf[index].g);
     AMS_REQUIRE(src != nullptr, "layer has no such buffer");
     const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
+    if (which == 0 && p->last_was_train && p->lazy_y[index]) {
+        // batch-statistics passes never materialise this layer's normalised output (its consumer applies the BN while
+        // staging): produce it on demand for the parity hooks, with the same arithmetic
+        const float* pool = net->bnpool + d.bn_off;
+        if (bn_apply(p->buf[index].z, pool, pool + d.cout, d.act, nullptr, p->buf[index].y, M, d.cout, net->stream)) return -1;
+    }
     AMS_REQUIRE(count == M * d.cout, "activation element count mismatch");
     AMS_CUDA_CHECK(cudaMemcpyAsync(host, src, count * 2, cudaMemcpyDeviceToHost, net->stream));
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
@@ -650,6 +656,31 @@ int ams_op_depthwise_fused(const void* in, const float* w, int n, int h, int w_,
     }
     cudaStreamSynchronize(as_stream(stream));
     if (ws) cudaFree(ws);
+    return rc;
+}
+
+int ams_op_depthwise_bwd_fused(const void* g, const void* z, const float* scale, const float* shift, int act, const float* coef,
+                               const void* zin, const float* in_scale, const float* in_shift, int in_act, const float* w,
+                               int n, int h, int w_, int c, int stride, int dil, void* gout, float* dw, double* bn_sums,
+                               void* stream) {
+    const Conv2dGeom gm = make_geom(n, h, w_, c, stride, dil);
+    const long long rows = dw_bwd_fused_rows(gm);
+    float* wsf = nullptr; double* wsd = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&wsf), static_cast<size_t>(rows) * 9 * c * sizeof(float)));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&wsd), static_cast<size_t>(rows) * 2 * c * sizeof(double)));
+    DwBwdFused f;
+    f.g = static_cast<const bf16*>(g); f.z = static_cast<const bf16*>(z); f.scale = scale; f.shift = shift; f.act = act; f.coef = coef;
+    f.zin = static_cast<const bf16*>(zin); f.in_scale = in_scale; f.in_shift = in_shift; f.in_act = in_act; f.w = w;
+    f.gout = static_cast<bf16*>(gout); f.dw = dw; f.dw_partial = wsf; f.dw_partial_floats = static_cast<size_t>(rows) * 9 * c;
+    f.bn_partial = wsd;
+    int got = 0;
+    int rc = dw_conv_bwd_fused(f, gm, &got, as_stream(stream));
+    if (!rc && bn_sums && in_scale) {
+        sum_rows_kernel<<<ceil_div(2 * c, 128), 128, 0, as_stream(stream)>>>(wsd, got, 2 * c, bn_sums);
+        if (cudaGetLastError() != cudaSuccess) rc = -1;
+    }
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(wsf); cudaFree(wsd);
     return rc;
 }
 

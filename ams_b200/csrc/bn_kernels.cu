@@ -488,6 +488,32 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     return 0;
 }
 
+int bn_backward_reduce(const bf16* dy, const bf16* z, const BnLayer& L, int act, float* coef, float* d_gamma, float* d_beta,
+                       double* ws, cudaStream_t s) {
+    const int chunks = red_chunks(L.M, L.C);
+    const long long rpc = ceil_div_ll(L.M, chunks);
+    bn_bwd_reduce_kernel<<<chunks, kRedThreads, red_smem(L.C), s>>>(dy, nullptr, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    AMS_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer& L, float* coef, float* d_gamma,
+                                  float* d_beta, cudaStream_t s) {
+    bn_bwd_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(partial, rows, L, d_gamma, d_beta, coef);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
+int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s) {
+    const long long total8 = L.M * L.C / 8;
+    bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s>>>(dy_masked, nullptr, z, L.scale, L.shift, coef, 0,
+                                                                                   total8, L.C, dz_out);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+
 int colsum_groups(const float* xf, const bf16* xb, int ld, long long rows_per_group, int groups, int C, float scale,
                   float* out, double* workspace, cudaStream_t s) {
     dim3 grid(groups, ceil_div(C, 64), kColsumSplits);

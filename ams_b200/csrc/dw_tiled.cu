@@ -281,6 +281,340 @@ int launch_fwd_cb(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
     return launch_fwd<S, D, 32>(p, t, s);
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused backward
+// One kernel for everything between "gradient wrt the depthwise layer's activated output" and "gradient wrt the raw
+// output of the layer that feeds it":
+//   staging : gz = bf16(A*mask(g) + B*z + Cc)   BatchNorm backward of the depthwise layer itself, applied while the
+//             tile of (g, z) with its halo is loaded (A, B, Cc from the column sums of a previous reduce pass)
+//   compute : per INPUT pixel i (tile owner) and tap k:  o = (i + pad - k*D) / S
+//             dX[i]   = sum_k w[k] * gz[o]               (data gradient)
+//             dW[k]  += x[i] * gz[o]                     (filter gradient; every (o,k) pair is owned by exactly one i)
+//             x[i]    = bf16(act(z_in*sc+sh))            the producer's BN+act recomputed from its raw output
+//             gm      = act'(..) ? bf16(dX[i]) : 0       stored as the gradient wrt the producer's BN output
+//             S1 += gm, S2 += gm * z_in                  column sums for the producer's BatchNorm backward
+// so the normalised input, the depthwise dz and the unmasked dX never exist in HBM: 3 tensor reads + 1 write
+// instead of 9 reads + 4 writes (bn_bwd reduce/apply + dw_bwd_filter + dw_bwd_data + next bn_bwd reduce).
+struct DwBwdParams {
+    const bf16* g; const bf16* z;                 // [N,Ho,Wo,C] gradient wrt act(BN(z)) and the raw depthwise output
+    const float* scale; const float* shift; int act;          // the depthwise layer's BN (activation mask)
+    const float* coef;                            // [3][C]: A, B, Cc of its BN backward
+    const bf16* zin;                              // [N,H,W,C] raw output of the producer (or its activation if in_scale == null)
+    const float* in_scale; const float* in_shift; int in_act;
+    const float* w;                               // [9][C]
+    bf16* gout;                                   // [N,H,W,C]
+    float* dw_partial;                            // [tile][9][C]
+    double* bn_partial;                           // [tile][2][C]  (null if in_scale == null)
+    int N, H, W, C, Ho, Wo, pad_top, pad_left;
+    int th, twt, ntx, nty, chunks, nstrips, oh, owp;
+};
+
+template <int S, int D, int PADX>
+struct BwdCols {
+    // staged column (relative to the strip's first staged column) read by input pixel t of the strip for tap kx, or -1
+    __host__ __device__ static constexpr int col(int t, int kx) {
+        return S == 1 ? (t + 2 * D - kx * D)
+                      : (((t + PADX - kx) % 2 != 0) ? -1 : ((t + PADX - kx + 2) / 2 - PADX));
+    }
+    static constexpr int NJ = S == 1 ? (kStrip + 2 * D) : 3;
+    static constexpr int STRIP_COLS = kStrip / S;       // staged columns a strip advances by
+};
+
+template <int S, int D, int CB, int PADX>
+__global__ void __launch_bounds__(dw_threads(CB), 2)
+dw_bwd_fused_kernel(const DwBwdParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int THREADS = dw_threads(CB), CV4 = CB / kCh, NPT = THREADS / CV4, CV8 = CB / 8, PXT = THREADS / CV8;
+    typedef BwdCols<S, D, PADX> Cols;
+    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+    const int chunk = blockIdx.x % p.chunks;
+    int t_ = blockIdx.x / p.chunks;
+    const long long tile = t_;
+    const int tx = t_ % p.ntx; t_ /= p.ntx;
+    const int ty = t_ % p.nty;
+    const int n = t_ / p.nty;
+    const int c_base = chunk * CB;
+    const int iy0 = ty * p.th, ix0 = tx * p.twt;
+    // first staged output row / column
+    const int oy_lo = S == 1 ? (iy0 + p.pad_top - 2 * D) : (iy0 / 2 - 1 + p.pad_top);
+    const int ox_lo = S == 1 ? (ix0 + p.pad_left - 2 * D) : (ix0 / 2 - 1 + p.pad_left);
+    const uint32_t w_smem = sbase;                                        // [9][CB] fp32
+    const uint32_t tile_smem = sbase + 9 * CB * 4;
+
+    // ---------------------------------------------------------------- stage gz = BN-backward(g, z) (+ halo)
+    {
+        const int c8 = threadIdx.x % CV8, lane_px = threadIdx.x / CV8;
+        const int c0 = c_base + c8 * 8;
+        float sc[8], sh[8], ca[8], cb[8], cc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            sc[q] = p.scale[c0 + q]; sh[q] = p.shift[c0 + q];
+            ca[q] = p.coef[c0 + q]; cb[q] = p.coef[p.C + c0 + q]; cc[q] = p.coef[2 * p.C + c0 + q];
+        }
+        for (int i = threadIdx.x; i < 9 * CB; i += THREADS) {
+            const int k = i / CB, c = i - k * CB;
+            reinterpret_cast<float*>(smem)[i] = p.w[k * p.C + c_base + c];
+        }
+        constexpr int U = 2;
+        int ly = lane_px / p.owp, lx = lane_px - ly * p.owp;
+        const int step_y = PXT / p.owp, step_x = PXT - step_y * p.owp;
+        uint32_t sdst = tile_smem + (lane_px * CB + c8 * 8) * 2;
+        const long long img = static_cast<long long>(n) * p.Ho * p.Wo * p.C + c0;
+        uint4 vg[U], vz[U], ng[U], nz[U];
+        int st[U], stn[U];
+        auto issue = [&](uint4* dg, uint4* dz, int* state) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int gy = oy_lo + ly, gx = ox_lo + lx;
+                state[u] = ly < p.oh ? ((gy >= 0 && gy < p.Ho && gx >= 0 && gx < p.Wo) ? 2 : 1) : 0;
+                if (state[u] == 2) {
+                    const long long off = img + (static_cast<long long>(gy) * p.Wo + gx) * p.C;
+                    dg[u] = ldg_stream(p.g + off);
+                    dz[u] = ldg_stream(p.z + off);
+                }
+                lx += step_x; ly += step_y;
+                if (lx >= p.owp) { lx -= p.owp; ++ly; }
+            }
+        };
+        issue(ng, nz, stn);
+        while (stn[0]) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) { vg[u] = ng[u]; vz[u] = nz[u]; st[u] = stn[u]; }
+            if (st[U - 1]) issue(ng, nz, stn); else stn[0] = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (st[u]) {
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (st[u] == 2) {
+                        float g[8], z[8];
+                        unpack8(vg[u], g);
+                        unpack8(vz[u], z);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float yh = fmaf(z[q], sc[q], sh[q]);
+                            float gm = g[q];
+                            if (p.act == 1) gm = yh > 0.f ? gm : 0.f;
+                            else if (p.act == 2) gm = (yh > 0.f && yh < 6.f) ? gm : 0.f;
+                            g[q] = fmaf(ca[q], gm, fmaf(cb[q], z[q], cc[q]));
+                        }
+                        o = pack8(g);
+                    }
+                    sts128(sdst + u * (PXT * CB * 2), o);
+                }
+            }
+            sdst += U * (PXT * CB * 2);
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- compute: thread = 4 channels x strips of 4 input pixels
+    const int l4 = threadIdx.x % CV4, pt = threadIdx.x / CV4;
+    const int c0 = c_base + l4 * kCh;
+    float isc[kCh], ish[kCh];
+    if (p.in_scale) {
+#pragma unroll
+        for (int q = 0; q < kCh; ++q) { isc[q] = p.in_scale[c0 + q]; ish[q] = p.in_shift[c0 + q]; }
+    }
+    float2 dW[9][2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dW[k][0] = dW[k][1] = make_float2(0.f, 0.f);
+    float2 s1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    const uint32_t row_bytes = static_cast<uint32_t>(p.owp) * CB * 2;
+    const uint32_t w_mine = w_smem + l4 * kCh * 4;
+    int r = pt / p.nstrips, s = pt - r * p.nstrips;
+    const int step_r = NPT / p.nstrips, step_s = NPT - step_r * p.nstrips;
+    for (; r < p.th; r += step_r, s += step_s) {
+        if (s >= p.nstrips) { s -= p.nstrips; ++r; if (r >= p.th) break; }
+        const int iy = iy0 + r;
+        if (iy >= p.H) continue;
+        const int lx0 = s * kStrip;
+        // the producer's output at the strip's 4 pixels -> x (activated, bf16-rounded) and the activation mask
+        const bf16* zrow = p.zin + ((static_cast<long long>(n) * p.H + iy) * p.W + ix0 + lx0) * p.C + c0;
+        uint2 zraw[kStrip];
+        bool pvalid[kStrip];
+#pragma unroll
+        for (int a = 0; a < kStrip; ++a) {
+            pvalid[a] = (lx0 + a < p.twt) && (ix0 + lx0 + a < p.W);
+            zraw[a] = make_uint2(0u, 0u);
+            if (pvalid[a]) zraw[a] = *reinterpret_cast<const uint2*>(zrow + static_cast<long long>(a) * p.C);
+        }
+        float2 x[kStrip][2];
+        uint32_t mask = 0;                                  // bit a*4+q: gradient passes at pixel a, channel q
+#pragma unroll
+        for (int a = 0; a < kStrip; ++a) {
+            float f[4] = {bf16_lo(zraw[a].x), bf16_hi(zraw[a].x), bf16_lo(zraw[a].y), bf16_hi(zraw[a].y)};
+            if (p.in_scale) {
+#pragma unroll
+                for (int q = 0; q < kCh; ++q) {
+                    const float pre = fmaf(f[q], isc[q], ish[q]);
+                    const bool pass = p.in_act == 2 ? (pre > 0.f && pre < 6.f) : (p.in_act == 1 ? pre > 0.f : true);
+                    if (pass && pvalid[a]) mask |= 1u << (a * 4 + q);
+                    f[q] = act_apply(pre, p.in_act);
+                }
+                const uint2 pk = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+                x[a][0] = unpack2(pk.x); x[a][1] = unpack2(pk.y);
+            } else {
+                if (pvalid[a]) mask |= 0xfu << (a * 4);
+                x[a][0] = make_float2(f[0], f[1]); x[a][1] = make_float2(f[2], f[3]);
+            }
+            if (!pvalid[a]) x[a][0] = x[a][1] = make_float2(0.f, 0.f);
+        }
+        float2 gx[kStrip][2];
+#pragma unroll
+        for (int a = 0; a < kStrip; ++a) gx[a][0] = gx[a][1] = make_float2(0.f, 0.f);
+        const uint32_t strip_base = tile_smem + (s * Cols::STRIP_COLS * CB + l4 * kCh) * 2;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ay = iy + p.pad_top - ky * D;
+            if (S == 2 && (ay & 1)) continue;
+            const int orow = (S == 1 ? ay : (ay >> 1)) - oy_lo;            // in [0, oh): rows outside the image are staged zeros
+            const uint32_t rowp = strip_base + static_cast<uint32_t>(orow) * row_bytes;
+            float2 wv[3][2];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                float4 wf;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(wf.x), "=f"(wf.y), "=f"(wf.z), "=f"(wf.w)
+                             : "r"(w_mine + (ky * 3 + kx) * (CB * 4)));
+                wv[kx][0] = make_float2(wf.x, wf.y); wv[kx][1] = make_float2(wf.z, wf.w);
+            }
+#pragma unroll
+            for (int j = 0; j < Cols::NJ; ++j) {
+                const uint2 raw = lds64(rowp + j * (CB * 2));
+                const float2 v0 = unpack2(raw.x), v1 = unpack2(raw.y);
+#pragma unroll
+                for (int a = 0; a < kStrip; ++a) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        if (Cols::col(a, kx) == j) {
+                            ffma2(gx[a][0], v0, wv[kx][0]); ffma2(gx[a][1], v1, wv[kx][1]);
+                            ffma2(dW[ky * 3 + kx][0], x[a][0], v0); ffma2(dW[ky * 3 + kx][1], x[a][1], v1);
+                        }
+                    }
+                }
+            }
+        }
+        bf16* orow_p = p.gout + ((static_cast<long long>(n) * p.H + iy) * p.W + ix0 + lx0) * p.C + c0;
+#pragma unroll
+        for (int a = 0; a < kStrip; ++a) {
+            if (!pvalid[a]) continue;
+            float f[4] = {gx[a][0].x, gx[a][0].y, gx[a][1].x, gx[a][1].y};
+#pragma unroll
+            for (int q = 0; q < kCh; ++q) if (!((mask >> (a * 4 + q)) & 1u)) f[q] = 0.f;
+            const uint2 pk = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            *reinterpret_cast<uint2*>(orow_p + static_cast<long long>(a) * p.C) = pk;
+            if (p.bn_partial) {
+                const float2 g0 = unpack2(pk.x), g1 = unpack2(pk.y);
+                const float2 z0 = unpack2(zraw[a].x), z1 = unpack2(zraw[a].y);
+                fadd2(s1[0], g0); fadd2(s1[1], g1);
+                ffma2(s2[0], g0, z0); ffma2(s2[1], g1, z1);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- fixed-order block reductions -> per-tile partials
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem);                // [NPT][11][CB]
+    {
+        float* mine = red + static_cast<size_t>(pt) * 11 * CB + l4 * kCh;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            mine[k * CB + 0] = dW[k][0].x; mine[k * CB + 1] = dW[k][0].y; mine[k * CB + 2] = dW[k][1].x; mine[k * CB + 3] = dW[k][1].y;
+        }
+        mine[9 * CB + 0] = s1[0].x; mine[9 * CB + 1] = s1[0].y; mine[9 * CB + 2] = s1[1].x; mine[9 * CB + 3] = s1[1].y;
+        mine[10 * CB + 0] = s2[0].x; mine[10 * CB + 1] = s2[0].y; mine[10 * CB + 2] = s2[1].x; mine[10 * CB + 3] = s2[1].y;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 11 * CB; i += THREADS) {
+        const int k = i / CB, c = i - k * CB;
+        if (k < 9) {
+            float a = 0.f;
+            for (int q = 0; q < NPT; ++q) a += red[static_cast<size_t>(q) * 11 * CB + i];
+            p.dw_partial[(tile * 9 + k) * p.C + c_base + c] = a;
+        } else if (p.bn_partial) {
+            double a = 0.0;
+            for (int q = 0; q < NPT; ++q) a += static_cast<double>(red[static_cast<size_t>(q) * 11 * CB + i]);
+            p.bn_partial[(tile * 2 + (k - 9)) * p.C + c_base + c] = a;
+        }
+    }
+}
+
+// out[i] = sum over rows of partial[row][i]; block = 32 outputs x 32 row-lanes (coalesced), fixed order => deterministic
+__global__ void __launch_bounds__(1024)
+dw_reduce_rows_kernel(const float* __restrict__ partial, int rows, int n, float* __restrict__ out) {
+    __shared__ double s_s[32][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cl;
+    double a = 0.0;
+    if (i < n) {
+#pragma unroll 4
+        for (int r = rl; r < rows; r += 32) a += static_cast<double>(partial[static_cast<long long>(r) * n + i]);
+    }
+    s_s[rl][cl] = a;
+    __syncthreads();
+    if (rl != 0 || i >= n) return;
+    for (int k = 1; k < 32; ++k) a += s_s[k][cl];
+    out[i] = static_cast<float>(a);
+}
+
+struct DwBwdTile { int th, twt, ntx, nty, cb, chunks, nstrips, oh, owp; size_t smem; long long blocks; };
+
+DwBwdTile pick_bwd_tile(const Conv2dGeom& g, size_t smem_cap) {
+    DwBwdTile best{};
+    double best_cost = 1e300;
+    const int cb = pick_cb(g.C);
+    if (!cb) return best;
+    const int S = g.stride, D = g.dil;
+    const int cv4 = cb / kCh;
+    const int npt = 256 / cv4;
+    const size_t fixed = 9 * static_cast<size_t>(cb) * 4;
+    for (int th = 2; th <= 32; th += (S == 2 ? 2 : 1)) {
+        const int nty = ceil_div(g.H, th);
+        for (int ntx = 1; ntx <= 40; ++ntx) {
+            int twt = ceil_div(g.W, ntx);
+            if (S == 2) twt += twt & 1;                         // even tile origins keep the tap parity compile-time
+            if (twt < 8 && ntx > 1) break;
+            if (ceil_div(g.W, twt) != ntx) continue;
+            const int nstrips = ceil_div(twt, kStrip);
+            const int oh = S == 1 ? th + 2 * D : th / 2 + 1;
+            const int owp = S == 1 ? nstrips * kStrip + 2 * D : nstrips * 2 + 1;
+            size_t smem = fixed + static_cast<size_t>(oh) * owp * cb * 2;
+            if (smem > smem_cap) continue;
+            smem = std::max(smem, static_cast<size_t>(npt) * 11 * cb * sizeof(float));
+            const int iters = ceil_div(th * nstrips, npt);
+            const long long blocks = static_cast<long long>(g.N) * nty * ntx * (g.C / cb);
+            const double compute = static_cast<double>(iters) * npt * kStrip * 2.0;
+            const double stage = static_cast<double>(oh) * owp * 1.2;
+            const double waves = static_cast<double>(ceil_div_ll(blocks, kNumSMs * 2LL));
+            const double cost = waves * (compute + stage + 400.0);
+            if (cost < best_cost) {
+                best_cost = cost;
+                best = DwBwdTile{th, twt, ntx, nty, cb, g.C / cb, nstrips, oh, owp, smem, blocks};
+            }
+        }
+    }
+    return best;
+}
+
+constexpr size_t kBwdSmemCap = 100 * 1024;
+
+template <int S, int D, int CB, int PADX>
+int launch_bwd(const DwBwdParams& p, const DwBwdTile& t, cudaStream_t s) {
+    static bool attr = false;
+    if (!attr) {
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_bwd_fused_kernel<S, D, CB, PADX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        attr = true;
+    }
+    dw_bwd_fused_kernel<S, D, CB, PADX><<<static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s>>>(p);
+    AMS_LAUNCH_CHECK();
+    return 0;
+}
+template <int S, int D, int PADX>
+int launch_bwd_cb(const DwBwdParams& p, const DwBwdTile& t, cudaStream_t s) {
+    if (t.cb == 64) return launch_bwd<S, D, 64, PADX>(p, t, s);
+    if (t.cb == 48) return launch_bwd<S, D, 48, PADX>(p, t, s);
+    return launch_bwd<S, D, 32, PADX>(p, t, s);
+}
+
 }  // namespace
 
 // diagnostics (tools/): the tile the planner picks for a geometry
@@ -319,6 +653,36 @@ int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const
     if (g.stride == 1 && g.dil == 1) return launch_fwd_cb<1, 1>(p, t, s);
     if (g.stride == 2 && g.dil == 1) return launch_fwd_cb<2, 1>(p, t, s);
     return launch_fwd_cb<1, 2>(p, t, s);
+}
+
+
+long long dw_bwd_fused_rows(const Conv2dGeom& g) {
+    const DwBwdTile t = pick_bwd_tile(g, kBwdSmemCap);
+    return static_cast<long long>(g.N) * t.nty * t.ntx;
+}
+
+int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s) {
+    AMS_REQUIRE(dw_tiled_supported(g), "fused depthwise backward: unsupported channels / stride / dilation");
+    const DwBwdTile t = pick_bwd_tile(g, kBwdSmemCap);
+    AMS_REQUIRE(t.blocks > 0, "fused depthwise backward: no tile fits shared memory");
+    const long long rows = static_cast<long long>(g.N) * t.nty * t.ntx;
+    AMS_REQUIRE(a.dw_partial_floats >= static_cast<size_t>(rows) * 9 * g.C, "fused depthwise backward: dW workspace too small");
+    DwBwdParams p;
+    p.g = a.g; p.z = a.z; p.scale = a.scale; p.shift = a.shift; p.act = a.act; p.coef = a.coef;
+    p.zin = a.zin; p.in_scale = a.in_scale; p.in_shift = a.in_shift; p.in_act = a.in_act; p.w = a.w;
+    p.gout = a.gout; p.dw_partial = a.dw_partial; p.bn_partial = a.in_scale ? a.bn_partial : nullptr;
+    p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.Ho = g.Ho; p.Wo = g.Wo; p.pad_top = g.pad_top; p.pad_left = g.pad_left;
+    p.th = t.th; p.twt = t.twt; p.ntx = t.ntx; p.nty = t.nty; p.chunks = t.chunks; p.nstrips = t.nstrips; p.oh = t.oh; p.owp = t.owp;
+    int rc;
+    if (g.stride == 1 && g.dil == 1) rc = launch_bwd_cb<1, 1, 0>(p, t, s);
+    else if (g.stride == 1) rc = launch_bwd_cb<1, 2, 0>(p, t, s);
+    else if (g.pad_left & 1) rc = launch_bwd_cb<2, 1, 1>(p, t, s);
+    else rc = launch_bwd_cb<2, 1, 0>(p, t, s);
+    if (rc) return rc;
+    dw_reduce_rows_kernel<<<ceil_div(9 * g.C, 32), 1024, 0, s>>>(a.dw_partial, static_cast<int>(rows), 9 * g.C, a.dw);
+    AMS_LAUNCH_CHECK();
+    if (rows_out) *rows_out = static_cast<int>(rows);
+    return 0;
 }
 
 }  // namespace ams

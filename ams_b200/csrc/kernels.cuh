@@ -42,6 +42,21 @@ int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const
                       int in_act, const float* out_scale, const float* out_shift, int out_act, bf16* out, double* stats,
                       int* stats_rows, cudaStream_t s);
 
+// fused backward (dw_tiled.cu): BN backward of the depthwise layer applied while (g, z) is staged, data gradient +
+// filter gradient from the same staged tile, the producer's BN+act recomputed from its raw output `zin`, activation
+// mask applied to the stored gradient, column sums for the producer's BN backward.  coef = [3][C] (A, B, Cc) of
+// bn_backward_reduce.  in_scale == null: `zin` is the (materialised) input activation and bn_partial is not written.
+struct DwBwdFused {
+    const bf16* g; const bf16* z; const float* scale; const float* shift; int act; const float* coef;
+    const bf16* zin; const float* in_scale; const float* in_shift; int in_act;
+    const float* w;
+    bf16* gout; float* dw;                  // [N,H,W,C] gradient wrt the producer's BN output (masked); dW [9][C]
+    float* dw_partial; size_t dw_partial_floats;    // >= dw_bwd_fused_rows * 9 * C
+    double* bn_partial;                     // [rows][2][C]
+};
+long long dw_bwd_fused_rows(const Conv2dGeom& g);
+int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s);
+
 // ---- BatchNorm, training mode
 struct BnLayer {            // device pointers into the parameter / state arenas, all [C] fp32
     int C;
@@ -67,6 +82,16 @@ int bn_fold_frozen(const float* gamma, const float* beta, const float* mv_mean, 
 // If dy2 != null the incoming gradient is dy + dy2 (two consumers).
 int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, bf16* dz_out,
                 float* d_gamma, float* d_beta, double* workspace, cudaStream_t s);
+
+// the three pieces of bn_backward, for callers that fuse the apply pass (or the reduce pass) into another kernel:
+// column sums of (dy masked, dy masked * z) -> coef [3][C] (dz = A*g + B*z + Cc), d_gamma, d_beta
+int bn_backward_reduce(const bf16* dy, const bf16* z, const BnLayer& L, int act, float* coef, float* d_gamma, float* d_beta,
+                       double* workspace, cudaStream_t s);
+// same from per-tile partial sums [rows][2][C] a producer kernel wrote (dy already masked)
+int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer& L, float* coef, float* d_gamma,
+                                  float* d_beta, cudaStream_t s);
+// dz = A*dy + B*z + Cc for an already-masked dy (dz_out may alias dy)
+int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s);
 
 // ---- ASPP image-pooling branch folded into a per-image bias
 struct ImgPoolFwd {

@@ -218,6 +218,18 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
         p->buf.resize(L.size());
         p->fwd_frozen.resize(L.size()); p->fwd_train.resize(L.size()); p->dgrad.resize(L.size()); p->wgrad.resize(L.size());
         p->has_fwd.assign(L.size(), 0); p->has_dgrad.assign(L.size(), 0); p->has_wgrad.assign(L.size(), 0);
+        p->dw_fused.assign(L.size(), 0); p->lazy_y.assign(L.size(), 0);
+        const char* nofuse = getenv("AMS_NO_DW_FUSION");
+        for (size_t i = 0; i < L.size(); ++i) {
+            const LayerDef& d = L[i];
+            if (d.kind != kDepthwise || (nofuse && nofuse[0] == '1')) continue;
+            Conv2dGeom g{N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+            if (!dw_tiled_supported(g) || !L[d.input].has_bn) continue;
+            p->dw_fused[i] = 1;
+            p->lazy_y[d.input] = 1;
+        }
+        if (dev_alloc(&p->coef[0], 3 * 1024, &p->allocations)) return -1;
+        if (dev_alloc(&p->coef[1], 3 * 1024, &p->allocations)) return -1;
         if (dev_alloc(reinterpret_cast<float**>(&p->in_frames), static_cast<size_t>(N) * c.height * c.width * 3, &p->allocations)) return -1;
         if (dev_alloc(&p->in_labels, static_cast<size_t>(N) * c.height * c.width, &p->allocations)) return -1;
         if (dev_alloc(&p->pred, static_cast<size_t>(N) * c.height * c.width, &p->allocations)) return -1;
@@ -238,6 +250,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             if (d.kind == kDepthwise) {
                 Conv2dGeom g{N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
                 bn_ws = std::max(bn_ws, static_cast<size_t>(dw_tiled_stats_rows(g)) * 2 * d.cout + 3 * static_cast<size_t>(d.cout));
+                bn_ws = std::max(bn_ws, static_cast<size_t>(dw_bwd_fused_rows(g)) * 2 * d.cout + 3 * static_cast<size_t>(d.cout));
             }
         }
         if (dev_alloc(&p->bn_ws, bn_ws, &p->allocations)) return -1;
@@ -294,6 +307,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             if (d.kind == kDepthwise) {
                 Conv2dGeom g{N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
                 red_ws = std::max(red_ws, dw_bwd_workspace_floats(g));
+                red_ws = std::max(red_ws, static_cast<size_t>(dw_bwd_fused_rows(g)) * 9 * d.cin);
             }
             if (d.kind == kStem) red_ws = std::max(red_ws, stem_bwd_workspace_floats(N, d.out_h, d.out_w));
             if (d.kind == kConv1x1) red_ws = std::max(red_ws, wgrad_workspace_floats(d.k_rows, d.cout, M, net->num_sms));
@@ -401,8 +415,12 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
         } else if (d.kind == kDepthwise) {
             Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
             // training: batch statistics of the stored z come out of the same kernel (per-tile partials)
+            const bool lazy_in = !frozen && p->lazy_y[d.input];      // producer's BN + act applied while staging its raw z
+            const LayerDef& pd = L[d.input];
+            const BnLayer pbl = bn_layer(net, pd, 0);
             PROF("dw_fwd", 2.0 * p->N * d.in_h * d.in_w * d.cin + out_bytes,
-                 dw_conv_fwd_tiled(p->buf[d.input].y, net->params + d.w_off, g, nullptr, nullptr, 0, sc, sh, d.act, conv_out,
+                 dw_conv_fwd_tiled(lazy_in ? p->buf[d.input].z : p->buf[d.input].y, net->params + d.w_off, g,
+                                   lazy_in ? pbl.scale : nullptr, lazy_in ? pbl.shift : nullptr, pd.act, sc, sh, d.act, conv_out,
                                    frozen ? nullptr : p->bn_ws, &dw_rows, s));
         } else {
             const double gb = 2.0 * M * d.k_rows + 2.0 * d.k_rows * d.cout + out_bytes + ((frozen && d.residual >= 0) ? out_bytes : 0.0);
@@ -416,8 +434,9 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
                 PROF("bn_finalize", 16.0 * dw_rows * d.cout, bn_finalize_partials(p->bn_ws, dw_rows, bl, update_moving ? 1 : 0, s));
             else
                 PROF("bn_stats", out_bytes, bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s));
-            PROF("bn_apply", (d.residual >= 0 ? 3.0 : 2.0) * out_bytes,
-                 bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s));
+            if (!p->lazy_y[i])
+                PROF("bn_apply", (d.residual >= 0 ? 3.0 : 2.0) * out_bytes,
+                     bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s));
         }
     }
     p->last_was_train = !frozen;
@@ -430,6 +449,7 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     const ams_config& c = net->cfg;
     cudaStream_t s = net->stream;
     const int nl = static_cast<int>(L.size());
+    p->pending_bn_rows = 0;
     // head: loss + d low-res logits
     HeadGeom hg = net->head; hg.N = p->N; hg.normalize = normalize ? 1 : 0;
     const LayerDef& lg = L[nl - 1];
@@ -448,8 +468,32 @@ int net_backward(Net* net, Plan* p, bool normalize) {
         LayerBuf& b = p->buf[i];
         BnLayer bl = bn_layer(net, d, M);
         const double tb = 2.0 * M * d.cout;
-        // reduce pass reads dy,z; apply pass reads dy,z and writes dz
-        PROF("bn_bwd", 5.0 * tb, bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s));
+        if (d.kind == kDepthwise && p->dw_fused[i]) {
+            // BN-backward column sums of this layer, then ONE kernel: BN-backward apply while staging (g, z), filter +
+            // data gradient, the producer's activation mask and the column sums of ITS BN backward
+            const LayerDef& pd = L[d.input];
+            const BnLayer pbl = bn_layer(net, pd, 0);
+            Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
+            PROF("bn_bwd_reduce", 2.0 * tb, bn_backward_reduce(b.g, b.z, bl, d.act, p->coef[0], net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s));
+            DwBwdFused f;
+            f.g = b.g; f.z = b.z; f.scale = bl.scale; f.shift = bl.shift; f.act = d.act; f.coef = p->coef[0];
+            f.zin = p->buf[d.input].z; f.in_scale = pbl.scale; f.in_shift = pbl.shift; f.in_act = pd.act;
+            f.w = net->params + d.w_off; f.gout = p->buf[d.input].g; f.dw = net->grads + d.w_off;
+            f.dw_partial = p->red_ws; f.dw_partial_floats = p->red_ws_floats; f.bn_partial = p->bn_ws;
+            const double ib = 2.0 * p->N * d.in_h * d.in_w * d.cin;
+            PROF("dw_bwd_fused", 2.0 * tb + 2.0 * ib, dw_conv_bwd_fused(f, g, &p->pending_bn_rows, s));
+            continue;
+        }
+        if (p->pending_bn_rows > 0) {
+            // the fused depthwise backward left the masked gradient in b.g and the column sums in bn_ws
+            PROF("bn_bwd_finalize", 16.0 * p->pending_bn_rows * d.cout,
+                 bn_backward_finalize_partials(p->bn_ws, p->pending_bn_rows, bl, p->coef[1], net->grads + d.gamma_off, net->grads + d.beta_off, s));
+            PROF("bn_bwd_apply", 3.0 * tb, bn_backward_apply(b.g, b.z, bl, p->coef[1], b.gz, s));
+            p->pending_bn_rows = 0;
+        } else {
+            // reduce pass reads dy,z; apply pass reads dy,z and writes dz
+            PROF("bn_bwd", 5.0 * tb, bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s));
+        }
         if (d.kind == kConv1x1) {
             PROF("gemm_wgrad", 2.0 * M * d.k_rows + tb, wgrad_launch(p->wgrad[i], s));
             if (d.name == "concat_projection") {

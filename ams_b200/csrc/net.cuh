@@ -63,6 +63,11 @@ struct Plan {
     std::vector<GemmPlan> fwd_frozen, fwd_train, dgrad;
     std::vector<WgradPlan> wgrad;
     std::vector<char> has_fwd, has_dgrad, has_wgrad;
+    // training-mode fusion (dw_tiled.cu): dw_fused[i] = depthwise layer i runs the fused backward and reads its
+    // producer's RAW output; lazy_y[j] = layer j's normalised output is never materialised in training mode
+    std::vector<char> dw_fused, lazy_y;
+    float* coef[2] = {nullptr, nullptr};       // BN-backward coefficients [3][Cmax]: [0] depthwise layer, [1] its producer
+    int pending_bn_rows = 0;                   // > 0: bn_ws holds the fused kernel's column sums for the next layer
     bool have_backward = false;
     bool last_was_train = false;
 };

@@ -150,6 +150,13 @@ int ams_op_depthwise(const void* in_bf16, const float* w, int n, int h, int w_, 
 int ams_op_depthwise_fused(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
                            const float* in_scale, const float* in_shift, int in_act, void* out_bf16, double* stats_out,
                            void* stream);
+/* fused depthwise backward (see ams_b200/csrc/dw_tiled.cu): coef = [3][c] BN-backward coefficients of the depthwise
+ * layer; zin = raw output of the producer whose BN (in_scale/in_shift) + activation is recomputed; bn_sums [2][c] fp64
+ * DEVICE = column sums (masked gradient, masked gradient * zin) for the producer's BN backward */
+int ams_op_depthwise_bwd_fused(const void* g_bf16, const void* z_bf16, const float* scale, const float* shift, int act,
+                               const float* coef, const void* zin_bf16, const float* in_scale, const float* in_shift,
+                               int in_act, const float* w, int n, int h, int w_, int c, int stride, int dilation,
+                               void* gout_bf16, float* dw, double* bn_sums, void* stream);
 int ams_op_depthwise_bwd(const void* x_bf16, const void* dz_bf16, const float* w, int n, int h, int w_, int c, int stride,
                          int dilation, void* dx_bf16, float* dw, void* stream);
 int ams_op_stem(const void* frames, int frames_dtype, int n, int h, int w_, const float* w, const float* scale,

@@ -163,6 +163,55 @@ def test_depthwise_bwd(n, h, w, c, stride, dil):
     assert ok1 and ok2
 
 
+def _fma32(a, b, c):
+    """fp32 fmaf(a, b, c) (one rounding), emulated in float64."""
+    return (a.double() * b.double() + c.double()).float()
+
+
+@pytest.mark.parametrize('n,h,w,c,stride,dil', [(2, 33, 65, 32, 1, 1), (1, 65, 129, 96, 2, 1), (2, 17, 33, 960, 1, 2),
+                                                (1, 64, 30, 144, 2, 1), (1, 9, 17, 384, 1, 1), (2, 129, 257, 192, 1, 1),
+                                                (1, 33, 65, 192, 2, 1), (3, 5, 7, 576, 1, 2)])
+def test_depthwise_bwd_fused(n, h, w, c, stride, dil):
+    """Fused depthwise backward: BN-backward apply of the depthwise layer while staging (g, z), filter + data gradient,
+    the producer's BN + ReLU6 recomputed from its raw output, the activation mask on the stored gradient and the column
+    sums for the producer's BN backward -- against autograd through the same (bf16-stored) tensors."""
+    L = nat.lib()
+    zin = bf16_round(rnd(n, h, w, c, seed=31, scale=2.0))
+    isc = torch.rand(c, generator=torch.Generator().manual_seed(32)) + 0.5
+    ish = rnd(c, seed=33, scale=0.5)
+    pre = _fma32(zin, isc, ish)
+    x = bf16_round(pre.clamp(0, 6)).requires_grad_(True)
+    wt = rnd(3, 3, c, seed=34, scale=0.4).requires_grad_(True)
+    y = _dw_ref(x, wt, stride, dil)
+    z = bf16_round(y.detach())
+    g = bf16_round(rnd(*y.shape, seed=35, scale=0.1))
+    sc2 = torch.rand(c, generator=torch.Generator().manual_seed(36)) + 0.5
+    sh2 = rnd(c, seed=37, scale=0.5) + 1.0
+    coef = torch.stack([torch.rand(c, generator=torch.Generator().manual_seed(38)) + 0.5, rnd(c, seed=39, scale=0.01),
+                        rnd(c, seed=40, scale=0.01)])
+    yh = _fma32(z, sc2, sh2)
+    gm = torch.where((yh > 0) & (yh < 6), g, torch.zeros_like(g))
+    gz = bf16_round(_fma32(coef[0].expand_as(gm), gm, _fma32(coef[1].expand_as(z), z, coef[2].expand_as(z))))
+    y.backward(gz)
+    passm = (pre > 0) & (pre < 6)
+    gout_ref = torch.where(passm, bf16_round(x.grad), torch.zeros_like(pre))
+    gout = torch.full((n, h, w, c), float('nan'), dtype=BF, device=DEV)
+    dw = torch.full((3, 3, c), float('nan'), dtype=torch.float32, device=DEV)
+    sums = torch.full((2, c), float('nan'), dtype=torch.float64, device=DEV)
+    call(L.ams_op_depthwise_bwd_fused, P(g.to(DEV, BF)), P(z.to(DEV, BF)), P(sc2.to(DEV)), P(sh2.to(DEV)), 2, P(coef.to(DEV)),
+         P(zin.to(DEV, BF)), P(isc.to(DEV)), P(ish.to(DEV)), 2, P(wt.detach().to(DEV)), n, h, w, c, stride, dil, P(gout), P(dw),
+         P(sums), stream_ptr())
+    torch.cuda.synchronize()
+    tag = '%s s%d d%d' % ((n, h, w, c), stride, dil)
+    ok1, _ = err_stats('fused dw bwd: masked dX ' + tag, gout, gout_ref, 2 * ULP, 2e-4)   # 9-term fp32 sums in another order: 1-ulp flips
+    ok2, _ = err_stats('fused dw bwd: dW ' + tag, dw, wt.grad, 1e-4, 1e-5 * float(wt.grad.abs().max()))
+    go = gout.float().cpu().double()
+    s1, s2 = go.reshape(-1, c).sum(0), (go * zin.double()).reshape(-1, c).sum(0)
+    assert ok1 and ok2
+    assert torch.allclose(sums[0].cpu(), s1, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(sums[1].cpu(), s2, rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize('n,h,w,u8', [(2, 64, 128, True), (1, 33, 47, False), (1, 48, 80, True)])
 def test_stem(n, h, w, u8):
     L = nat.lib()
