@@ -13,12 +13,11 @@ constexpr int kRedThreads = 256;
 constexpr int kFlush = 16;          // fp32 run length before flushing into fp64
 
 int red_chunks(long long M, int C) {
-    // enough blocks to fill the machine while every thread still walks >= 8 rows; the partial matrix
-    // (chunks x 2C doubles) is kept small so that the one-warp-per-channel finalize stays cheap
+    // enough blocks to fill the machine (several CTAs per SM: these passes are latency-bound on the small layers) while
+    // every thread still walks >= 8 rows; the finalize reads the partial rows coalesced, so many rows are cheap
     const int c8 = C / 8;
     const int rows_per_block = std::max(1, kRedThreads / std::min(c8, kRedThreads));
-    long long want = std::min<long long>(4 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8));
-    want = std::min<long long>(want, std::max<long long>(kNumSMs, 65536 / C));
+    const long long want = std::min<long long>(6 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8));
     return static_cast<int>(std::max<long long>(1, want));
 }
 
