@@ -90,6 +90,9 @@ ams_net* ams_create(const ams_config* cfg) {
     net->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&net->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
     if (cudaStreamCreateWithFlags(&net->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     net->stream = net->own_stream;
     if (net_build_topology(net)) return fail("topology");
     const LayerDef& lg = net->layers.back();
@@ -161,6 +164,9 @@ void ams_destroy(ams_net* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (net->own_stream) cudaStreamDestroy(net->own_stream);
     if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
+    if (net->side_stream) cudaStreamDestroy(net->side_stream);
+    if (net->ev_fork) cudaEventDestroy(net->ev_fork);
+    if (net->ev_join) cudaEventDestroy(net->ev_join);
     delete net;
 }
 

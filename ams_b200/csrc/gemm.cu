@@ -28,6 +28,7 @@ constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;    // 6 warps
 constexpr int kMaxStages = 8;
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kWgradSmemBudget = 100 * 1024;
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -266,6 +267,24 @@ __device__ __forceinline__ void lds8(const float* p, float* o) {
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2f(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+}
+__device__ __forceinline__ void fadd2(float2& d, const float2& a) {
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)));
+}
+
 template <int F>
 __global__ void __launch_bounds__(kGemm2Threads, 2)
 gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -323,7 +342,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    t5::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    t5::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + (p.b_resident ? 0 : stage_b));
                     t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * p.block_k, m_tile * BLOCK_M);
                     if (!p.b_resident)
@@ -335,15 +354,15 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
         int stage = 0; uint32_t phase = 0; int it = 0;
-        if (p.b_resident) t5::mbar_wait(bres_bar, 0);
+        if (p.b_resident) t5::mbar_wait_relaxed(bres_bar, 0);
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int as = (p.acc_stages == 2) ? (it & 1) : 0;
             const uint32_t aphase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-            t5::mbar_wait(&tempty_bar[as], aphase ^ 1);
+            t5::mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1);
             t5::fence_after_thread_sync();
             const uint32_t tmem_d = tmem_base + as * p.block_n;
             for (int kb = 0; kb < p.k_blocks; ++kb) {
-                t5::mbar_wait(&full_bar[stage], phase);
+                t5::mbar_wait_relaxed(&full_bar[stage], phase);
                 t5::fence_after_thread_sync();
                 if (lane == 0) {
                     const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
@@ -369,16 +388,22 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int half = (warp - 2) >> 2;             // which of the two warps of this quarter
         const int row = q * 32 + lane;
         const int nchunks = p.block_n >> 4;
-        // statistics slicing: nslices * block_n <= 256 threads, nslices a power of two <= 16
+        // statistics slicing: nslices * (block_n / 8) <= 256 threads, nslices a power of two <= 16
+        const int ncg = p.block_n >> 3;
         int nslices = 1;
-        while (nslices < 16 && nslices * 2 * p.block_n <= kEpiThreads) nslices <<= 1;
+        while (nslices < 16 && nslices * 2 * ncg <= kEpiThreads) nslices <<= 1;
         const int rows_per_slice = BLOCK_M / nslices;
+        // division-free copy-out: this thread's first 16-byte chunk (row, chunk) and its step per 256 threads
+        const int cpr = max(p.N >> 3, 1);
+        const int co_r0 = et / cpr, co_c0 = et - co_r0 * cpr;
+        const int co_dr = kEpiThreads / cpr, co_dc = kEpiThreads - co_dr * cpr;
         int it = 0, buf = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
             const int as = (p.acc_stages == 2) ? (it & 1) : 0;
             const uint32_t aphase = (p.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
             uint8_t* cbuf = smC + buf * cbuf_bytes;
+            const uint32_t cbuf_s = t5::smem_u32(cbuf);
             // the TMA store that last read this staging buffer must have finished reading it
             if (!p.linear_out && et == 0) { if (p.stage_bufs == 2) t5::tma_store_wait_read<1>(); else t5::tma_store_wait_read<0>(); }
             t5::named_barrier_sync(1, kEpiThreads);
@@ -442,14 +467,14 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 // swizzled staging write: box = 64 columns, 16-byte chunk index XOR (row & 7)
                 if (p.linear_out) {
                     // dense rows of `pitch` bytes (pitch/16 odd => 8 consecutive rows hit 8 different 16-byte bank groups)
-                    uint8_t* rowp = cbuf + row * p.pitch + c0 * 2;
-                    if (c0 < p.N) *reinterpret_cast<uint4*>(rowp) = pack8(v);
-                    if (c0 + 8 < p.N) *reinterpret_cast<uint4*>(rowp + 16) = pack8(v + 8);
+                    const uint32_t rowp = cbuf_s + row * p.pitch + c0 * 2;
+                    if (c0 < p.N) sts128(rowp, pack8(v));
+                    if (c0 + 8 < p.N) sts128(rowp + 16, pack8(v + 8));
                 } else {
-                    uint8_t* rowp = cbuf + (c0 >> 6) * (BLOCK_M * 128) + row * 128;
+                    const uint32_t rowp = cbuf_s + (c0 >> 6) * (BLOCK_M * 128) + row * 128;
                     const int ci = (c0 & 63) >> 3;
-                    *reinterpret_cast<uint4*>(rowp + ((ci ^ (row & 7)) << 4)) = pack8(v);
-                    *reinterpret_cast<uint4*>(rowp + (((ci + 1) ^ (row & 7)) << 4)) = pack8(v + 8);
+                    sts128(rowp + ((ci ^ (row & 7)) << 4), pack8(v));
+                    sts128(rowp + (((ci + 1) ^ (row & 7)) << 4), pack8(v + 8));
                 }
             };
             for (int j = half; j < nchunks; j += 4) {
@@ -467,30 +492,40 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (!p.linear_out) t5::fence_proxy_async_smem();     // generic-proxy writes -> visible to the TMA unit
             t5::named_barrier_sync(2, kEpiThreads);
             if (F & kEpiStats) {
-                // column statistics of the stored bf16 tile: thread = (slice of rows, column)
-                const int c = et % p.block_n, slice = et / p.block_n;
+                // column statistics of the stored bf16 tile: thread = (slice of rows, group of 8 columns), 128-bit
+                // shared-memory reads, packed fp32x2 accumulation
+                const int g8 = et % ncg, slice = et / ncg;
                 if (slice < nslices) {
-                    float s = 0.f, sq = 0.f;
+                    float2 s2[4], q2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s2[k] = q2[k] = make_float2(0.f, 0.f);
                     const int r0 = slice * rows_per_slice;
                     if (p.linear_out) {
-                        const uint8_t* colp = cbuf + c * 2;
-#pragma unroll 8
-                        for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
-                            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * p.pitch));
-                            s += x;
-                            sq = fmaf(x, x, sq);
+                        uint32_t a = cbuf_s + r0 * p.pitch + (g8 << 4);
+#pragma unroll 4
+                        for (int rr = 0; rr < rows_per_slice; ++rr, a += p.pitch) {
+                            const uint4 v = lds128(a);
+                            const float2 f0 = unpack2f(v.x), f1 = unpack2f(v.y), f2 = unpack2f(v.z), f3 = unpack2f(v.w);
+                            fadd2(s2[0], f0); fadd2(s2[1], f1); fadd2(s2[2], f2); fadd2(s2[3], f3);
+                            ffma2(q2[0], f0, f0); ffma2(q2[1], f1, f1); ffma2(q2[2], f2, f2); ffma2(q2[3], f3, f3);
                         }
                     } else {
-                        const uint8_t* colp = cbuf + (c >> 6) * (BLOCK_M * 128) + (c & 7) * 2;
-                        const int ci = (c & 63) >> 3;
-#pragma unroll 8
+                        const uint32_t a0 = cbuf_s + (g8 >> 3) * (BLOCK_M * 128);
+                        const int ci = g8 & 7;
+#pragma unroll 4
                         for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
-                            const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + rr * 128 + ((ci ^ (rr & 7)) << 4)));
-                            s += x;
-                            sq = fmaf(x, x, sq);
+                            const uint4 v = lds128(a0 + rr * 128 + ((ci ^ (rr & 7)) << 4));
+                            const float2 f0 = unpack2f(v.x), f1 = unpack2f(v.y), f2 = unpack2f(v.z), f3 = unpack2f(v.w);
+                            fadd2(s2[0], f0); fadd2(s2[1], f1); fadd2(s2[2], f2); fadd2(s2[3], f3);
+                            ffma2(q2[0], f0, f0); ffma2(q2[1], f1, f1); ffma2(q2[2], f2, f2); ffma2(q2[3], f3, f3);
                         }
                     }
-                    s_part[slice * p.block_n + c] = make_float2(s, sq);
+                    float2* dstp = s_part + slice * p.block_n + (g8 << 3);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        dstp[2 * k] = make_float2(s2[k].x, q2[k].x);
+                        dstp[2 * k + 1] = make_float2(s2[k].y, q2[k].y);
+                    }
                 }
                 t5::named_barrier_sync(3, kEpiThreads);
                 if (et < p.block_n) {
@@ -502,13 +537,14 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
             if (p.linear_out) {
                 // the tile is one contiguous run of global memory (all N columns, ldc == N): fully coalesced 16-byte stores
-                const int cpr = p.N >> 3;                                   // 16-byte chunks per row
                 const int rows_valid = static_cast<int>(min(static_cast<long long>(BLOCK_M), p.M - static_cast<long long>(m_tile) * BLOCK_M));
                 const int total = rows_valid * cpr;
                 uint4* gdst = reinterpret_cast<uint4*>(p.out + static_cast<long long>(m_tile) * BLOCK_M * p.ldc);
+                int rr = co_r0, cc = co_c0;
                 for (int i = et; i < total; i += kEpiThreads) {
-                    const int rr = i / cpr, cc = i - rr * cpr;
-                    stg_stream(gdst + i, *reinterpret_cast<const uint4*>(cbuf + rr * p.pitch + (cc << 4)));
+                    stg_stream(gdst + i, lds128(cbuf_s + rr * p.pitch + (cc << 4)));
+                    cc += co_dc; rr += co_dr;
+                    if (cc >= cpr) { cc -= cpr; ++rr; }
                 }
             } else if (et == 0) {
                 for (int b = 0; b < p.nboxes; ++b)
@@ -830,7 +866,8 @@ int wgrad_plan(const WgradDesc& d, int num_sms, WgradPlan* plan) {
     plan->tmem_cols = tmem_cols_for(plan->block_n);
     const size_t stage_bytes = size_t(2 + plan->boxes_b) * kWgradBoxBytes;
     const size_t fixed = 1024 + (2 * kMaxStages + 2) * 8 + 16;
-    int stages = int((kSmemBudget - fixed) / stage_bytes);
+    // <= ~100 KB: the filter gradients run on a side stream and must leave room for the chain's CTAs on the same SM
+    int stages = int((kWgradSmemBudget - fixed) / stage_bytes);
     plan->stages = std::max(2, std::min(stages, kMaxStages));
     plan->smem_bytes = fixed + plan->stages * stage_bytes;
     if (encode_2d_bf16(&plan->tmX, d.X, d.Cin, d.M, size_t(d.ldx) * 2, 64, BLOCK_K)) return -1;

@@ -290,7 +290,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
         }
     }
     if (need_backward && !p->have_backward) {
-        size_t red_ws = 0;
+        size_t red_ws = 0, wg_ws = 0;
         const LayerDef& lg = L.back();
         const long long M16 = static_cast<long long>(N) * lg.out_h * lg.out_w;
         if (dev_alloc(&p->dlogits_f32, static_cast<size_t>(M16) * 32, &p->allocations)) return -1;
@@ -310,11 +310,13 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
                 red_ws = std::max(red_ws, static_cast<size_t>(dw_bwd_fused_rows(g)) * 9 * d.cin);
             }
             if (d.kind == kStem) red_ws = std::max(red_ws, stem_bwd_workspace_floats(N, d.out_h, d.out_w));
-            if (d.kind == kConv1x1) red_ws = std::max(red_ws, wgrad_workspace_floats(d.k_rows, d.cout, M, net->num_sms));
+            if (d.kind == kConv1x1) wg_ws = std::max(wg_ws, wgrad_workspace_floats(d.k_rows, d.cout, M, net->num_sms));
         }
-        red_ws = std::max(red_ws, wgrad_workspace_floats(lg.cin, lg.cout, M16, net->num_sms));
+        wg_ws = std::max(wg_ws, wgrad_workspace_floats(lg.cin, lg.cout, M16, net->num_sms));
         if (dev_alloc(&p->red_ws, red_ws, &p->allocations)) return -1;
         p->red_ws_floats = red_ws;
+        if (dev_alloc(&p->wgrad_ws, wg_ws, &p->allocations)) return -1;
+        p->wgrad_ws_floats = wg_ws;
         for (size_t i = 0; i < L.size(); ++i) {
             const LayerDef& d = L[i];
             if (d.kind != kConv1x1 && d.kind != kLogits) continue;
@@ -326,7 +328,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             else { w.dZ = p->buf[i].gz; w.ldz = d.cout; }
             w.Cout = d.cout; w.M = M;
             w.dW = net->grads + d.w_off + static_cast<long long>(d.k_rows0) * d.cout; w.lddw = d.cout;
-            w.workspace = p->red_ws; w.workspace_floats = p->red_ws_floats;
+            w.workspace = p->wgrad_ws; w.workspace_floats = p->wgrad_ws_floats;
             if (wgrad_plan(w, net->num_sms, &p->wgrad[i])) return -1;
             p->has_wgrad[i] = 1;
             // data gradient: g[input] = dz * W^T (+ skip gradient / image-pool gradient)
@@ -450,6 +452,16 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     cudaStream_t s = net->stream;
     const int nl = static_cast<int>(L.size());
     p->pending_bn_rows = 0;
+    // Filter gradients of the 1x1 convs: nothing downstream in the backward chain reads them, so outside profiling
+    // they go to a side stream (fork after their dz is ready, one join at the end) and overlap with the chain.
+    const bool side = !net->prof.enabled && net->side_stream != nullptr;
+    bool forked = false;
+    auto wgrad_on_side = [&](const WgradPlan& wp) -> int {
+        AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
+        AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+        forked = true;
+        return wgrad_launch(wp, net->side_stream);
+    };
     // head: loss + d low-res logits
     HeadGeom hg = net->head; hg.N = p->N; hg.normalize = normalize ? 1 : 0;
     const LayerDef& lg = L[nl - 1];
@@ -458,7 +470,8 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     PROF("head_loss_bwd", static_cast<double>(p->N) * c.height * c.width + 4.0 * M16 * 32 * 2,
          head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s));
     PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
-    PROF("gemm_wgrad", 2.0 * M16 * (lg.cin + 32), wgrad_launch(p->wgrad[nl - 1], s));
+    if (side) { if (wgrad_on_side(p->wgrad[nl - 1])) return -1; }
+    else PROF("gemm_wgrad", 2.0 * M16 * (lg.cin + 32), wgrad_launch(p->wgrad[nl - 1], s));
     PROF("gemm_dgrad", 2.0 * M16 * (lg.cin + 32), gemm_launch(p->dgrad[nl - 1], s));
     for (int i = nl - 2; i >= 0; --i) {
         const LayerDef& d = L[i];
@@ -495,7 +508,8 @@ int net_backward(Net* net, Plan* p, bool normalize) {
             PROF("bn_bwd", 5.0 * tb, bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s));
         }
         if (d.kind == kConv1x1) {
-            PROF("gemm_wgrad", 2.0 * M * d.k_rows + tb, wgrad_launch(p->wgrad[i], s));
+            if (side) { if (wgrad_on_side(p->wgrad[i])) return -1; }
+            else PROF("gemm_wgrad", 2.0 * M * d.k_rows + tb, wgrad_launch(p->wgrad[i], s));
             if (d.name == "concat_projection") {
                 const LayerDef& ipd = L[nl - 4];
                 ImgPoolBwd ib;
@@ -520,6 +534,10 @@ int net_backward(Net* net, Plan* p, bool normalize) {
                                       d.out_h, d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, b.gz,
                                       net->grads + d.w_off, p->red_ws, p->red_ws_floats, s));
         }
+    }
+    if (forked) {
+        AMS_CUDA_CHECK(cudaEventRecord(net->ev_join, net->side_stream));
+        AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_join, 0));
     }
     return 0;
 }

@@ -60,6 +60,7 @@ struct Plan {
     float *pooled = nullptr, *ip_z = nullptr, *ip_act = nullptr, *bias_img = nullptr, *ip_dbias = nullptr, *dfeat_rowbias = nullptr;
     double* bn_ws = nullptr; double* small_ws = nullptr;
     float* red_ws = nullptr; size_t red_ws_floats = 0;
+    float* wgrad_ws = nullptr; size_t wgrad_ws_floats = 0;       // split-K partials of the side-stream filter gradients
     std::vector<GemmPlan> fwd_frozen, fwd_train, dgrad;
     std::vector<WgradPlan> wgrad;
     std::vector<char> has_fwd, has_dgrad, has_wgrad;
@@ -101,6 +102,8 @@ struct Net {
     ams_config cfg{};
     int num_sms = kNumSMs;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    // filter gradients of the 1x1 convs run on a side stream, concurrently with the backward chain that does not need them
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::vector<VarInfo> vars;
     std::unordered_map<std::string, int> var_index;
     std::vector<int> trainable_order;       // indices into vars, tf.trainable_variables() order

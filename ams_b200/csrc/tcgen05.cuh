@@ -39,6 +39,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// for the single-thread producer / MMA-issuer warps: back off between polls so that the spin does not take issue
+// slots from the epilogue warps that share the SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { __nanosleep(40); }
+}
 
 // ---- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
