@@ -626,6 +626,14 @@ extern "C" int ams_debug_dw_tile(int N, int H, int W, int C, int Ho, int Wo, int
     return 0;
 }
 
+extern "C" int ams_debug_dw_bwd_tile(int N, int H, int W, int C, int Ho, int Wo, int stride, int dil, int* out8) {
+    Conv2dGeom g{N, H, W, C, Ho, Wo, stride, dil, dil, dil};
+    const DwBwdTile t = pick_bwd_tile(g, kBwdSmemCap);
+    out8[0] = t.th; out8[1] = t.twt; out8[2] = t.ntx; out8[3] = t.nty; out8[4] = t.cb; out8[5] = static_cast<int>(t.smem);
+    out8[6] = static_cast<int>(t.blocks); out8[7] = t.nstrips;
+    return 0;
+}
+
 bool dw_tiled_supported(const Conv2dGeom& g) {
     return pick_cb(g.C) != 0 && ((g.stride == 1 && (g.dil == 1 || g.dil == 2)) || (g.stride == 2 && g.dil == 1));
 }
