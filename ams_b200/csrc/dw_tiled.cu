@@ -56,6 +56,7 @@ struct DwFwdParams {
     const float* out_scale; const float* out_shift; int out_act;   // != null: folded BN + act applied to the result
     double* stats;                                                  // != null: [tile][2][C] column sums of the stored tile
     int th, twt, ntx, nty, chunks, nstrips, ih, iwp;
+    int mg_w, mg_s, st_y, st_x, cs_r, cs_s;       // host-computed: division magics (n*mg>>16 == n/d, n < 256) and loop steps
 };
 
 // Stage rows [0,ih) x cols [0,iwp) x CB channels of `img` (image-relative origin gy0,gx0; outside the image = 0) as bf16
@@ -63,7 +64,8 @@ struct DwFwdParams {
 template <int CB, int THREADS>
 __device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restrict__ img /* + channel chunk */, int C, int H,
                                            int W, int gy0, int gx0, int ih, int iwp, const float* __restrict__ scale,
-                                           const float* __restrict__ shift, int act, int c_chunk0) {
+                                           const float* __restrict__ shift, int act, int c_chunk0, int mg_w, int step_y,
+                                           int step_x) {
     constexpr int CV8 = CB / 8, PXT = THREADS / CV8, U = 4;
     const int c8 = threadIdx.x % CV8, lane_px = threadIdx.x / CV8;
     float sc[8], sh[8];
@@ -71,8 +73,7 @@ __device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restric
 #pragma unroll
         for (int q = 0; q < 8; ++q) { sc[q] = scale[c_chunk0 + c8 * 8 + q]; sh[q] = shift[c_chunk0 + c8 * 8 + q]; }
     }
-    int ly = lane_px / iwp, lx = lane_px - ly * iwp;
-    const int step_y = PXT / iwp, step_x = PXT - step_y * iwp;
+    int ly = (lane_px * mg_w) >> 16, lx = lane_px - ly * iwp;
     uint32_t sdst = sbase + (lane_px * CB + c8 * 8) * 2;
     const bf16* src = img + c8 * 8;
     // software pipeline: the loads of batch k+1 are in flight while batch k is transformed and stored
@@ -126,7 +127,8 @@ dw_fwd_tiled_kernel(const DwFwdParams p) {
     const int oy0 = ty * p.th, ox0 = tx * p.twt;
 
     stage_tile<CB, THREADS>(sbase, p.in + static_cast<long long>(n) * p.H * p.W * p.C + c_base, p.C, p.H, p.W,
-                            oy0 * S - p.pad_top, ox0 * S - p.pad_left, p.ih, p.iwp, p.in_scale, p.in_shift, p.in_act, c_base);
+                            oy0 * S - p.pad_top, ox0 * S - p.pad_left, p.ih, p.iwp, p.in_scale, p.in_shift, p.in_act, c_base,
+                            p.mg_w, p.st_y, p.st_x);
     __syncthreads();
 
     // ---------------------------------------------------------------- compute: thread = 4 channels x strips of 4 pixels
@@ -146,8 +148,8 @@ dw_fwd_tiled_kernel(const DwFwdParams p) {
     float2 ssum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, ssq[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     constexpr int NCOLS = (kStrip - 1) * S + 2 * D + 1;
     const uint32_t row_bytes = static_cast<uint32_t>(p.iwp) * CB * 2;
-    int r = pt / p.nstrips, s = pt - r * p.nstrips;
-    const int step_r = NPT / p.nstrips, step_s = NPT - step_r * p.nstrips;
+    int r = (pt * p.mg_s) >> 16, s = pt - r * p.nstrips;
+    const int step_r = p.cs_r, step_s = p.cs_s;
     for (; r < p.th; r += step_r, s += step_s) {
         if (s >= p.nstrips) { s -= p.nstrips; ++r; if (r >= p.th) break; }
         float2 acc[kStrip][2];
@@ -307,6 +309,7 @@ struct DwBwdParams {
     double* bn_partial;                           // [tile][2][C]  (null if in_scale == null)
     int N, H, W, C, Ho, Wo, pad_top, pad_left;
     int th, twt, ntx, nty, chunks, nstrips, oh, owp;
+    int mg_w, mg_s, st_y, st_x, cs_r, cs_s;
 };
 
 template <int S, int D, int PADX>
@@ -345,19 +348,21 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
     {
         const int c8 = threadIdx.x % CV8, lane_px = threadIdx.x / CV8;
         const int c0 = c_base + c8 * 8;
-        float sc[8], sh[8], ca[8], cb[8], cc[8];
+        float2 sc2[4], sh2[4], ca2[4], cb2[4], cc2[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            sc[q] = p.scale[c0 + q]; sh[q] = p.shift[c0 + q];
-            ca[q] = p.coef[c0 + q]; cb[q] = p.coef[p.C + c0 + q]; cc[q] = p.coef[2 * p.C + c0 + q];
+        for (int h = 0; h < 4; ++h) {
+            sc2[h] = *reinterpret_cast<const float2*>(p.scale + c0 + 2 * h); sh2[h] = *reinterpret_cast<const float2*>(p.shift + c0 + 2 * h);
+            ca2[h] = *reinterpret_cast<const float2*>(p.coef + c0 + 2 * h);
+            cb2[h] = *reinterpret_cast<const float2*>(p.coef + p.C + c0 + 2 * h);
+            cc2[h] = *reinterpret_cast<const float2*>(p.coef + 2 * p.C + c0 + 2 * h);
         }
         for (int i = threadIdx.x; i < 9 * CB; i += THREADS) {
             const int k = i / CB, c = i - k * CB;
             reinterpret_cast<float*>(smem)[i] = p.w[k * p.C + c_base + c];
         }
         constexpr int U = 2;
-        int ly = lane_px / p.owp, lx = lane_px - ly * p.owp;
-        const int step_y = PXT / p.owp, step_x = PXT - step_y * p.owp;
+        int ly = (lane_px * p.mg_w) >> 16, lx = lane_px - ly * p.owp;
+        const int step_y = p.st_y, step_x = p.st_x;
         uint32_t sdst = tile_smem + (lane_px * CB + c8 * 8) * 2;
         const long long img = static_cast<long long>(n) * p.Ho * p.Wo * p.C + c0;
         uint4 vg[U], vz[U], ng[U], nz[U];
@@ -386,16 +391,25 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
                 if (st[u]) {
                     uint4 o = make_uint4(0u, 0u, 0u, 0u);
                     if (st[u] == 2) {
-                        float g[8], z[8];
-                        unpack8(vg[u], g);
-                        unpack8(vz[u], z);
+                        const uint32_t gw[4] = {vg[u].x, vg[u].y, vg[u].z, vg[u].w};
+                        const uint32_t zw[4] = {vz[u].x, vz[u].y, vz[u].z, vz[u].w};
+                        float g[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float yh = fmaf(z[q], sc[q], sh[q]);
-                            float gm = g[q];
-                            if (p.act == 1) gm = yh > 0.f ? gm : 0.f;
-                            else if (p.act == 2) gm = (yh > 0.f && yh < 6.f) ? gm : 0.f;
-                            g[q] = fmaf(ca[q], gm, fmaf(cb[q], z[q], cc[q]));
+                        for (int h = 0; h < 4; ++h) {
+                            // two channels at a time: packed fp32x2 FMAs, scalar compare/select for the activation mask
+                            const float2 z2 = unpack2(zw[h]);
+                            float2 gm = unpack2(gw[h]);
+                            float2 yh = sh2[h];
+                            ffma2(yh, z2, sc2[h]);
+                            if (p.act == 1) { gm.x = yh.x > 0.f ? gm.x : 0.f; gm.y = yh.y > 0.f ? gm.y : 0.f; }
+                            else if (p.act == 2) {
+                                gm.x = (yh.x > 0.f && yh.x < 6.f) ? gm.x : 0.f;
+                                gm.y = (yh.y > 0.f && yh.y < 6.f) ? gm.y : 0.f;
+                            }
+                            float2 t2 = cc2[h];
+                            ffma2(t2, cb2[h], z2);
+                            ffma2(t2, ca2[h], gm);
+                            g[2 * h] = t2.x; g[2 * h + 1] = t2.y;
                         }
                         o = pack8(g);
                     }
@@ -421,8 +435,8 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
     float2 s1[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, s2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
     const uint32_t row_bytes = static_cast<uint32_t>(p.owp) * CB * 2;
     const uint32_t w_mine = w_smem + l4 * kCh * 4;
-    int r = pt / p.nstrips, s = pt - r * p.nstrips;
-    const int step_r = NPT / p.nstrips, step_s = NPT - step_r * p.nstrips;
+    int r = (pt * p.mg_s) >> 16, s = pt - r * p.nstrips;
+    const int step_r = p.cs_r, step_s = p.cs_s;
     for (; r < p.th; r += step_r, s += step_s) {
         if (s >= p.nstrips) { s -= p.nstrips; ++r; if (r >= p.th) break; }
         const int iy = iy0 + r;
@@ -657,6 +671,12 @@ int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const
     p.stats = stats;
     p.th = t.th; p.twt = t.twt; p.ntx = t.ntx; p.nty = t.nty; p.chunks = t.chunks; p.nstrips = t.nstrips;
     p.ih = t.ih; p.iwp = t.iwp;
+    {
+        const int pxt = dw_threads(t.cb) / (t.cb / 8), npt = dw_threads(t.cb) / (t.cb / kCh);
+        p.mg_w = 65536 / t.iwp + 1; p.mg_s = 65536 / t.nstrips + 1;
+        p.st_y = pxt / t.iwp; p.st_x = pxt - p.st_y * t.iwp;
+        p.cs_r = npt / t.nstrips; p.cs_s = npt - p.cs_r * t.nstrips;
+    }
     if (stats_rows) *stats_rows = static_cast<int>(static_cast<long long>(g.N) * t.nty * t.ntx);
     if (g.stride == 1 && g.dil == 1) return launch_fwd_cb<1, 1>(p, t, s);
     if (g.stride == 2 && g.dil == 1) return launch_fwd_cb<2, 1>(p, t, s);
@@ -681,6 +701,12 @@ int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, c
     p.gout = a.gout; p.dw_partial = a.dw_partial; p.bn_partial = a.in_scale ? a.bn_partial : nullptr;
     p.N = g.N; p.H = g.H; p.W = g.W; p.C = g.C; p.Ho = g.Ho; p.Wo = g.Wo; p.pad_top = g.pad_top; p.pad_left = g.pad_left;
     p.th = t.th; p.twt = t.twt; p.ntx = t.ntx; p.nty = t.nty; p.chunks = t.chunks; p.nstrips = t.nstrips; p.oh = t.oh; p.owp = t.owp;
+    {
+        const int pxt = dw_threads(t.cb) / (t.cb / 8), npt = dw_threads(t.cb) / (t.cb / kCh);
+        p.mg_w = 65536 / t.owp + 1; p.mg_s = 65536 / t.nstrips + 1;
+        p.st_y = pxt / t.owp; p.st_x = pxt - p.st_y * t.owp;
+        p.cs_r = npt / t.nstrips; p.cs_s = npt - p.cs_r * t.nstrips;
+    }
     int rc;
     if (g.stride == 1 && g.dil == 1) rc = launch_bwd_cb<1, 1, 0>(p, t, s);
     else if (g.stride == 1) rc = launch_bwd_cb<1, 2, 0>(p, t, s);
