@@ -11,6 +11,8 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace ams
 
 using namespace ams;
@@ -156,7 +158,10 @@ void ams_destroy(ams_net* h) {
     Net* net = reinterpret_cast<Net*>(h);
     cudaSetDevice(net->cfg.device);
     cudaDeviceSynchronize();
-    for (auto& kv : net->plans) for (void* p : kv.second->allocations) cudaFree(p);
+    for (auto& kv : net->plans) {
+        for (cudaGraphExec_t g : kv.second->train_graph) if (g) cudaGraphExecDestroy(g);
+        for (void* p : kv.second->allocations) cudaFree(p);
+    }
     for (auto& q : net->slots) { if (q.frames) cudaFree(q.frames); if (q.labels) cudaFree(q.labels); if (q.consumed) cudaEventDestroy(q.consumed); }
     void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->before, net->delta_scratch, net->mask, net->moving,
                     net->bnpool, net->wpool, net->select_sc, net->head_st, net->cast_table, net->segs_dev, net->pack_bits,
@@ -376,8 +381,7 @@ int ams_train_forward_backward(ams_net* h, long long* out_n_valid, double* out_l
     NET(h);
     Plan* p = nullptr;
     if (net_dequeue(net, &p, true)) return -1;
-    if (net_forward(net, p, AMS_BN_BATCH, true)) return -1;
-    if (net_backward(net, p, false)) return -1;
+    if (net_train_fwd_bwd(net, p, false)) return -1;
     HeadStats hs;
     AMS_CUDA_CHECK(cudaMemcpyAsync(&hs, net->head_st, sizeof(HeadStats), cudaMemcpyDeviceToHost, net->stream));
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
@@ -400,8 +404,7 @@ int ams_train_step(ams_net* h, float lr, int masked, float* out_loss) {
     NET(h);
     Plan* p = nullptr;
     if (net_dequeue(net, &p, true)) return -1;
-    if (net_forward(net, p, AMS_BN_BATCH, true)) return -1;
-    if (net_backward(net, p, true)) return -1;
+    if (net_train_fwd_bwd(net, p, true)) return -1;
     if (apply_optimizer(net, lr, masked, 1.0f)) return -1;
     if (out_loss) {
         AMS_CUDA_CHECK(cudaMemcpyAsync(out_loss, p->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, net->stream));

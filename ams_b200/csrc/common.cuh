@@ -30,6 +30,8 @@ void set_last_error(const std::string& msg);
         }                                                                                        \
     } while (0)
 void count_launch();
+void count_launches(long long n);     // kernels inside a replayed CUDA graph
+long long launches_so_far();
 #define AMS_LAUNCH_CHECK()                      \
     do {                                        \
         ams::count_launch();                    \

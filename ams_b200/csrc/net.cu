@@ -542,6 +542,50 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- graph replay
+int net_train_fwd_bwd(Net* net, Plan* p, bool normalize) {
+    static const bool no_graph = [] { const char* e = getenv("AMS_NO_GRAPH"); return e && e[0] == '1'; }();
+    const int k = normalize ? 1 : 0;
+    auto eager = [&]() -> int {
+        if (net_forward(net, p, AMS_BN_BATCH, true)) return -1;
+        return net_backward(net, p, normalize);
+    };
+    if (no_graph || net->prof.enabled || p->train_runs < 0) return eager();
+    if (p->train_graph[k] && p->train_graph_dtype[k] == p->in_dtype) {
+        AMS_CUDA_CHECK(cudaGraphLaunch(p->train_graph[k], net->stream));
+        count_launches(p->train_graph_kernels[k]);
+        net->weights_dirty = false;              // the captured sequence starts with the bf16 weight refresh
+        p->last_was_train = true;
+        return 0;
+    }
+    if (p->train_runs == 0) { p->train_runs = 1; return eager(); }      // first step on this plan: sets kernel attributes
+    if (p->train_graph[k]) { cudaGraphExecDestroy(p->train_graph[k]); p->train_graph[k] = nullptr; }
+    net->weights_dirty = true;
+    cudaGraph_t graph = nullptr;
+    const long long launches0 = launches_so_far();
+    AMS_CUDA_CHECK(cudaStreamBeginCapture(net->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = eager();
+    const cudaError_t ec = cudaStreamEndCapture(net->stream, &graph);
+    if (rc || ec != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        p->train_runs = -1;                      // this plan stays eager
+        net->weights_dirty = true;
+        return eager();
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess || !exec) { cudaGetLastError(); p->train_runs = -1; net->weights_dirty = true; return eager(); }
+    p->train_graph[k] = exec;
+    p->train_graph_dtype[k] = p->in_dtype;
+    p->train_graph_kernels[k] = launches_so_far() - launches0;       // counted while capturing: replays add the same number
+    AMS_CUDA_CHECK(cudaGraphLaunch(exec, net->stream));
+    net->weights_dirty = false;
+    p->last_was_train = true;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- queue
 int net_dequeue(Net* net, Plan** plan_out, bool need_backward) {
     int slot = -1;

@@ -68,7 +68,10 @@ struct Plan {
     // producer's RAW output; lazy_y[j] = layer j's normalised output is never materialised in training mode
     std::vector<char> dw_fused, lazy_y;
     float* coef[2] = {nullptr, nullptr};       // BN-backward coefficients [3][Cmax]: [0] depthwise layer, [1] its producer
-    int pending_bn_rows = 0;                   // > 0: bn_ws holds the fused kernel's column sums for the next layer
+    int pending_bn_rows = 0;
+    // whole forward+backward captured once per (loss normalisation, frame dtype) and replayed (net_train_fwd_bwd)
+    cudaGraphExec_t train_graph[2] = {nullptr, nullptr}; int train_graph_dtype[2] = {-1, -1}; int train_runs = 0;
+    long long train_graph_kernels[2] = {0, 0};                   // > 0: bn_ws holds the fused kernel's column sums for the next layer
     bool have_backward = false;
     bool last_was_train = false;
 };
@@ -135,6 +138,9 @@ Plan* net_get_plan(Net* net, int N, bool need_backward);
 int net_prepare_weights(Net* net, bool frozen);
 int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving);
 int net_backward(Net* net, Plan* p, bool normalize);
+// forward (batch statistics, moving-average update) + backward of one distillation step: eager the first time on a plan,
+// then a CUDA graph replay (~450 launches, two streams) unless profiling or AMS_NO_GRAPH=1
+int net_train_fwd_bwd(Net* net, Plan* p, bool normalize);
 int net_dequeue(Net* net, Plan** plan_out, bool need_backward);
 
 }  // namespace ams
