@@ -89,8 +89,19 @@ __device__ __forceinline__ bool finalize_sums(const double* __restrict__ partial
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     double s = 0.0, q = 0.0;
     if (c < C) {
-#pragma unroll 4
-        for (int k = rl; k < chunks; k += kFinRows) {
+        // 16 independent row loads in flight per thread and pass (the rows are a latency chain otherwise)
+        int k = rl;
+        for (; k + 7 * kFinRows < chunks; k += 8 * kFinRows) {
+            double a[8], b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a[u] = partial[static_cast<long long>(k + u * kFinRows) * 2 * C + c];
+                b[u] = partial[static_cast<long long>(k + u * kFinRows) * 2 * C + C + c];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s += a[u]; q += b[u]; }
+        }
+        for (; k < chunks; k += kFinRows) {
             s += partial[static_cast<long long>(k) * 2 * C + c];
             q += partial[static_cast<long long>(k) * 2 * C + C + c];
         }
