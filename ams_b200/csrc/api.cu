@@ -160,6 +160,7 @@ void ams_destroy(ams_net* h) {
     cudaDeviceSynchronize();
     for (auto& kv : net->plans) {
         for (cudaGraphExec_t g : kv.second->train_graph) if (g) cudaGraphExecDestroy(g);
+        for (cudaGraphExec_t g : kv.second->infer_graph) if (g) cudaGraphExecDestroy(g);
         for (void* p : kv.second->allocations) cudaFree(p);
     }
     for (auto& q : net->slots) { if (q.frames) cudaFree(q.frames); if (q.labels) cudaFree(q.labels); if (q.consumed) cudaEventDestroy(q.consumed); }
@@ -309,17 +310,53 @@ int ams_queue_size(ams_net* h) {
 static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels, int64_t* out_cm, float* out_loss) {
     Plan* p = nullptr;
     if (net_dequeue(net, &p, false)) return -1;
-    if (net_forward(net, p, bn_mode, false)) return -1;
     HeadGeom hg = net->head; hg.N = p->N;
     HeadStats hs;
-    if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
-    {
+    auto body = [&]() -> int {
+        if (net_forward(net, p, bn_mode, false)) return -1;
+        if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
         cudaStream_t s = net->stream;
         const double px_ = static_cast<double>(p->N) * net->cfg.height * net->cfg.width;
         net->prof.begin(s, "head_infer", px_ * (metric ? 5.0 : 4.0) + 4.0 * p->N * hg.h * hg.w * 32);
         const int rc = head_infer(p->logits, hg, metric ? p->in_labels : nullptr, p->pred, net->head_st, s);
         net->prof.end(s);
-        if (rc) return -1;
+        return rc ? -1 : 0;
+    };
+    // frozen client inference: the ~60 launches of forward + head are captured once per plan and replayed
+    static const bool no_graph = [] { const char* e = getenv("AMS_NO_GRAPH"); return e && e[0] == '1'; }();
+    const int k = metric ? 1 : 0;
+    if (bn_mode != AMS_BN_MOVING || no_graph || net->prof.enabled || p->infer_runs < 0) {
+        if (body()) return -1;
+    } else {
+        if (net_prepare_weights(net, true)) return -1;           // conditional work stays outside the graph
+        if (p->infer_graph[k] && p->infer_graph_dtype[k] == p->in_dtype) {
+            AMS_CUDA_CHECK(cudaGraphLaunch(p->infer_graph[k], net->stream));
+            count_launches(p->infer_graph_kernels[k]);
+            p->last_was_train = false;
+        } else if (p->infer_runs == 0) {
+            p->infer_runs = 1;
+            if (body()) return -1;
+        } else {
+            if (p->infer_graph[k]) { cudaGraphExecDestroy(p->infer_graph[k]); p->infer_graph[k] = nullptr; }
+            const long long launches0 = launches_so_far();
+            cudaGraph_t graph = nullptr;
+            AMS_CUDA_CHECK(cudaStreamBeginCapture(net->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = body();
+            const cudaError_t ec = cudaStreamEndCapture(net->stream, &graph);
+            cudaGraphExec_t exec = nullptr;
+            if (rc || ec != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess || !exec) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                p->infer_runs = -1;                               // this plan stays eager
+                if (body()) return -1;
+            } else {
+                cudaGraphDestroy(graph);
+                p->infer_graph[k] = exec;
+                p->infer_graph_dtype[k] = p->in_dtype;
+                p->infer_graph_kernels[k] = launches_so_far() - launches0;
+                AMS_CUDA_CHECK(cudaGraphLaunch(exec, net->stream));
+            }
+        }
     }
     const size_t px = static_cast<size_t>(p->N) * net->cfg.height * net->cfg.width;
     if (out_labels) AMS_CUDA_CHECK(cudaMemcpyAsync(out_labels, p->pred, px * sizeof(int32_t), cudaMemcpyDeviceToHost, net->stream));

@@ -71,7 +71,10 @@ struct Plan {
     int pending_bn_rows = 0;
     // whole forward+backward captured once per (loss normalisation, frame dtype) and replayed (net_train_fwd_bwd)
     cudaGraphExec_t train_graph[2] = {nullptr, nullptr}; int train_graph_dtype[2] = {-1, -1}; int train_runs = 0;
-    long long train_graph_kernels[2] = {0, 0};                   // > 0: bn_ws holds the fused kernel's column sums for the next layer
+    long long train_graph_kernels[2] = {0, 0};
+    // frozen inference (forward + head), keyed by [with metric]
+    cudaGraphExec_t infer_graph[2] = {nullptr, nullptr}; int infer_graph_dtype[2] = {-1, -1}; int infer_runs = 0;
+    long long infer_graph_kernels[2] = {0, 0};                   // > 0: bn_ws holds the fused kernel's column sums for the next layer
     bool have_backward = false;
     bool last_was_train = false;
 };

@@ -148,13 +148,19 @@ class Student:
         return self._L.ams_queue_size(self._h)
 
     # ------------------------------------------------------------------ inference
+    def _label_buffer(self, n):
+        """Fresh int32 [n,H,W] array in page-locked host memory (torch's caching host allocator recycles the blocks):
+        the 2 MB/frame label map then leaves the device at PCIe speed instead of through a pageable staging copy."""
+        import torch
+        return torch.empty((n, self.height, self.width), dtype=torch.int32, pin_memory=True).numpy()
+
     def infer(self, n, bn_mode):
-        out = np.empty((n, self.height, self.width), dtype=np.int32)
+        out = self._label_buffer(n)
         nat.check(self._L.ams_infer(self._h, bn_mode, _ptr(out)), 'infer')
         return out
 
     def infer_metric(self, n, bn_mode):
-        out = np.empty((n, self.height, self.width), dtype=np.int32)
+        out = self._label_buffer(n)
         cm = np.zeros((self.class_count, self.class_count), dtype=np.int64)
         loss = C.c_float()
         nat.check(self._L.ams_infer_metric(self._h, bn_mode, _ptr(out), _ptr(cm), C.byref(loss)), 'infer_metric')
