@@ -12,6 +12,7 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() { static const bool on = [] { const char* e = getenv("AMS_NO_PDL"); return !(e && e[0] == '1'); }(); return on; }
 long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 }  // namespace ams
 

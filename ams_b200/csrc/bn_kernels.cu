@@ -24,6 +24,7 @@ int red_chunks(long long M, int C) {
 // partial[chunk][0][c] = sum z, partial[chunk][1][c] = sum z^2 over the rows of the chunk
 __global__ void __launch_bounds__(kRedThreads)
 bn_stats_kernel(const bf16* __restrict__ z, long long M, int C, long long rows_per_chunk, double* __restrict__ partial) {
+    pdl_entry();
     extern __shared__ double s_acc[];                     // [rows_in_block][2][C]
     const int c8n = C >> 3;
     const int tpr = min(c8n, kRedThreads);                // threads per row
@@ -116,6 +117,7 @@ __device__ __forceinline__ bool finalize_sums(const double* __restrict__ partial
 
 __global__ void __launch_bounds__(32 * kFinRows)
 bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, int update_moving) {
+    pdl_entry();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, q;
     if (!finalize_sums(partial, chunks, L.C, c, &s, &q)) return;
@@ -142,6 +144,7 @@ bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, in
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                 const bf16* __restrict__ residual, bf16* __restrict__ y, long long total8, int C) {
+    pdl_entry();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total8) return;
     const int c0 = static_cast<int>(i % (C >> 3)) * 8;
@@ -164,6 +167,7 @@ bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, con
 
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mm, const float* mv, float eps,
                                float* scale, float* shift, int C) {
+    pdl_entry();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float sc = gamma[c] * rsqrtf(mv[c] + eps);
@@ -182,6 +186,7 @@ __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
                      const float* __restrict__ scale, const float* __restrict__ shift, int act, long long M, int C,
                      long long rows_per_chunk, double* __restrict__ partial) {
+    pdl_entry();
     extern __shared__ double s_acc[];
     const int c8n = C >> 3;
     const int tpr = min(c8n, kRedThreads);
@@ -257,6 +262,7 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
 // coef[0][c]=A, [1][c]=B, [2][c]=Cc with dz = A*g + B*z + Cc ; also d_gamma, d_beta
 __global__ void __launch_bounds__(32 * kFinRows)
 bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, float* d_gamma, float* d_beta, float* coef) {
+    pdl_entry();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s1, sz;
     if (!finalize_sums(partial, chunks, L.C, c, &s1, &sz)) return;
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
                     int act, long long total8, int C, bf16* dz_out) {
+    pdl_entry();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= total8) return;
     const int c8n = C >> 3;
@@ -312,6 +319,7 @@ constexpr int kColsumSplits = 32;
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb, int ld, long long rpg, int C,
                       double* __restrict__ partial) {
+    pdl_entry();
     __shared__ double s_red[4][64];
     const int g = blockIdx.x, split = blockIdx.z;
     const int c = blockIdx.y * 64 + (threadIdx.x & 63);
@@ -336,6 +344,7 @@ colsum_partial_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb,
             s_red[0][threadIdx.x] + s_red[1][threadIdx.x] + s_red[2][threadIdx.x] + s_red[3][threadIdx.x];
 }
 __global__ void colsum_final_kernel(const double* __restrict__ partial, int groups, int C, float scale, float* __restrict__ out) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= groups * C) return;
     const int g = i / C, c = i % C;
@@ -349,6 +358,7 @@ __global__ void colsum_final_kernel(const double* __restrict__ partial, int grou
 // out[n][co] = sum_c in[n][c] * w[c][co]      (thread per output, coalesced over co)
 __global__ void __launch_bounds__(256)
 small_fc_kernel(const float* __restrict__ in, const float* __restrict__ w, int N, int Cin, int Cout, float* __restrict__ out) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N * Cout) return;
     const int n = i / Cout, co = i % Cout;
@@ -362,6 +372,7 @@ small_fc_kernel(const float* __restrict__ in, const float* __restrict__ w, int N
 __global__ void __launch_bounds__(256)
 small_fc_t_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ gate, int N, int C,
                   int Cout, float scale, float* __restrict__ out) {
+    pdl_entry();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= N * C) return;
     const int n = warp / C, c = warp % C;
@@ -373,6 +384,7 @@ small_fc_t_kernel(const float* __restrict__ g, const float* __restrict__ w, cons
 // out[c][co] = sum_n a[n][c] * b[n][co]
 __global__ void __launch_bounds__(256)
 small_outer_kernel(const float* __restrict__ a, const float* __restrict__ b, int N, int C, int Cout, float* __restrict__ out) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C * Cout) return;
     const int c = i / Cout, co = i % Cout;
@@ -383,6 +395,7 @@ small_outer_kernel(const float* __restrict__ a, const float* __restrict__ b, int
 // BN over the batch dimension + ReLU (training statistics or frozen)
 __global__ void __launch_bounds__(256)
 imgpool_bn_kernel(ImgPoolFwd a) {
+    pdl_entry();
     const int co = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = a.N, Cm = a.Cmid;
     if (co >= Cm) return;
@@ -416,6 +429,7 @@ imgpool_bn_kernel(ImgPoolFwd a) {
 // BN backward over the batch dimension: dact -> dz in place, d_gamma, d_beta
 __global__ void __launch_bounds__(256)
 imgpool_bn_bwd_kernel(ImgPoolFwd a, float* __restrict__ dact, float* __restrict__ d_gamma, float* __restrict__ d_beta) {
+    pdl_entry();
     const int co = blockIdx.x * blockDim.x + threadIdx.x;
     const int N = a.N, Cm = a.Cmid;
     if (co >= Cm) return;
@@ -454,31 +468,26 @@ int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double*
     const long long rpc = ceil_div_ll(L.M, chunks);
     const size_t smem = red_smem(L.C);
     AMS_REQUIRE(smem <= 48 * 1024, "BN reduction shared memory");
-    bn_stats_kernel<<<chunks, kRedThreads, smem, s>>>(z, L.M, L.C, rpc, ws);
-    AMS_LAUNCH_CHECK();
-    bn_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(ws, chunks, L, update_moving);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_stats_kernel), chunks, kRedThreads, smem, s, z, L.M, L.C, rpc, ws);
+    AMS_LAUNCH((bn_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, update_moving);
     return 0;
 }
 
 int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, int update_moving, cudaStream_t s) {
-    bn_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(partial, chunks, L, update_moving);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, partial, chunks, L, update_moving);
     return 0;
 }
 
 int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y, long long M,
              int C, cudaStream_t s) {
     const long long total8 = M * C / 8;
-    bn_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s>>>(z, scale, shift, act, residual, y, total8, C);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_apply_kernel), static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s, z, scale, shift, act, residual, y, total8, C);
     return 0;
 }
 
 int bn_fold_frozen(const float* gamma, const float* beta, const float* mm, const float* mv, float eps, float* scale,
                    float* shift, int C, cudaStream_t s) {
-    bn_fold_kernel<<<ceil_div(C, 128), 128, 0, s>>>(gamma, beta, mm, mv, eps, scale, shift, C);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_fold_kernel), ceil_div(C, 128), 128, 0, s, gamma, beta, mm, mv, eps, scale, shift, C);
     return 0;
 }
 
@@ -488,13 +497,10 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     const long long rpc = ceil_div_ll(L.M, chunks);
     const size_t smem = red_smem(L.C);
     float* coef = reinterpret_cast<float*>(ws + static_cast<size_t>(chunks) * 2 * L.C);
-    bn_bwd_reduce_kernel<<<chunks, kRedThreads, smem, s>>>(dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
-    AMS_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_bwd_reduce_kernel), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, d_gamma, d_beta, coef);
     const long long total8 = L.M * L.C / 8;
-    bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s>>>(dy, dy2, z, L.scale, L.shift, coef, act, total8, L.C, dz_out);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, total8, L.C, dz_out);
     return 0;
 }
 
@@ -502,35 +508,28 @@ int bn_backward_reduce(const bf16* dy, const bf16* z, const BnLayer& L, int act,
                        double* ws, cudaStream_t s) {
     const int chunks = red_chunks(L.M, L.C);
     const long long rpc = ceil_div_ll(L.M, chunks);
-    bn_bwd_reduce_kernel<<<chunks, kRedThreads, red_smem(L.C), s>>>(dy, nullptr, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
-    AMS_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(ws, chunks, L, d_gamma, d_beta, coef);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_bwd_reduce_kernel), chunks, kRedThreads, red_smem(L.C), s, dy, nullptr, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, d_gamma, d_beta, coef);
     return 0;
 }
 
 int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer& L, float* coef, float* d_gamma,
                                   float* d_beta, cudaStream_t s) {
-    bn_bwd_finalize_kernel<<<ceil_div(L.C, 32), 32 * kFinRows, 0, s>>>(partial, rows, L, d_gamma, d_beta, coef);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, partial, rows, L, d_gamma, d_beta, coef);
     return 0;
 }
 
 int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s) {
     const long long total8 = L.M * L.C / 8;
-    bn_bwd_apply_kernel<<<static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s>>>(dy_masked, nullptr, z, L.scale, L.shift, coef, 0,
-                                                                                   total8, L.C, dz_out);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s, dy_masked, nullptr, z, L.scale, L.shift, coef, 0, total8, L.C, dz_out);
     return 0;
 }
 
 int colsum_groups(const float* xf, const bf16* xb, int ld, long long rows_per_group, int groups, int C, float scale,
                   float* out, double* workspace, cudaStream_t s) {
     dim3 grid(groups, ceil_div(C, 64), kColsumSplits);
-    colsum_partial_kernel<<<grid, 256, 0, s>>>(xf, xb, ld, rows_per_group, C, workspace);
-    AMS_LAUNCH_CHECK();
-    colsum_final_kernel<<<ceil_div(groups * C, 128), 128, 0, s>>>(workspace, groups, C, scale, out);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((colsum_partial_kernel), grid, 256, 0, s, xf, xb, ld, rows_per_group, C, workspace);
+    AMS_LAUNCH((colsum_final_kernel), ceil_div(groups * C, 128), 128, 0, s, workspace, groups, C, scale, out);
     return 0;
 }
 size_t colsum_workspace_doubles(int groups, int C) { return static_cast<size_t>(groups) * kColsumSplits * C; }
@@ -538,12 +537,9 @@ size_t colsum_workspace_doubles(int groups, int C) { return static_cast<size_t>(
 int imgpool_forward(const ImgPoolFwd& a, cudaStream_t s) {
     // pooled[n][c] = mean over HW of feat
     if (colsum_groups(nullptr, a.feat, a.Cin, a.HW, a.N, a.Cin, 1.f / static_cast<float>(a.HW), a.pooled, a.ws, s)) return -1;
-    small_fc_kernel<<<ceil_div(a.N * a.Cmid, 256), 256, 0, s>>>(a.pooled, a.w_pool, a.N, a.Cin, a.Cmid, a.z);
-    AMS_LAUNCH_CHECK();
-    imgpool_bn_kernel<<<ceil_div(a.Cmid, 256), 256, 0, s>>>(a);
-    AMS_LAUNCH_CHECK();
-    small_fc_kernel<<<ceil_div(a.N * a.Cout, 256), 256, 0, s>>>(a.act, a.w_proj_top, a.N, a.Cmid, a.Cout, a.bias_img);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((small_fc_kernel), ceil_div(a.N * a.Cmid, 256), 256, 0, s, a.pooled, a.w_pool, a.N, a.Cin, a.Cmid, a.z);
+    AMS_LAUNCH((imgpool_bn_kernel), ceil_div(a.Cmid, 256), 256, 0, s, a);
+    AMS_LAUNCH((small_fc_kernel), ceil_div(a.N * a.Cout, 256), 256, 0, s, a.act, a.w_proj_top, a.N, a.Cmid, a.Cout, a.bias_img);
     return 0;
 }
 
@@ -552,17 +548,11 @@ int imgpool_backward(const ImgPoolBwd& b, cudaStream_t s) {
     float* dact = b.dbias + static_cast<size_t>(a.N) * a.Cout;       // caller allocates N*(Cout+Cmid) floats
     if (colsum_groups(nullptr, b.dz_proj, a.Cout, a.HW, a.N, a.Cout, 1.f, b.dbias, a.ws, s)) return -1;
     // d act = relu'(act) * dbias * w_proj_top^T ;  d w_proj_top = act^T dbias
-    small_fc_t_kernel<<<ceil_div(a.N * a.Cmid * 32, 256), 256, 0, s>>>(b.dbias, a.w_proj_top, a.act, a.N, a.Cmid, a.Cout, 1.f, dact);
-    AMS_LAUNCH_CHECK();
-    small_outer_kernel<<<ceil_div(a.Cmid * a.Cout, 256), 256, 0, s>>>(a.act, b.dbias, a.N, a.Cmid, a.Cout, b.d_w_proj_top);
-    AMS_LAUNCH_CHECK();
-    imgpool_bn_bwd_kernel<<<ceil_div(a.Cmid, 256), 256, 0, s>>>(a, dact, b.d_gamma, b.d_beta);
-    AMS_LAUNCH_CHECK();
-    small_outer_kernel<<<ceil_div(a.Cin * a.Cmid, 256), 256, 0, s>>>(a.pooled, dact, a.N, a.Cin, a.Cmid, b.d_w_pool);
-    AMS_LAUNCH_CHECK();
-    small_fc_t_kernel<<<ceil_div(a.N * a.Cin * 32, 256), 256, 0, s>>>(dact, a.w_pool, nullptr, a.N, a.Cin, a.Cmid,
-                                                                      1.f / static_cast<float>(a.HW), b.dfeat_rowbias);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((small_fc_t_kernel), ceil_div(a.N * a.Cmid * 32, 256), 256, 0, s, b.dbias, a.w_proj_top, a.act, a.N, a.Cmid, a.Cout, 1.f, dact);
+    AMS_LAUNCH((small_outer_kernel), ceil_div(a.Cmid * a.Cout, 256), 256, 0, s, a.act, b.dbias, a.N, a.Cmid, a.Cout, b.d_w_proj_top);
+    AMS_LAUNCH((imgpool_bn_bwd_kernel), ceil_div(a.Cmid, 256), 256, 0, s, a, dact, b.d_gamma, b.d_beta);
+    AMS_LAUNCH((small_outer_kernel), ceil_div(a.Cin * a.Cmid, 256), 256, 0, s, a.pooled, dact, a.N, a.Cin, a.Cmid, b.d_w_pool);
+    AMS_LAUNCH((small_fc_t_kernel), ceil_div(a.N * a.Cin * 32, 256), 256, 0, s, dact, a.w_pool, nullptr, a.N, a.Cin, a.Cmid, 1.f / static_cast<float>(a.HW), b.dfeat_rowbias);
     return 0;
 }
 

@@ -38,6 +38,35 @@ long long launches_so_far();
         AMS_CUDA_CHECK(cudaGetLastError());     \
     } while (0)
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the step starts with pdl_entry(): it lets the NEXT kernel of the stream be scheduled as soon as all
+// CTAs of this one are resident (its CTAs then park in griddepcontrol.wait), and waits for the PREVIOUS kernel to
+// complete and flush before touching global memory.  Launch latency and prologues overlap the predecessor's tail.
+// Kernels that allocate tensor memory trigger only after their tcgen05.alloc (a parked dependent holding TMEM
+// columns must never be what a not-yet-allocated CTA of the running kernel is waiting for).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// AMS_LAUNCH((kernel<T>), grid, block, smem, stream, args...): PDL launch + launch counter + error check
+#define AMS_STRIP_PARENS(...) __VA_ARGS__
+#define AMS_LAUNCH(kernel, grid, block, smem, stream, ...)                                                       \
+    do {                                                                                                         \
+        ams::count_launch();                                                                                     \
+        AMS_CUDA_CHECK(ams::launch_pdl(AMS_STRIP_PARENS kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)); \
+    } while (0)
+
 constexpr int kNumSMs = 148;   // B200; grids of the persistent kernels are sized from the runtime value
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

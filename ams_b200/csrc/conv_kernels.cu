@@ -37,6 +37,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ w, const float* __restrict__ scale,
                 const float* __restrict__ shift, bf16* __restrict__ out) {
+    pdl_entry();
     __shared__ float sw[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
@@ -74,46 +75,64 @@ stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ 
     stg256(o, pack8(acc), pack8(acc + 8));
 }
 
-// filter gradient: block stages P output pixels (27-tap patches + 32 dz values), thread (k, co4) owns 4 weights
-constexpr int kStemBwdPix = 128;
+// filter gradient: a block owns `rows_per_block` output rows; per segment of 64 output pixels it stages the three
+// normalised input rows the segment touches ONCE (coalesced, pad values resolved there) plus the 64 x 32 dz values,
+// then thread (tap k, 4 output channels) walks the pixels: one broadcast word + one 128-bit dz read per 4 FMAs.
+constexpr int kStemBwdPix = 64;
 constexpr int kStemBwdThreads = 27 * 8;
+constexpr int kStemRowFloats = (2 * kStemBwdPix + 1) * 3 + 1;       // 129 input pixels x 3 channels (+1: odd stride)
 template <typename T>
 __global__ void __launch_bounds__(kStemBwdThreads)
 stem_bwd_filter_kernel(const T* __restrict__ in, StemGeom g, const bf16* __restrict__ dz, float* __restrict__ partial,
-                       int pix_per_block) {
-    __shared__ float s_patch[kStemBwdPix][28];
+                       int rows_per_block) {
+    pdl_entry();
+    __shared__ float s_in[3][kStemRowFloats];
     __shared__ __align__(16) float s_dz[kStemBwdPix][32];
     const int k = threadIdx.x / 8, co4 = threadIdx.x % 8;
+    const int ky = k / 9, kxc = k % 9;                                  // kxc = kx*3 + c
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
-    const long long p_begin = static_cast<long long>(blockIdx.x) * pix_per_block;
-    const long long p_end = min(p_begin + pix_per_block, total);
-    for (long long p0 = p_begin; p0 < p_end; p0 += kStemBwdPix) {
-        const int np = static_cast<int>(min(static_cast<long long>(kStemBwdPix), p_end - p0));
-        __syncthreads();
-        for (int i = threadIdx.x; i < np * 9; i += blockDim.x) {
-            const int pp = i / 9, tap = i % 9;
-            const long long pix = p0 + pp;
-            const int ox = static_cast<int>(pix % g.Wo);
-            const int oy = static_cast<int>((pix / g.Wo) % g.Ho);
-            const int n = static_cast<int>(pix / (static_cast<long long>(g.Wo) * g.Ho));
-            float v[3];
-            stem_pixel<T>(in, g, n, oy * 2 - g.pad_top + tap / 3, ox * 2 - g.pad_left + tap % 3, v);
-            s_patch[pp][tap * 3 + 0] = v[0]; s_patch[pp][tap * 3 + 1] = v[1]; s_patch[pp][tap * 3 + 2] = v[2];
-        }
-        for (int i = threadIdx.x; i < np * 4; i += blockDim.x) {
-            const int pp = i / 4, c8 = i % 4;
-            float f[8];
-            unpack8(ldg_stream(dz + (p0 + pp) * 32 + c8 * 8), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s_dz[pp][c8 * 8 + j] = f[j];
-        }
-        __syncthreads();
-        for (int pp = 0; pp < np; ++pp) {
-            const float a = s_patch[pp][k];
-            const float4 d = *reinterpret_cast<const float4*>(&s_dz[pp][co4 * 4]);
-            acc[0] = fmaf(a, d.x, acc[0]); acc[1] = fmaf(a, d.y, acc[1]);
-            acc[2] = fmaf(a, d.z, acc[2]); acc[3] = fmaf(a, d.w, acc[3]);
+    const int total_rows = g.N * g.Ho;
+    const int r_begin = blockIdx.x * rows_per_block, r_end = min(r_begin + rows_per_block, total_rows);
+    const float pad_t = __fsub_rn(__fmul_rn(g.norm_scale, g.pad_value), g.norm_shift);
+    for (int row = r_begin; row < r_end; ++row) {
+        const int n = row / g.Ho, oy = row - n * g.Ho;
+        for (int ox0 = 0; ox0 < g.Wo; ox0 += kStemBwdPix) {
+            const int np = min(kStemBwdPix, g.Wo - ox0);
+            __syncthreads();
+            // input rows 2*oy - pad + {0,1,2}, columns 2*ox0 - pad .. + 2*np
+            const int ncol = 2 * np + 1;
+            for (int i = threadIdx.x; i < 3 * ncol; i += kStemBwdThreads) {
+                const int r3 = i / ncol, cx = i - r3 * ncol;
+                const int y = oy * 2 - g.pad_top + r3, x = ox0 * 2 - g.pad_left + cx;
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f;                     // conv zero pad
+                if (y >= 0 && x >= 0 && y < g.Hp && x < g.Wp) {
+                    if (y >= g.H || x >= g.W) { v0 = v1 = v2 = pad_t; }   // graph mean-pixel pad
+                    else {
+                        const T* px = in + (static_cast<long long>(n) * g.H * g.W + static_cast<long long>(y) * g.W + x) * 3;
+                        v0 = __fsub_rn(__fmul_rn(g.norm_scale, load_px<T>(px)), g.norm_shift);
+                        v1 = __fsub_rn(__fmul_rn(g.norm_scale, load_px<T>(px + 1)), g.norm_shift);
+                        v2 = __fsub_rn(__fmul_rn(g.norm_scale, load_px<T>(px + 2)), g.norm_shift);
+                    }
+                }
+                s_in[r3][cx * 3] = v0; s_in[r3][cx * 3 + 1] = v1; s_in[r3][cx * 3 + 2] = v2;
+            }
+            const long long p0 = (static_cast<long long>(n) * g.Ho + oy) * g.Wo + ox0;
+            for (int i = threadIdx.x; i < np * 4; i += kStemBwdThreads) {
+                const int pp = i >> 2, c8 = i & 3;
+                float f[8];
+                unpack8(ldg_stream(dz + (p0 + pp) * 32 + c8 * 8), f);
+                *reinterpret_cast<float4*>(&s_dz[pp][c8 * 8]) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(&s_dz[pp][c8 * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+            __syncthreads();
+            const float* a_ptr = &s_in[ky][kxc];
+#pragma unroll 4
+            for (int pp = 0; pp < np; ++pp) {
+                const float a = a_ptr[pp * 6];
+                const float4 d = *reinterpret_cast<const float4*>(&s_dz[pp][co4 * 4]);
+                acc[0] = fmaf(a, d.x, acc[0]); acc[1] = fmaf(a, d.y, acc[1]);
+                acc[2] = fmaf(a, d.z, acc[2]); acc[3] = fmaf(a, d.w, acc[3]);
+            }
         }
     }
     float* o = partial + static_cast<long long>(blockIdx.x) * 864 + k * 32 + co4 * 4;
@@ -123,6 +142,7 @@ stem_bwd_filter_kernel(const T* __restrict__ in, StemGeom g, const bf16* __restr
 // out[i] = sum over chunks of partial[chunk][i]; one warp per output, fixed lane assignment (deterministic)
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int n, int chunks) {
+    pdl_entry();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= n) return;
     double acc = 0.0;
@@ -137,6 +157,7 @@ template <int S, int D, int TW>
 __global__ void __launch_bounds__(256)
 dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGeom g, const float* __restrict__ scale,
               const float* __restrict__ shift, int act, bf16* __restrict__ out) {
+    pdl_entry();
     const int C8 = g.C >> 3;
     const int WG = (g.Wo + TW - 1) / TW;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -212,6 +233,7 @@ dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGe
 template <int S, int D>
 __global__ void __launch_bounds__(256)
 dw_bwd_data_kernel(const bf16* __restrict__ dz, const float* __restrict__ w, Conv2dGeom g, bf16* __restrict__ dx) {
+    pdl_entry();
     const int C8 = g.C >> 3;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = static_cast<long long>(g.N) * g.H * g.W * C8;
@@ -258,6 +280,7 @@ template <int S, int D>
 __global__ void __launch_bounds__(256, 2)
 dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Conv2dGeom g, float* __restrict__ partial,
                      int strips_per_block) {
+    pdl_entry();
     extern __shared__ float s_red[];                       // [rows_in_block][tpr][73]
     constexpr int TW = kDwfTW;
     constexpr int NCOLS = (TW - 1) * S + 2 * D + 1;
@@ -335,7 +358,7 @@ dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Co
 
 int blocks_for(long long total, int threads) { return static_cast<int>((total + threads - 1) / threads); }
 
-constexpr int kStemPixPerBlock = 2048;
+constexpr int kStemRowsPerBlock = 4;
 int dw_strips_per_block(const Conv2dGeom& g) {
     const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, kDwfTW);
     const int rows_in_block = 256 / std::min(g.C / 8, 256);
@@ -353,32 +376,28 @@ int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int
     StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
     const long long total = static_cast<long long>(N) * Ho * Wo * 2;
     if (in_is_u8)
-        stem_fwd_kernel<uint8_t><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const uint8_t*>(in), g, w, scale, shift, out);
+        AMS_LAUNCH((stem_fwd_kernel<uint8_t>), blocks_for(total, 256), 256, 0, s, static_cast<const uint8_t*>(in), g, w, scale, shift, out);
     else
-        stem_fwd_kernel<float><<<blocks_for(total, 256), 256, 0, s>>>(static_cast<const float*>(in), g, w, scale, shift, out);
-    AMS_LAUNCH_CHECK();
+        AMS_LAUNCH((stem_fwd_kernel<float>), blocks_for(total, 256), 256, 0, s, static_cast<const float*>(in), g, w, scale, shift, out);
     return 0;
 }
 
 size_t stem_bwd_workspace_floats(int N, int Ho, int Wo) {
-    const long long total = static_cast<long long>(N) * Ho * Wo;
-    return static_cast<size_t>(ceil_div_ll(total, kStemPixPerBlock)) * 864;
+    (void)Wo;
+    return static_cast<size_t>(ceil_div(N * Ho, kStemRowsPerBlock)) * 864;
 }
 
 int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
                          int pad_left, float pad_value, float norm_scale, float norm_shift, const bf16* dz, float* dw,
                          float* workspace, size_t workspace_floats, cudaStream_t s) {
     StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
-    const long long total = static_cast<long long>(N) * Ho * Wo;
-    const int chunks = static_cast<int>(ceil_div_ll(total, kStemPixPerBlock));
+    const int chunks = ceil_div(N * Ho, kStemRowsPerBlock);
     AMS_REQUIRE(workspace_floats >= static_cast<size_t>(chunks) * 864, "stem bwd workspace too small");
     if (in_is_u8)
-        stem_bwd_filter_kernel<uint8_t><<<chunks, kStemBwdThreads, 0, s>>>(static_cast<const uint8_t*>(in), g, dz, workspace, kStemPixPerBlock);
+        AMS_LAUNCH((stem_bwd_filter_kernel<uint8_t>), chunks, kStemBwdThreads, 0, s, static_cast<const uint8_t*>(in), g, dz, workspace, kStemRowsPerBlock);
     else
-        stem_bwd_filter_kernel<float><<<chunks, kStemBwdThreads, 0, s>>>(static_cast<const float*>(in), g, dz, workspace, kStemPixPerBlock);
-    AMS_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div(864 * 32, 256), 256, 0, s>>>(workspace, dw, 864, chunks);
-    AMS_LAUNCH_CHECK();
+        AMS_LAUNCH((stem_bwd_filter_kernel<float>), chunks, kStemBwdThreads, 0, s, static_cast<const float*>(in), g, dz, workspace, kStemRowsPerBlock);
+    AMS_LAUNCH((reduce_partials_kernel), ceil_div(864 * 32, 256), 256, 0, s, workspace, dw, 864, chunks);
     return 0;
 }
 
@@ -388,22 +407,20 @@ int dw_conv_fwd(const bf16* in, const float* w, const Conv2dGeom& g, const float
     constexpr int TW = 4;
     const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, TW) * (g.C / 8);
     const int nb = blocks_for(total, 256);
-    if (g.stride == 1 && g.dil == 1) dw_fwd_kernel<1, 1, TW><<<nb, 256, 0, s>>>(in, w, g, scale, shift, act, out);
-    else if (g.stride == 2 && g.dil == 1) dw_fwd_kernel<2, 1, TW><<<nb, 256, 0, s>>>(in, w, g, scale, shift, act, out);
-    else if (g.stride == 1 && g.dil == 2) dw_fwd_kernel<1, 2, TW><<<nb, 256, 0, s>>>(in, w, g, scale, shift, act, out);
+    if (g.stride == 1 && g.dil == 1) AMS_LAUNCH((dw_fwd_kernel<1, 1, TW>), nb, 256, 0, s, in, w, g, scale, shift, act, out);
+    else if (g.stride == 2 && g.dil == 1) AMS_LAUNCH((dw_fwd_kernel<2, 1, TW>), nb, 256, 0, s, in, w, g, scale, shift, act, out);
+    else if (g.stride == 1 && g.dil == 2) AMS_LAUNCH((dw_fwd_kernel<1, 2, TW>), nb, 256, 0, s, in, w, g, scale, shift, act, out);
     else AMS_REQUIRE(false, "unsupported depthwise stride/dilation");
-    AMS_LAUNCH_CHECK();
     return 0;
 }
 
 int dw_conv_bwd_data(const bf16* dz, const float* w, const Conv2dGeom& g, bf16* dx, cudaStream_t s) {
     const long long total = static_cast<long long>(g.N) * g.H * g.W * (g.C / 8);
     const int nb = blocks_for(total, 256);
-    if (g.stride == 1 && g.dil == 1) dw_bwd_data_kernel<1, 1><<<nb, 256, 0, s>>>(dz, w, g, dx);
-    else if (g.stride == 2 && g.dil == 1) dw_bwd_data_kernel<2, 1><<<nb, 256, 0, s>>>(dz, w, g, dx);
-    else if (g.stride == 1 && g.dil == 2) dw_bwd_data_kernel<1, 2><<<nb, 256, 0, s>>>(dz, w, g, dx);
+    if (g.stride == 1 && g.dil == 1) AMS_LAUNCH((dw_bwd_data_kernel<1, 1>), nb, 256, 0, s, dz, w, g, dx);
+    else if (g.stride == 2 && g.dil == 1) AMS_LAUNCH((dw_bwd_data_kernel<2, 1>), nb, 256, 0, s, dz, w, g, dx);
+    else if (g.stride == 1 && g.dil == 2) AMS_LAUNCH((dw_bwd_data_kernel<1, 2>), nb, 256, 0, s, dz, w, g, dx);
     else AMS_REQUIRE(false, "unsupported depthwise stride/dilation");
-    AMS_LAUNCH_CHECK();
     return 0;
 }
 
@@ -428,13 +445,11 @@ int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float
         AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_bwd_filter_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         attr = true;
     }
-    if (g.stride == 1 && g.dil == 1) dw_bwd_filter_kernel<1, 1><<<chunks, 256, smem, s>>>(x, dz, g, workspace, spb);
-    else if (g.stride == 2 && g.dil == 1) dw_bwd_filter_kernel<2, 1><<<chunks, 256, smem, s>>>(x, dz, g, workspace, spb);
-    else if (g.stride == 1 && g.dil == 2) dw_bwd_filter_kernel<1, 2><<<chunks, 256, smem, s>>>(x, dz, g, workspace, spb);
+    if (g.stride == 1 && g.dil == 1) AMS_LAUNCH((dw_bwd_filter_kernel<1, 1>), chunks, 256, smem, s, x, dz, g, workspace, spb);
+    else if (g.stride == 2 && g.dil == 1) AMS_LAUNCH((dw_bwd_filter_kernel<2, 1>), chunks, 256, smem, s, x, dz, g, workspace, spb);
+    else if (g.stride == 1 && g.dil == 2) AMS_LAUNCH((dw_bwd_filter_kernel<1, 2>), chunks, 256, smem, s, x, dz, g, workspace, spb);
     else AMS_REQUIRE(false, "unsupported depthwise stride/dilation");
-    AMS_LAUNCH_CHECK();
-    reduce_partials_kernel<<<ceil_div(9 * g.C * 32, 256), 256, 0, s>>>(workspace, dw, 9 * g.C, chunks);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((reduce_partials_kernel), ceil_div(9 * g.C * 32, 256), 256, 0, s, workspace, dw, 9 * g.C, chunks);
     return 0;
 }
 

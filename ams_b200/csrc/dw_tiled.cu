@@ -115,6 +115,7 @@ __device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restric
 template <int S, int D, int CB>
 __global__ void __launch_bounds__(dw_threads(CB), 3)
 dw_fwd_tiled_kernel(const DwFwdParams p) {
+    pdl_entry();
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int THREADS = dw_threads(CB), CV4 = CB / kCh, NPT = THREADS / CV4;
     const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
@@ -272,8 +273,7 @@ int launch_fwd(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
         AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_fwd_tiled_kernel<S, D, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr = true;
     }
-    dw_fwd_tiled_kernel<S, D, CB><<<static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s>>>(p);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((dw_fwd_tiled_kernel<S, D, CB>), static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s, p);
     return 0;
 }
 template <int S, int D>
@@ -326,6 +326,7 @@ struct BwdCols {
 template <int S, int D, int CB, int PADX>
 __global__ void __launch_bounds__(dw_threads(CB), 2)
 dw_bwd_fused_kernel(const DwBwdParams p) {
+    pdl_entry();
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int THREADS = dw_threads(CB), CV4 = CB / kCh, NPT = THREADS / CV4, CV8 = CB / 8, PXT = THREADS / CV8;
     typedef BwdCols<S, D, PADX> Cols;
@@ -555,6 +556,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
 // out[i] = sum over rows of partial[row][i]; block = 32 outputs x 32 row-lanes (coalesced), fixed order => deterministic
 __global__ void __launch_bounds__(1024)
 dw_reduce_rows_kernel(const float* __restrict__ partial, int rows, int n, float* __restrict__ out) {
+    pdl_entry();
     __shared__ double s_s[32][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + cl;
@@ -618,8 +620,7 @@ int launch_bwd(const DwBwdParams& p, const DwBwdTile& t, cudaStream_t s) {
         AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_bwd_fused_kernel<S, D, CB, PADX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         attr = true;
     }
-    dw_bwd_fused_kernel<S, D, CB, PADX><<<static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s>>>(p);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((dw_bwd_fused_kernel<S, D, CB, PADX>), static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s, p);
     return 0;
 }
 template <int S, int D, int PADX>
@@ -713,8 +714,7 @@ int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, c
     else if (g.pad_left & 1) rc = launch_bwd_cb<2, 1, 1>(p, t, s);
     else rc = launch_bwd_cb<2, 1, 0>(p, t, s);
     if (rc) return rc;
-    dw_reduce_rows_kernel<<<ceil_div(9 * g.C, 32), 1024, 0, s>>>(a.dw_partial, static_cast<int>(rows), 9 * g.C, a.dw);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((dw_reduce_rows_kernel), ceil_div(9 * g.C, 32), 1024, 0, s, a.dw_partial, static_cast<int>(rows), 9 * g.C, a.dw);
     if (rows_out) *rows_out = static_cast<int>(rows);
     return 0;
 }

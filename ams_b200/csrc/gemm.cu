@@ -109,7 +109,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int s = 0; s < 2; ++s) { t5::mbar_init(&tfull_bar[s], 1); t5::mbar_init(&tempty_bar[s], 128); }
         t5::fence_barrier_init();
     }
-    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
+    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); pdl_launch_dependents(); }
+    pdl_wait();
     for (int n = threadIdx.x; n < p.n_alloc; n += kGemmThreads) {
         s_scale[n] = (n < p.N) ? (p.scale ? p.scale[n] : 1.f) : 0.f;
         s_shift[n] = (n < p.N && p.shift) ? p.shift[n] : 0.f;
@@ -320,7 +321,8 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         t5::mbar_init(bres_bar, 1);
         t5::fence_barrier_init();
     }
-    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
+    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); pdl_launch_dependents(); }
+    pdl_wait();
     for (int n = threadIdx.x; n < p.n_alloc; n += kGemm2Threads) {
         s_scale[n] = (n < p.N) ? (p.scale ? p.scale[n] : 1.f) : 0.f;
         s_shift[n] = (n < p.N && p.shift) ? p.shift[n] : 0.f;
@@ -612,7 +614,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         t5::mbar_init(done_bar, 1);
         t5::fence_barrier_init();
     }
-    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); }
+    if (warp == 1) { t5::tmem_alloc(tmem_ptr, p.tmem_cols); t5::tmem_relinquish(); pdl_launch_dependents(); }
+    pdl_wait();
     t5::fence_before_thread_sync();
     __syncthreads();
     t5::fence_after_thread_sync();
@@ -696,6 +699,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Cin, int Cout, int lddw, int splits,
                     long long split_stride, int warp_per_item) {
+    pdl_entry();
     const long long n = static_cast<long long>(Cin) * Cout;
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -810,12 +814,11 @@ int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
         const int flags = ((d.scale || d.shift || d.act) ? kEpiAffine : 0) | (d.residual ? kEpiResidual : 0) |
                           (d.rowbias ? kEpiRowBias : 0) | (d.stats_partial ? kEpiStats : 0);
         switch (flags) {
-#define AMS_G2(FL) case FL: gemm_kmajor_v2_kernel<FL><<<pl.grid, kGemm2Threads, pl.smem_bytes, stream>>>(pl.tmA, pl.tmB, pl.tmC, p); break;
+#define AMS_G2(FL) case FL: AMS_LAUNCH((gemm_kmajor_v2_kernel<FL>), pl.grid, kGemm2Threads, pl.smem_bytes, stream, pl.tmA, pl.tmB, pl.tmC, p); break;
             AMS_G2(0) AMS_G2(1) AMS_G2(2) AMS_G2(3) AMS_G2(4) AMS_G2(5) AMS_G2(6) AMS_G2(7)
             AMS_G2(8) AMS_G2(9) AMS_G2(10) AMS_G2(11) AMS_G2(12) AMS_G2(13) AMS_G2(14) AMS_G2(15)
 #undef AMS_G2
         }
-        AMS_LAUNCH_CHECK();
         return 0;
     }
     GemmKParams p;
@@ -826,8 +829,7 @@ int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
     p.out = d.out; p.ldc = d.ldc; p.out_fp32 = d.out_fp32;
     p.scale = d.scale; p.shift = d.shift; p.rowbias = d.rowbias; p.rows_per_image = d.rows_per_image;
     p.residual = d.residual; p.ldr = d.ldr; p.act = d.act;
-    gemm_kmajor_kernel<<<pl.grid, kGemmThreads, pl.smem_bytes, stream>>>(pl.tmA, pl.tmB, p);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((gemm_kmajor_kernel), pl.grid, kGemmThreads, pl.smem_bytes, stream, pl.tmA, pl.tmB, p);
     return 0;
 }
 
@@ -889,15 +891,13 @@ int wgrad_launch(const WgradPlan& pl, cudaStream_t stream) {
     if (pl.splits == 1) { p.out = d.dW; p.ld_out = d.lddw; p.split_stride = 0; }
     else { p.out = d.workspace; p.ld_out = d.Cout; p.split_stride = static_cast<long long>(d.Cin) * d.Cout; }
     const int grid = pl.ci_tiles * pl.co_tiles * pl.splits;
-    gemm_wgrad_kernel<<<grid, kGemmThreads, pl.smem_bytes, stream>>>(pl.tmX, pl.tmZ, p);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((gemm_wgrad_kernel), grid, kGemmThreads, pl.smem_bytes, stream, pl.tmX, pl.tmZ, p);
     if (pl.splits > 1) {
         const long long n = static_cast<long long>(d.Cin) * d.Cout;
         const int wpi = pl.splits > 16 ? 1 : 0;
         const long long threads = ceil_div_ll(n, 4) * (wpi ? 32 : 1);
-        wgrad_reduce_kernel<<<int(ceil_div_ll(threads, 256)), 256, 0, stream>>>(d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
-                                                                               pl.splits, p.split_stride, wpi);
-        AMS_LAUNCH_CHECK();
+        AMS_LAUNCH((wgrad_reduce_kernel), int(ceil_div_ll(threads, 256)), 256, 0, stream, d.workspace, d.dW, d.Cin, d.Cout, d.lddw,
+                   pl.splits, p.split_stride, wpi);
     }
     return 0;
 }

@@ -49,6 +49,7 @@ constexpr int kRY = 16;
 __global__ void __launch_bounds__(256)
 head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ HeadConst g,
                   const uint8_t* __restrict__ labels, int32_t* __restrict__ pred, HeadStats* __restrict__ st) {
+    pdl_entry();
     __shared__ int s_hist[kMaxC * kMaxC];
     __shared__ int s_lut[256];
     __shared__ double s_loss[8];
@@ -137,6 +138,7 @@ head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ Head
 __global__ void __launch_bounds__(256)
 label_confmat_kernel(const uint8_t* __restrict__ before, const uint8_t* __restrict__ after, long long n,
                      const __grid_constant__ HeadConst g, HeadStats* __restrict__ st) {
+    pdl_entry();
     const int cc = g.cc;
     __shared__ int s_hist[kMaxC * kMaxC];
     __shared__ int s_lut[256];
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(256)
 head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadConst g,
                  const uint8_t* __restrict__ labels, float* __restrict__ rowbuf, double* __restrict__ row_loss,
                  int* __restrict__ row_valid) {
+    pdl_entry();
     extern __shared__ float s_g[];                 // [W][cc]
     __shared__ int s_lut[256];
     __shared__ double s_loss[8];
@@ -249,6 +252,7 @@ head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadC
 
 __global__ void head_finalize_kernel(const double* __restrict__ row_loss, const int* __restrict__ row_valid, int rows,
                                      HeadStats* st, float* loss_out) {
+    pdl_entry();
     __shared__ double s_l[256];
     __shared__ long long s_v[256];
     double l = 0.0; long long v = 0;
@@ -271,6 +275,7 @@ __global__ void head_finalize_kernel(const double* __restrict__ row_loss, const 
 __global__ void __launch_bounds__(256)
 head_cols_kernel(const float* __restrict__ rowbuf, const __grid_constant__ HeadConst g,
                  const HeadStats* __restrict__ st, float* __restrict__ dl_f32, bf16* __restrict__ dl_bf16) {
+    pdl_entry();
     const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long total = static_cast<long long>(g.N) * g.h * g.w * g.ldl;
     if (tid >= total) return;
@@ -300,6 +305,7 @@ head_cols_kernel(const float* __restrict__ rowbuf, const __grid_constant__ HeadC
 }
 
 __global__ void head_reset_kernel(HeadStats* st) {
+    pdl_entry();
     for (int i = threadIdx.x; i < kMaxClasses * kMaxClasses; i += blockDim.x) st->confmat[i] = 0;
     if (threadIdx.x == 0) { st->loss_sum = 0.0; st->n_valid = 0; }
 }
@@ -323,8 +329,7 @@ int make_const(const HeadGeom& g, HeadConst* c) {
 }  // namespace
 
 int head_reset(HeadStats* st, cudaStream_t s) {
-    head_reset_kernel<<<1, 256, 0, s>>>(st);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((head_reset_kernel), 1, 256, 0, s, st);
     return 0;
 }
 
@@ -333,8 +338,7 @@ int head_infer(const float* logits, const HeadGeom& g, const uint8_t* labels, in
     HeadConst c;
     if (make_const(g, &c)) return -1;
     dim3 grid(ceil_div(g.W, 256), ceil_div(g.H, kRY), g.N);
-    head_infer_kernel<<<grid, 256, 0, s>>>(logits, c, labels, pred, st);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((head_infer_kernel), grid, 256, 0, s, logits, c, labels, pred, st);
     return 0;
 }
 
@@ -345,8 +349,7 @@ int head_label_confmat(const uint8_t* before, const uint8_t* after, long long n,
     HeadConst c;
     if (make_const(g2, &c)) return -1;
     const int blocks = static_cast<int>(std::min<long long>(ceil_div_ll(n, 256 * 8), 4 * kNumSMs));
-    label_confmat_kernel<<<std::max(blocks, 1), 256, 0, s>>>(before, after, n, c, st);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((label_confmat_kernel), std::max(blocks, 1), 256, 0, s, before, after, n, c, st);
     return 0;
 }
 
@@ -373,13 +376,10 @@ int head_loss_backward(const float* logits, const HeadGeom& g, const uint8_t* la
         smem_set = smem;
     }
     AMS_REQUIRE(smem <= 200 * 1024, "row too wide for the head kernel");
-    head_rows_kernel<<<static_cast<int>(rows), 256, smem, s>>>(logits, c, labels, rowbuf, row_loss, row_valid);
-    AMS_LAUNCH_CHECK();
-    head_finalize_kernel<<<1, 256, 0, s>>>(row_loss, row_valid, static_cast<int>(rows), st, loss_out);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((head_rows_kernel), static_cast<int>(rows), 256, smem, s, logits, c, labels, rowbuf, row_loss, row_valid);
+    AMS_LAUNCH((head_finalize_kernel), 1, 256, 0, s, row_loss, row_valid, static_cast<int>(rows), st, loss_out);
     const long long total = static_cast<long long>(g.N) * g.h * g.w * g.ldl;
-    head_cols_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, s>>>(rowbuf, c, st, dl_f32, dl_bf16);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((head_cols_kernel), static_cast<int>(ceil_div_ll(total, 256)), 256, 0, s, rowbuf, c, st, dl_f32, dl_bf16);
     return 0;
 }
 

@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256)
 adam_masked_kernel(float* __restrict__ p, const float* __restrict__ g, float grad_scale, float* __restrict__ m,
                    float* __restrict__ v, const uint8_t* __restrict__ mask, long long n, float alpha, float omb1,
                    float omb2, float eps) {
+    pdl_entry();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     // TF1 ApplyAdam functor: m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= (m*alpha)/(sqrt(v)+eps)
@@ -25,11 +26,13 @@ adam_masked_kernel(float* __restrict__ p, const float* __restrict__ g, float gra
 
 __global__ void __launch_bounds__(256)
 abs_delta_kernel(const float* __restrict__ after, const float* __restrict__ before, float* __restrict__ d, long long n) {
+    pdl_entry();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) d[i] = fabsf(__fsub_rn(after[i], before[i]));
 }
 
 __global__ void select_init_kernel(SelectScratch* sc, unsigned int rank) {
+    pdl_entry();
     if (threadIdx.x < 256) sc->hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) { sc->prefix = 0; sc->rank = rank; sc->count_le = 0; sc->next_gt = 0xffffffffu; sc->kept = 0; }
 }
@@ -37,6 +40,7 @@ __global__ void select_init_kernel(SelectScratch* sc, unsigned int rank) {
 // histogram of byte (key >> shift) & 0xff over keys whose bits above shift+8 equal the current prefix
 __global__ void __launch_bounds__(256)
 radix_hist_kernel(const float* __restrict__ d, long long n, int shift, SelectScratch* sc) {
+    pdl_entry();
     __shared__ unsigned int s_h[256];
     s_h[threadIdx.x] = 0;
     __syncthreads();
@@ -52,6 +56,7 @@ radix_hist_kernel(const float* __restrict__ d, long long n, int shift, SelectScr
 }
 
 __global__ void radix_pick_kernel(SelectScratch* sc, int shift) {
+    pdl_entry();
     if (threadIdx.x == 0) {
         unsigned int rank = sc->rank, cum = 0;
         int b = 0;
@@ -71,6 +76,7 @@ __global__ void radix_pick_kernel(SelectScratch* sc, int shift) {
 // count of keys <= v_lo and the smallest key > v_lo
 __global__ void __launch_bounds__(256)
 select_neighbors_kernel(const float* __restrict__ d, long long n, SelectScratch* sc) {
+    pdl_entry();
     const unsigned int v = sc->prefix;
     unsigned int cnt = 0, nxt = 0xffffffffu;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -87,6 +93,7 @@ select_neighbors_kernel(const float* __restrict__ d, long long n, SelectScratch*
 }
 
 __global__ void select_threshold_kernel(SelectScratch* sc, unsigned int lo, unsigned int n, double w_lo, double w_hi) {
+    pdl_entry();
     if (threadIdx.x != 0) return;
     const unsigned int v_lo = sc->prefix;
     sc->v_lo = v_lo;
@@ -102,6 +109,7 @@ __global__ void select_threshold_kernel(SelectScratch* sc, unsigned int lo, unsi
 __global__ void __launch_bounds__(256)
 select_apply_kernel(float* __restrict__ after, const float* __restrict__ before, const float* __restrict__ d,
                     uint8_t* __restrict__ mask, long long n, SelectScratch* sc) {
+    pdl_entry();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const float thr = sc->threshold;
     bool keep = false;
@@ -118,6 +126,7 @@ select_apply_kernel(float* __restrict__ after, const float* __restrict__ before,
 __global__ void __launch_bounds__(256)
 pack_bits_kernel(const uint8_t* __restrict__ mask, const VarSeg* __restrict__ segs, int nseg, long long total_bytes,
                  uint8_t* __restrict__ out) {
+    pdl_entry();
     const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (b >= total_bytes) return;
     int lo = 0, hi = nseg - 1;                       // last segment with bit_byte_offset <= b
@@ -139,6 +148,7 @@ pack_bits_kernel(const uint8_t* __restrict__ mask, const VarSeg* __restrict__ se
 constexpr int kPackBlock = 1024;
 __global__ void __launch_bounds__(256)
 pack_count_kernel(const uint8_t* __restrict__ mask, long long n, unsigned int* __restrict__ counts) {
+    pdl_entry();
     __shared__ unsigned int s_c[8];
     const long long base = static_cast<long long>(blockIdx.x) * kPackBlock;
     unsigned int c = 0;
@@ -156,6 +166,7 @@ pack_count_kernel(const uint8_t* __restrict__ mask, long long n, unsigned int* _
     }
 }
 __global__ void pack_scan_kernel(unsigned int* counts, int nblocks, unsigned long long* kept_out) {
+    pdl_entry();
     // single thread exclusive scan (<= ~2100 blocks)
     if (threadIdx.x == 0) {
         unsigned long long run = 0;
@@ -166,6 +177,7 @@ __global__ void pack_scan_kernel(unsigned int* counts, int nblocks, unsigned lon
 __global__ void __launch_bounds__(256)
 pack_scatter_kernel(const float* __restrict__ params, const uint8_t* __restrict__ mask, long long n,
                     const unsigned int* __restrict__ offsets, __half* __restrict__ out) {
+    pdl_entry();
     __shared__ unsigned int s_w[8];
     const long long base = static_cast<long long>(blockIdx.x) * kPackBlock;
     bool keep[4]; unsigned int c = 0;
@@ -194,6 +206,7 @@ pack_scatter_kernel(const float* __restrict__ params, const uint8_t* __restrict_
 // fp32 HWIO [Cin][Cout] -> bf16 [Cout][ld_fwd] (transposed) and bf16 [Cin][ld_bwd]
 __global__ void __launch_bounds__(256)
 cast_weights_kernel(const WeightCast* __restrict__ table) {
+    pdl_entry();
     const WeightCast t = table[blockIdx.y];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= t.rows * t.Cout) return;
@@ -208,8 +221,7 @@ cast_weights_kernel(const WeightCast* __restrict__ table) {
 
 int adam_masked(float* p, const float* g, float grad_scale, float* m, float* v, const uint8_t* mask, long long n,
                 float alpha, float omb1, float omb2, float eps, cudaStream_t s) {
-    adam_masked_kernel<<<static_cast<int>(ceil_div_ll(n, 256)), 256, 0, s>>>(p, g, grad_scale, m, v, mask, n, alpha, omb1, omb2, eps);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((adam_masked_kernel), static_cast<int>(ceil_div_ll(n, 256)), 256, 0, s, p, g, grad_scale, m, v, mask, n, alpha, omb1, omb2, eps);
     return 0;
 }
 
@@ -218,22 +230,15 @@ int select_coordinates(float* after, const float* before, float* d, uint8_t* mas
     AMS_REQUIRE(n > 0 && n < (1LL << 32) && lo >= 0 && lo < n, "selection size / rank out of range");
     const int nb = static_cast<int>(ceil_div_ll(n, 256));
     const int nbr = std::min(nb, 8 * kNumSMs);
-    abs_delta_kernel<<<nb, 256, 0, s>>>(after, before, d, n);
-    AMS_LAUNCH_CHECK();
-    select_init_kernel<<<1, 256, 0, s>>>(sc, static_cast<unsigned int>(lo));
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((abs_delta_kernel), nb, 256, 0, s, after, before, d, n);
+    AMS_LAUNCH((select_init_kernel), 1, 256, 0, s, sc, static_cast<unsigned int>(lo));
     for (int shift = 24; shift >= 0; shift -= 8) {
-        radix_hist_kernel<<<nbr, 256, 0, s>>>(d, n, shift, sc);
-        AMS_LAUNCH_CHECK();
-        radix_pick_kernel<<<1, 256, 0, s>>>(sc, shift);
-        AMS_LAUNCH_CHECK();
+        AMS_LAUNCH((radix_hist_kernel), nbr, 256, 0, s, d, n, shift, sc);
+        AMS_LAUNCH((radix_pick_kernel), 1, 256, 0, s, sc, shift);
     }
-    select_neighbors_kernel<<<nbr, 256, 0, s>>>(d, n, sc);
-    AMS_LAUNCH_CHECK();
-    select_threshold_kernel<<<1, 32, 0, s>>>(sc, static_cast<unsigned int>(lo), static_cast<unsigned int>(n), 1.0 - w_hi, w_hi);
-    AMS_LAUNCH_CHECK();
-    select_apply_kernel<<<nb, 256, 0, s>>>(after, before, d, mask, n, sc);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((select_neighbors_kernel), nbr, 256, 0, s, d, n, sc);
+    AMS_LAUNCH((select_threshold_kernel), 1, 32, 0, s, sc, static_cast<unsigned int>(lo), static_cast<unsigned int>(n), 1.0 - w_hi, w_hi);
+    AMS_LAUNCH((select_apply_kernel), nb, 256, 0, s, after, before, d, mask, n, sc);
     return 0;
 }
 
@@ -244,21 +249,16 @@ int pack_delta(const float* params, const uint8_t* mask, const VarSeg* segs_dev,
                unsigned long long* kept_out, cudaStream_t s) {
     const int nblocks = pack_delta_blocks(n);
     AMS_REQUIRE(nblocks <= nblocks_alloc, "pack_delta scratch too small");
-    pack_bits_kernel<<<static_cast<int>(ceil_div_ll(mask_bytes, 256)), 256, 0, s>>>(mask, segs_dev, nseg, mask_bytes, out_bits);
-    AMS_LAUNCH_CHECK();
-    pack_count_kernel<<<nblocks, 256, 0, s>>>(mask, n, block_counts);
-    AMS_LAUNCH_CHECK();
-    pack_scan_kernel<<<1, 32, 0, s>>>(block_counts, nblocks, kept_out);
-    AMS_LAUNCH_CHECK();
-    pack_scatter_kernel<<<nblocks, 256, 0, s>>>(params, mask, n, block_counts, out_vals);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((pack_bits_kernel), static_cast<int>(ceil_div_ll(mask_bytes, 256)), 256, 0, s, mask, segs_dev, nseg, mask_bytes, out_bits);
+    AMS_LAUNCH((pack_count_kernel), nblocks, 256, 0, s, mask, n, block_counts);
+    AMS_LAUNCH((pack_scan_kernel), 1, 32, 0, s, block_counts, nblocks, kept_out);
+    AMS_LAUNCH((pack_scatter_kernel), nblocks, 256, 0, s, params, mask, n, block_counts, out_vals);
     return 0;
 }
 
 int cast_weights(const WeightCast* table_dev, int n_layers, int max_elems, cudaStream_t s) {
     dim3 grid(ceil_div(max_elems, 256), n_layers);
-    cast_weights_kernel<<<grid, 256, 0, s>>>(table_dev);
-    AMS_LAUNCH_CHECK();
+    AMS_LAUNCH((cast_weights_kernel), grid, 256, 0, s, table_dev);
     return 0;
 }
 
