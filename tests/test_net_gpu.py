@@ -173,16 +173,21 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
 
 
-def test_train_step_against_oracle():
+@pytest.mark.parametrize('tag,n,h,w,cls', [
+    ('cityscapes', 2, 64, 128, [0, 1, 2, 8, 10, 11, 13]),
+    ('cityscapes', 1, 64, 128, [0, 1, 2, 8, 10, 11, 13]),      # batch 1: image_pooling BN over a single value (output == beta)
+    ('cityscapes', 2, 96, 192, list(range(19))),               # ragged tiles: 49x97 / 25x49 / 13x25 / 7x13 feature maps
+    ('pascalvoc2012', 2, 64, 128, [0, 2, 7, 15]),              # 21-class graph: PadV2 stem, depthwise BN decay 0.98
+])
+def test_train_step_against_oracle(tag, n, h, w, cls):
     """Backward parity, teacher-forced: the oracle's autograd runs on a graph whose stored tensors (every raw conv
     output z and every layer output y) carry the DEVICE's values, so both sides differentiate the same function at
     the same point; what is left is the bf16 storage of the device's gradient tensors (a few % per tensor).
     The un-forced comparison is logged only: a forward re-computed with different bf16 rounding flips ReLU masks
     and is amplified by the pooled-branch BatchNorm (oracle bf16 vs fp64 gradients agree to cos 0.8-0.96 only)."""
-    spec, V, fr = make_checkpoint()
-    cls = [0, 1, 2, 8, 10, 11, 13]
-    labels = so.synthetic_labels(N, H, W, seed=2, block=16)
-    st = load_student(spec, V, cls)
+    spec, V, fr = make_checkpoint(tag, 1, n, h, w)
+    labels = so.synthetic_labels(n, h, w, seed=2, block=16)
+    st = load_student(spec, V, cls, h, w)
     st.enqueue(fr, labels)
     loss = st.train_step(1e-3, masked=False)
     g_dev = st.split_trainable(st.get_gradients())
