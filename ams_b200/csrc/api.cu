@@ -96,6 +96,7 @@ ams_net* ams_create(const ams_config* cfg) {
     if (cudaStreamCreateWithFlags(&net->side_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
     if (cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaEventCreateWithFlags(&net->ev_pool, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     net->stream = net->own_stream;
     if (net_build_topology(net)) return fail("topology");
     const LayerDef& lg = net->layers.back();
@@ -174,6 +175,7 @@ void ams_destroy(ams_net* h) {
     if (net->side_stream) cudaStreamDestroy(net->side_stream);
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
+    if (net->ev_pool) cudaEventDestroy(net->ev_pool);
     delete net;
 }
 

@@ -531,10 +531,12 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
                 t5::named_barrier_sync(3, kEpiThreads);
                 if (et < p.block_n) {
-                    double s = 0.0, sq = 0.0;
+                    // 128 rows of one tile: fp32 is enough (fixed order); the running sums over tiles are fp64
+                    float s = 0.f, sq = 0.f;
+#pragma unroll 4
                     for (int sl = 0; sl < nslices; ++sl) { const float2 v2 = s_part[sl * p.block_n + et]; s += v2.x; sq += v2.y; }
-                    s_run[n_tile * p.block_n + et] += s;
-                    s_run[p.n_alloc + n_tile * p.block_n + et] += sq;
+                    s_run[n_tile * p.block_n + et] += static_cast<double>(s);
+                    s_run[p.n_alloc + n_tile * p.block_n + et] += static_cast<double>(sq);
                 }
             }
             if (p.linear_out) {

@@ -390,6 +390,7 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
     const bool frozen = (bn_mode == AMS_BN_MOVING);
     cudaStream_t s = net->stream;
     if (net_prepare_weights(net, frozen)) return -1;
+    bool pool_pending = false;
     for (size_t i = 0; i < L.size(); ++i) {
         const LayerDef& d = L[i];
         net->prof.layer = d.name.c_str();
@@ -397,8 +398,21 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
         LayerBuf& b = p->buf[i];
         const double out_bytes = 2.0 * M * d.cout;
         if (d.kind == kImagePool) {
-            PROF("imgpool_fwd", 2.0 * p->N * L[d.input].out_h * L[d.input].out_w * d.cin, imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s));
+            // six tiny latency-bound kernels: off the chain (side stream) while aspp0 runs; joined before concat_projection
+            if (!net->prof.enabled && net->side_stream) {
+                AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
+                AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+                if (imgpool_forward(imgpool_desc(net, p, frozen, update_moving), net->side_stream)) return -1;
+                AMS_CUDA_CHECK(cudaEventRecord(net->ev_join, net->side_stream));
+                pool_pending = true;
+            } else {
+                PROF("imgpool_fwd", 2.0 * p->N * L[d.input].out_h * L[d.input].out_w * d.cin, imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s));
+            }
             continue;
+        }
+        if (pool_pending && d.name == "concat_projection") {
+            AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_join, 0));
+            pool_pending = false;
         }
         if (d.kind == kLogits) {
             PROF("gemm_logits", 2.0 * M * d.cin + 4.0 * M * 32, gemm_launch(p->fwd_frozen[i], s));
@@ -455,7 +469,7 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     // Filter gradients of the 1x1 convs: nothing downstream in the backward chain reads them, so outside profiling
     // they go to a side stream (fork after their dz is ready, one join at the end) and overlap with the chain.
     const bool side = !net->prof.enabled && net->side_stream != nullptr;
-    bool forked = false;
+    bool forked = false, pool_bwd_pending = false;
     auto wgrad_on_side = [&](const WgradPlan& wp) -> int {
         AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
         AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
@@ -469,7 +483,14 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     net->prof.layer = lg.name.c_str();
     PROF("head_loss_bwd", static_cast<double>(p->N) * c.height * c.width + 4.0 * M16 * 32 * 2,
          head_loss_backward(p->logits, hg, p->in_labels, p->rowbuf, p->dlogits_f32, p->dlogits_bf16, net->head_st, p->loss_dev, s));
-    PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
+    if (side) {
+        AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
+        AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+        forked = true;
+        if (colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, net->side_stream)) return -1;
+    } else {
+        PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
+    }
     if (side) { if (wgrad_on_side(p->wgrad[nl - 1])) return -1; }
     else PROF("gemm_wgrad", 2.0 * M16 * (lg.cin + 32), wgrad_launch(p->wgrad[nl - 1], s));
     PROF("gemm_dgrad", 2.0 * M16 * (lg.cin + 32), gemm_launch(p->dgrad[nl - 1], s));
@@ -508,11 +529,10 @@ int net_backward(Net* net, Plan* p, bool normalize) {
             PROF("bn_bwd", 5.0 * tb, bn_backward(b.g, nullptr, b.z, bl, d.act, b.gz, net->grads + d.gamma_off, net->grads + d.beta_off, p->bn_ws, s));
         }
         if (d.kind == kConv1x1) {
-            if (side) { if (wgrad_on_side(p->wgrad[i])) return -1; }
-            else PROF("gemm_wgrad", 2.0 * M * d.k_rows + tb, wgrad_launch(p->wgrad[i], s));
-            if (d.name == "concat_projection") {
+            const bool is_cp = d.name == "concat_projection";
+            ImgPoolBwd ib;
+            if (is_cp) {
                 const LayerDef& ipd = L[nl - 4];
-                ImgPoolBwd ib;
                 ib.f = imgpool_desc(net, p, false, false);
                 ib.dz_proj = b.gz;
                 ib.dbias = p->ip_dbias;
@@ -520,7 +540,25 @@ int net_backward(Net* net, Plan* p, bool normalize) {
                 ib.d_w_pool = net->grads + ipd.w_off;
                 ib.d_gamma = net->grads + ipd.gamma_off; ib.d_beta = net->grads + ipd.beta_off;
                 ib.dfeat_rowbias = p->dfeat_rowbias;
-                PROF("imgpool_bwd", tb, imgpool_backward(ib, s));
+            }
+            if (side) {
+                if (is_cp) {
+                    // pooled-branch backward first on the side stream; the chain needs its row bias only at the aspp0 dgrad
+                    AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
+                    AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+                    forked = true;
+                    if (imgpool_backward(ib, net->side_stream)) return -1;
+                    AMS_CUDA_CHECK(cudaEventRecord(net->ev_pool, net->side_stream));
+                    pool_bwd_pending = true;
+                }
+                if (wgrad_on_side(p->wgrad[i])) return -1;
+            } else {
+                PROF("gemm_wgrad", 2.0 * M * d.k_rows + tb, wgrad_launch(p->wgrad[i], s));
+                if (is_cp) PROF("imgpool_bwd", tb, imgpool_backward(ib, s));
+            }
+            if (pool_bwd_pending && d.name == "aspp0") {
+                AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_pool, 0));
+                pool_bwd_pending = false;
             }
             PROF("gemm_dgrad", tb + 2.0 * M * d.k_rows + 2.0 * d.k_rows * d.cout, gemm_launch(p->dgrad[i], s));
         } else if (d.kind == kDepthwise) {

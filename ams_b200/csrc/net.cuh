@@ -109,7 +109,7 @@ struct Net {
     int num_sms = kNumSMs;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     // filter gradients of the 1x1 convs run on a side stream, concurrently with the backward chain that does not need them
-    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pool = nullptr;
     std::vector<VarInfo> vars;
     std::unordered_map<std::string, int> var_index;
     std::vector<int> trainable_order;       // indices into vars, tf.trainable_variables() order

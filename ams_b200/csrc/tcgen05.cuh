@@ -42,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // for the single-thread producer / MMA-issuer warps: back off between polls so that the spin does not take issue
 // slots from the epilogue warps that share the SM sub-partition
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { __nanosleep(40); }
+    while (!mbar_try_wait(bar, parity)) { __nanosleep(100); }
 }
 
 // ---- TMA
