@@ -141,28 +141,55 @@ bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, in
     }
 }
 
+// Elementwise passes: a thread owns one 8-channel group (its per-channel parameters live in registers) and walks kEwRows
+// rows of the block's row range with all loads issued before the arithmetic; block = min(C/8, 256) channel groups x rows.
+constexpr int kEwRows = 4;
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                const bf16* __restrict__ residual, bf16* __restrict__ y, long long total8, int C) {
+                const bf16* __restrict__ residual, bf16* __restrict__ y, int M, int C) {
     pdl_entry();
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total8) return;
-    const int c0 = static_cast<int>(i % (C >> 3)) * 8;
-    float v[8];
-    unpack8(ldg_stream(z + i * 8), v);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const int c8n = C >> 3;
+    const int tpr = min(c8n, 256), rib = 256 / tpr;
+    const int lr = threadIdx.x / tpr, lc = threadIdx.x - lr * tpr;
+    if (lr >= rib) return;
+    for (int c8 = lc; c8 < c8n; c8 += tpr) {
+        const int c0 = c8 * 8;
+        float sc[8], sh[8];
+        {
+            const float4 s0 = *reinterpret_cast<const float4*>(scale + c0), s1 = *reinterpret_cast<const float4*>(scale + c0 + 4);
+            const float4 h0 = *reinterpret_cast<const float4*>(shift + c0), h1 = *reinterpret_cast<const float4*>(shift + c0 + 4);
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+        }
+        const int r0 = blockIdx.x * (rib * kEwRows) + lr;
+        uint4 vz[kEwRows], vr[kEwRows];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = act_apply(fmaf(v[q], sc[q], sh[q]), act);
-    if (residual) {
-        float r[8];
-        unpack8(ldg_stream(residual + i * 8), r);
+        for (int u = 0; u < kEwRows; ++u) {
+            const int r = r0 + u * rib;
+            if (r < M) {
+                const long long off = static_cast<long long>(r) * C + c0;
+                vz[u] = ldg_stream(z + off);
+                if (residual) vr[u] = ldg_stream(residual + off);
+            }
+        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] += r[q];
+        for (int u = 0; u < kEwRows; ++u) {
+            const int r = r0 + u * rib;
+            if (r < M) {
+                float v[8];
+                unpack8(vz[u], v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = act_apply(fmaf(v[q], sc[q], sh[q]), act);
+                if (residual) {
+                    float f[8];
+                    unpack8(vr[u], f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += f[q];
+                }
+                stg_stream(y + static_cast<long long>(r) * C + c0, pack8(v));
+            }
+        }
     }
-    stg_stream(y + i * 8, pack8(v));
 }
 
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mm, const float* mv, float eps,
@@ -287,29 +314,51 @@ __device__ __forceinline__ void load8f(const float* p, float* o) {
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
-                    int act, long long total8, int C, bf16* dz_out) {
+                    int act, int M, int C, bf16* dz_out) {
     pdl_entry();
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total8) return;
     const int c8n = C >> 3;
-    const int c0 = static_cast<int>(i % c8n) * 8;
-    float g[8], v[8], sc[8], sh[8], ca[8], cb[8], cc[8];
-    unpack8(*reinterpret_cast<const uint4*>(dy + i * 8), g);      // may alias dz_out: plain load
-    unpack8(ldg_stream(z + i * 8), v);
-    load8f(scale + c0, sc); load8f(shift + c0, sh);
-    load8f(coef + c0, ca); load8f(coef + C + c0, cb); load8f(coef + 2 * C + c0, cc);
-    if (dy2) {
-        float g2[8];
-        unpack8(ldg_stream(dy2 + i * 8), g2);
+    const int tpr = min(c8n, 256), rib = 256 / tpr;
+    const int lr = threadIdx.x / tpr, lc = threadIdx.x - lr * tpr;
+    if (lr >= rib) return;
+    for (int c8 = lc; c8 < c8n; c8 += tpr) {
+        const int c0 = c8 * 8;
+        float sc[8], sh[8], ca[8], cb[8], cc[8];
+        load8f(scale + c0, sc); load8f(shift + c0, sh);
+        load8f(coef + c0, ca); load8f(coef + C + c0, cb); load8f(coef + 2 * C + c0, cc);
+        const int r0 = blockIdx.x * (rib * kEwRows) + lr;
+        uint4 vg[kEwRows], vz[kEwRows], vg2[kEwRows];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) g[q] += g2[q];
-    }
+        for (int u = 0; u < kEwRows; ++u) {
+            const int r = r0 + u * rib;
+            if (r < M) {
+                const long long off = static_cast<long long>(r) * C + c0;
+                vg[u] = *reinterpret_cast<const uint4*>(dy + off);           // may alias dz_out: plain load
+                vz[u] = ldg_stream(z + off);
+                if (dy2) vg2[u] = ldg_stream(dy2 + off);
+            }
+        }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const float gm = act_mask(g[q], fmaf(v[q], sc[q], sh[q]), act);
-        g[q] = fmaf(ca[q], gm, fmaf(cb[q], v[q], cc[q]));
+        for (int u = 0; u < kEwRows; ++u) {
+            const int r = r0 + u * rib;
+            if (r < M) {
+                float g[8], v[8];
+                unpack8(vg[u], g);
+                unpack8(vz[u], v);
+                if (dy2) {
+                    float g2[8];
+                    unpack8(vg2[u], g2);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] += g2[q];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float gm = act_mask(g[q], fmaf(v[q], sc[q], sh[q]), act);
+                    g[q] = fmaf(ca[q], gm, fmaf(cb[q], v[q], cc[q]));
+                }
+                stg_stream(dz_out + static_cast<long long>(r) * C + c0, pack8(g));
+            }
+        }
     }
-    stg_stream(dz_out + i * 8, pack8(g));
 }
 
 // ------------------------------------------------------------------------------------ generic column sums
@@ -480,8 +529,8 @@ int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, in
 
 int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y, long long M,
              int C, cudaStream_t s) {
-    const long long total8 = M * C / 8;
-    AMS_LAUNCH((bn_apply_kernel), static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s, z, scale, shift, act, residual, y, total8, C);
+    const int rib = 256 / std::min(C / 8, 256);
+    AMS_LAUNCH((bn_apply_kernel), static_cast<int>(ceil_div_ll(M, rib * kEwRows)), 256, 0, s, z, scale, shift, act, residual, y, static_cast<int>(M), C);
     return 0;
 }
 
@@ -499,8 +548,8 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     float* coef = reinterpret_cast<float*>(ws + static_cast<size_t>(chunks) * 2 * L.C);
     AMS_LAUNCH((bn_bwd_reduce_kernel), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, d_gamma, d_beta, coef);
-    const long long total8 = L.M * L.C / 8;
-    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, total8, L.C, dz_out);
+    const int rib = 256 / std::min(L.C / 8, 256);
+    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(L.M, rib * kEwRows)), 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, static_cast<int>(L.M), L.C, dz_out);
     return 0;
 }
 
@@ -520,8 +569,8 @@ int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer
 }
 
 int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s) {
-    const long long total8 = L.M * L.C / 8;
-    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(total8, 256)), 256, 0, s, dy_masked, nullptr, z, L.scale, L.shift, coef, 0, total8, L.C, dz_out);
+    const int rib = 256 / std::min(L.C / 8, 256);
+    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(L.M, rib * kEwRows)), 256, 0, s, dy_masked, nullptr, z, L.scale, L.shift, coef, 0, static_cast<int>(L.M), L.C, dz_out);
     return 0;
 }
 
