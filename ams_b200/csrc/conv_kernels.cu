@@ -358,7 +358,7 @@ dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Co
 
 int blocks_for(long long total, int threads) { return static_cast<int>((total + threads - 1) / threads); }
 
-constexpr int kStemRowsPerBlock = 4;
+constexpr int kStemRowsPerBlock = 1;        // ~2k small CTAs, 9 resident per SM: the per-segment staging round trips overlap
 int dw_strips_per_block(const Conv2dGeom& g) {
     const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, kDwfTW);
     const int rows_in_block = 256 / std::min(g.C / 8, 256);
