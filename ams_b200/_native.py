@@ -68,6 +68,8 @@ _SIGNATURES = {
     'ams_layout_tensor_info': (_i, [_i, _i, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll)]),
     'ams_layout_num_layers': (_i, [_i, _i]),
     'ams_layout_layer_info': (_i, [_i, _i, _i, C.c_char_p, _i] + [C.POINTER(_i)] * 6 + [C.POINTER(_f)] * 2 + [C.POINTER(_i)]),
+    'ams_debug_dw_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
+    'ams_debug_dw_bwd_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
     'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -138,6 +138,11 @@ int ams_layout_layer_info(int num_classes, int graph_variant, int index, char* n
                           int* cout, int* stride, int* dilation, int* act, float* bn_eps, float* bn_one_minus_decay,
                           int* residual_from);
 
+/* ---- host-only diagnostics: the shared-memory tile the depthwise kernels pick for a geometry (no CUDA calls).
+ * out8 = {tile_h, tile_w, tiles_x, tiles_y, channel_chunk, smem_bytes, ctas, threads (fwd) | strips per row (bwd)} */
+int ams_debug_dw_tile(int n, int h, int w, int c, int ho, int wo, int stride, int dilation, int* out8);
+int ams_debug_dw_bwd_tile(int n, int h, int w, int c, int ho, int wo, int stride, int dilation, int* out8);
+
 /* ---- op-level entry points on raw DEVICE pointers (kernel unit tests; see tests/test_ops_gpu.py) */
 int ams_op_conv1x1(const void* a_bf16, const void* w_bf16 /*[N][K]*/, int M, int N, int K, const float* scale,
                    const float* shift, const float* rowbias, int rows_per_image, const void* residual_bf16, int act,

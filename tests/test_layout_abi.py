@@ -71,3 +71,45 @@ def test_product_never_imports_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'student_oracle' not in src and 'metagraph_interp' not in src and 'import oracle' not in src, f
+
+
+def _dw_geometries():
+    """(H, W, C, Ho, Wo, stride, dilation) of the 17 depthwise layers at several frame sizes (TF SAME geometry)."""
+    blocks = [(32, 1, 1), (96, 2, 1), (144, 1, 1), (144, 2, 1), (192, 1, 1), (192, 1, 1), (192, 2, 1), (384, 1, 1), (384, 1, 1),
+              (384, 1, 1), (384, 1, 1), (576, 1, 1), (576, 1, 1), (576, 1, 1), (960, 1, 2), (960, 1, 2), (960, 1, 2)]
+    out = []
+    for height in (64, 96, 256, 512):
+        h, w = (height + 2) // 2, (2 * height + 2) // 2                 # stem output of the (H+1) x (2H+1) padded frame
+        for c, s, d in blocks:
+            ho, wo = -(-h // s), -(-w // s)
+            out.append((h, w, c, ho, wo, s, d))
+            h, w = ho, wo
+    return out
+
+
+@pytest.mark.parametrize('batch', [1, 8])
+def test_depthwise_tile_planner_invariants(batch):
+    """Host-only: for every depthwise geometry the planners pick a tile that covers the image, fits the shared-memory
+    budget of its occupancy target, keeps stride-2 tile origins even, and the magic-number divisions the kernels use
+    (n * (65536 / d + 1) >> 16 == n / d for n < 256) are exact for the chosen strip / tile widths."""
+    import ctypes as C
+    lib = nat.lib()
+    out = (C.c_int * 8)()
+    for (h, w, c, ho, wo, s, d) in _dw_geometries():
+        assert lib.ams_debug_dw_tile(batch, h, w, c, ho, wo, s, d, out) == 0
+        th, tw, ntx, nty, cb, smem, ctas, threads = list(out)
+        assert c % cb == 0 and cb in (32, 48, 64) and threads in (252, 256)
+        assert th * nty >= ho and tw * ntx >= wo and 0 < smem <= 72 * 1024
+        assert ctas == batch * ntx * nty * (c // cb)
+        nstrips = -(-tw // 4)
+        iwp = (nstrips * 4 - 1) * s + 2 * d + 1
+        for dd in (iwp, nstrips):
+            assert all(((n * (65536 // dd + 1)) >> 16) == n // dd for n in range(256)), (dd,)
+        assert lib.ams_debug_dw_bwd_tile(batch, h, w, c, ho, wo, s, d, out) == 0
+        th, tw, ntx, nty, cb, smem, ctas, nstrips = list(out)
+        assert th * nty >= h and tw * ntx >= w and 0 < smem <= 100 * 1024 and c % cb == 0
+        if s == 2:
+            assert th % 2 == 0 and tw % 2 == 0
+        owp = nstrips * 4 + 2 * d if s == 1 else nstrips * 2 + 1
+        for dd in (owp, nstrips):
+            assert all(((n * (65536 // dd + 1)) >> 16) == n // dd for n in range(256)), (dd,)
