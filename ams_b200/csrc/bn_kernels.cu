@@ -90,21 +90,19 @@ __device__ __forceinline__ bool finalize_sums(const double* __restrict__ partial
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     double s = 0.0, q = 0.0;
     if (c < C) {
-        // 16 independent row loads in flight per thread and pass (the rows are a latency chain otherwise)
-        int k = rl;
-        for (; k + 7 * kFinRows < chunks; k += 8 * kFinRows) {
+        // 16 independent row loads in flight per thread and pass (the rows are a latency chain otherwise); the ragged
+        // tail is one more predicated pass, not a serial loop
+        for (int k = rl; k < chunks; k += 8 * kFinRows) {
             double a[8], b[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                a[u] = partial[static_cast<long long>(k + u * kFinRows) * 2 * C + c];
-                b[u] = partial[static_cast<long long>(k + u * kFinRows) * 2 * C + C + c];
+                const int kk = k + u * kFinRows;
+                const bool ok = kk < chunks;
+                a[u] = ok ? partial[static_cast<long long>(kk) * 2 * C + c] : 0.0;
+                b[u] = ok ? partial[static_cast<long long>(kk) * 2 * C + C + c] : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) { s += a[u]; q += b[u]; }
-        }
-        for (; k < chunks; k += kFinRows) {
-            s += partial[static_cast<long long>(k) * 2 * C + c];
-            q += partial[static_cast<long long>(k) * 2 * C + C + c];
         }
     }
     s_s[rl][cl] = s; s_q[rl][cl] = q;
