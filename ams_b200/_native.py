@@ -44,6 +44,7 @@ _SIGNATURES = {
     'ams_set_trainable': (_i, [_vp, _vp]),
     'ams_reset_optimizer': (_i, [_vp]),
     'ams_enqueue': (_i, [_vp, _vp, _i, _vp, _i]),
+    'ams_enqueue_raw': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i]),
     'ams_queue_size': (_i, [_vp]),
     'ams_infer': (_i, [_vp, _i, _vp]),
     'ams_infer_metric': (_i, [_vp, _i, _vp, _vp, C.POINTER(_f)]),
@@ -73,6 +74,7 @@ _SIGNATURES = {
     'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    'ams_op_resize_u8': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     'ams_op_depthwise_fused': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     'ams_op_depthwise_bwd_fused': (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'ams_op_depthwise_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

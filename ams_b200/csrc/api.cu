@@ -166,6 +166,8 @@ void ams_destroy(ams_net* h) {
         for (void* p : kv.second->allocations) cudaFree(p);
     }
     for (auto& q : net->slots) { if (q.frames) cudaFree(q.frames); if (q.labels) cudaFree(q.labels); if (q.consumed) cudaEventDestroy(q.consumed); }
+    if (net->raw_frames) cudaFree(net->raw_frames);
+    if (net->raw_labels) cudaFree(net->raw_labels);
     void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->before, net->delta_scratch, net->mask, net->moving,
                     net->bnpool, net->wpool, net->select_sc, net->head_st, net->cast_table, net->segs_dev, net->pack_bits,
                     net->pack_vals, net->pack_counts, net->pack_kept};
@@ -297,6 +299,54 @@ int ams_enqueue(ams_net* h, const void* frames, int dtype, const uint8_t* labels
     if (labels) AMS_CUDA_CHECK(cudaMemcpyAsync(q.labels, labels, px, cudaMemcpyHostToDevice, net->copy_stream));
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->copy_stream));
     q.n = n; q.dtype = dtype; q.has_labels = labels != nullptr;
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        net->filled.push_back(slot);
+    }
+    net->qcv.notify_all();
+    return 0;
+}
+int ams_enqueue_raw(ams_net* h, const uint8_t* frames, int src_h, int src_w, int bgr_to_rgb, const uint8_t* labels, int lab_h,
+                    int lab_w, int n) {
+    NET(h);
+    AMS_REQUIRE(frames && n > 0 && src_h > 0 && src_w > 0, "frames must be non-empty");
+    AMS_REQUIRE(!labels || (lab_h > 0 && lab_w > 0), "label size missing");
+    int slot = -1;
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        const bool got = net->qcv.wait_for(lk, std::chrono::seconds(60), [&] { return !net->free_slots.empty(); });
+        AMS_REQUIRE(got, "input queue stayed full for 60 s: nothing is consuming it (queue_capacity too small?)");
+        slot = net->free_slots.front();
+        net->free_slots.pop_front();
+    }
+    QueueSlot& q = net->slots[slot];
+    if (q.consumed_pending) { AMS_CUDA_CHECK(cudaEventSynchronize(q.consumed)); q.consumed_pending = false; }
+    const size_t px = static_cast<size_t>(n) * net->cfg.height * net->cfg.width;
+    if (ensure_slot(q, px * 3, px)) return -1;
+    const size_t fraw = static_cast<size_t>(n) * src_h * src_w * 3;
+    if (fraw > net->raw_frames_cap) {
+        if (net->raw_frames) cudaFree(net->raw_frames);
+        AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&net->raw_frames), fraw));
+        net->raw_frames_cap = fraw;
+    }
+    cudaStream_t cs = net->copy_stream;
+    AMS_CUDA_CHECK(cudaMemcpyAsync(net->raw_frames, frames, fraw, cudaMemcpyHostToDevice, cs));
+    // cv2.resize(frame, (W, H)) + cv2.cvtColor(BGR2RGB)  -- run.py:415-416
+    if (resize_u8(net->raw_frames, n, src_h, src_w, 3, static_cast<uint8_t*>(q.frames), net->cfg.height, net->cfg.width, 0,
+                  bgr_to_rgb ? 1 : 0, cs)) return -1;
+    if (labels) {
+        const size_t lraw = static_cast<size_t>(n) * lab_h * lab_w;
+        if (lraw > net->raw_labels_cap) {
+            if (net->raw_labels) cudaFree(net->raw_labels);
+            AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&net->raw_labels), lraw));
+            net->raw_labels_cap = lraw;
+        }
+        AMS_CUDA_CHECK(cudaMemcpyAsync(net->raw_labels, labels, lraw, cudaMemcpyHostToDevice, cs));
+        // cv2.resize(label, (W, H), interpolation=cv2.INTER_NEAREST)  -- run.py:183, :421
+        if (resize_u8(net->raw_labels, n, lab_h, lab_w, 1, q.labels, net->cfg.height, net->cfg.width, 1, 0, cs)) return -1;
+    }
+    AMS_CUDA_CHECK(cudaStreamSynchronize(cs));
+    q.n = n; q.dtype = AMS_FRAMES_U8; q.has_labels = labels != nullptr;
     {
         std::unique_lock<std::mutex> lk(net->qmu);
         net->filled.push_back(slot);
@@ -706,6 +756,12 @@ int ams_op_depthwise_fused(const void* in, const float* w, int n, int h, int w_,
     cudaStreamSynchronize(as_stream(stream));
     if (ws) cudaFree(ws);
     return rc;
+}
+
+int ams_op_resize_u8(const void* src, int n, int src_h, int src_w, int channels, void* dst, int dst_h, int dst_w, int nearest,
+                     int swap_rb, void* stream) {
+    return resize_u8(static_cast<const uint8_t*>(src), n, src_h, src_w, channels, static_cast<uint8_t*>(dst), dst_h, dst_w, nearest,
+                     swap_rb, as_stream(stream));
 }
 
 int ams_op_depthwise_bwd_fused(const void* g, const void* z, const float* scale, const float* shift, int act, const float* coef,

@@ -149,6 +149,10 @@ int head_loss_backward(const float* logits, const HeadGeom& g, const uint8_t* la
                        float* dlogits_f32, bf16* dlogits_bf16, HeadStats* st, float* loss_out /*device*/,
                        cudaStream_t s);
 
+// ---- frame ingest (ingest_kernels.cu): cv2.resize INTER_LINEAR / INTER_NEAREST on uint8, optional BGR<->RGB swap
+int resize_u8(const uint8_t* src, int n, int sh, int sw, int cn, uint8_t* dst, int dh, int dw, int nearest, int swap_rb,
+              cudaStream_t s);
+
 // ---- generic reductions
 // colsum[g][c] = sum over rows of group g (rows_per_group consecutive rows) of x[row][c]   (deterministic)
 int colsum_groups(const float* x_f32, const bf16* x_bf16, int ld, long long rows_per_group, int groups, int C,

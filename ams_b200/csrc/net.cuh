@@ -133,6 +133,8 @@ struct Net {
     std::mutex qmu; std::condition_variable qcv;
     std::vector<QueueSlot> slots; std::deque<int> filled; std::deque<int> free_slots;
     int last_n = 0;
+    // staging for ams_enqueue_raw (camera-size frames / label maps before the on-device resize), owned by the feeder thread
+    uint8_t* raw_frames = nullptr; size_t raw_frames_cap = 0; uint8_t* raw_labels = nullptr; size_t raw_labels_cap = 0;
     Profiler prof;
 };
 

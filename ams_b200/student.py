@@ -144,6 +144,21 @@ class Student:
         nat.check(self._L.ams_enqueue(self._h, _ptr(f), dt, _ptr(lab), frames.shape[0]), 'enqueue')
         return frames.shape[0]
 
+    def enqueue_raw(self, frames, labels=None, bgr=True):
+        """Camera-size uint8 frames [n,h,w,3] (BGR as decoded by cv2 when bgr=True) and optional teacher label maps
+        [n,lh,lw]: resized on the device exactly as the reference does on the host -- cv2.resize(frame, (W, H)) +
+        cv2.cvtColor(BGR2RGB), labels with INTER_NEAREST (run.py:181-183, :415-421) -- then queued like enqueue()."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert frames.ndim == 4 and frames.shape[3] == 3, frames.shape
+        lab, lh, lw = None, 0, 0
+        if labels is not None:
+            lab = np.ascontiguousarray(labels, dtype=np.uint8)
+            assert lab.ndim == 3 and lab.shape[0] == frames.shape[0], lab.shape
+            lh, lw = lab.shape[1:]
+        nat.check(self._L.ams_enqueue_raw(self._h, _ptr(frames), frames.shape[1], frames.shape[2], 1 if bgr else 0, _ptr(lab),
+                                          lh, lw, frames.shape[0]), 'enqueue_raw')
+        return frames.shape[0]
+
     def queue_size(self):
         return self._L.ams_queue_size(self._h)
 

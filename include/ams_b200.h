@@ -74,6 +74,13 @@ int ams_reset_optimizer(ams_net* net);
  * selected classes, e.g. 255, are ignored pixels), NULL = all-ignored (predict_input enqueues zeros, :178).
  * Copies before returning; callable concurrently with ams_train_step / ams_infer*. */
 int ams_enqueue(ams_net* net, const void* frames, int frames_dtype, const uint8_t* labels, int n);
+/* Frame ingest on the device: the reference resizes every camera frame on the host before feeding it --
+ * cv2.resize(frame, (W, H)) [INTER_LINEAR] + cv2.cvtColor(BGR2RGB) and, for teacher label maps,
+ * cv2.resize(label, (W, H), interpolation=cv2.INTER_NEAREST)  (run.py:181-183, :263-264, :415-421).
+ * frames: [n,src_h,src_w,3] u8 as decoded (BGR when bgr_to_rgb != 0); labels: [n,lab_h,lab_w] u8 or NULL.
+ * Results are bit-identical to OpenCV's uint8 paths; same queue semantics and threading rules as ams_enqueue. */
+int ams_enqueue_raw(ams_net* net, const uint8_t* frames, int src_h, int src_w, int bgr_to_rgb, const uint8_t* labels,
+                    int lab_h, int lab_w, int n);
 int ams_queue_size(ams_net* net);
 
 /* ---- inference on the oldest queued batch.
@@ -150,6 +157,10 @@ int ams_op_conv1x1(const void* a_bf16, const void* w_bf16 /*[N][K]*/, int M, int
 int ams_op_wgrad(const void* x_bf16, int cin, const void* dz_bf16, int cout, long long M, float* dw, void* stream);
 int ams_op_depthwise(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
                      const float* scale, const float* shift, int act, void* out_bf16, void* stream);
+/* cv2.resize on DEVICE buffers: [n,src_h,src_w,channels] u8 -> [n,dst_h,dst_w,channels]; nearest != 0: INTER_NEAREST
+ * (1 channel), else INTER_LINEAR (1 or 3 channels; swap_rb exchanges channels 0 and 2 on the way out) */
+int ams_op_resize_u8(const void* src, int n, int src_h, int src_w, int channels, void* dst, int dst_h, int dst_w, int nearest,
+                     int swap_rb, void* stream);
 /* tiled depthwise with the producer's BN+act applied while staging the input (in_scale/in_shift may be NULL) and the
  * batch statistics of the stored output: stats_out[2][c] fp64 DEVICE = column sums (sum, sum of squares) */
 int ams_op_depthwise_fused(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,

@@ -180,3 +180,30 @@ def test_teacher_forcing_is_value_neutral():
     l1, g1, _, _ = ts.loss_and_grads(fr, lab, np.arange(19))
     l2, g2, _, _ = ts.loss_and_grads(fr, lab, np.arange(19), forced=forced)
     assert l1 == l2 and all(np.array_equal(g1[k], g2[k]) for k in g1)
+
+
+# ----------------------------------------------------------------------------- frame ingest (cv2.resize) oracle
+def test_resize_oracle_matches_cv2_golden_vectors():
+    """The ingest oracle against outputs of OpenCV itself (tests/golden/resize_golden.npz, generated here by
+    oracle/make_resize_golden.py): INTER_LINEAR uint8 and INTER_NEAREST, bit for bit."""
+    import cv2_resize_oracle as ro
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'resize_golden.npz'))
+    i = 0
+    while 'src_%d' % i in g:
+        dh, dw = g['linear_%d' % i].shape[:2]
+        assert np.array_equal(ro.resize_linear_u8(g['src_%d' % i], dw, dh), g['linear_%d' % i]), i
+        assert np.array_equal(ro.resize_nearest_u8(g['lab_%d' % i], dw, dh), g['nearest_%d' % i]), i
+        i += 1
+    assert i >= 7
+
+
+def test_resize_oracle_matches_cv2_live_when_available():
+    cv2 = pytest.importorskip('cv2')
+    import cv2_resize_oracle as ro
+    rng = np.random.default_rng(11)
+    for (sh, sw, dh, dw) in [(270, 480, 128, 256), (120, 213, 128, 256), (256, 512, 128, 256), (97, 61, 40, 33), (30, 40, 64, 128)]:
+        img = rng.integers(0, 256, size=(sh, sw, 3), dtype=np.uint8)
+        lab = rng.integers(0, 19, size=(sh, sw), dtype=np.uint8)
+        assert np.array_equal(ro.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), (sh, sw, dh, dw)
+        assert np.array_equal(ro.resize_nearest_u8(lab, dw, dh), cv2.resize(lab, (dw, dh), interpolation=cv2.INTER_NEAREST))
+        assert np.array_equal(ro.ingest_frame(img, dh, dw), cv2.cvtColor(cv2.resize(img, (dw, dh)), cv2.COLOR_BGR2RGB))
