@@ -285,6 +285,48 @@ def run_ours(args, rank, world, local_rank):
         ms, ms_e2e = float(t[0]), float(t[1])
     mark('max over ranks done')
 
+    # ---- secondary (config C3): 8 camera streams of 1080p frames sharded by stream over the ranks (no communication);
+    # per iteration one frame per local stream: H2D of the raw frames, cv2-exact resize + BGR->RGB on the device
+    # (feeder thread, copy stream), frozen inference, argmax + confusion matrix, D2H of the label maps
+    streams_total = 8
+    n_local = max(1, streams_total // world)
+    T_STREAM = 12
+    raw = []
+    for i in range(2):
+        rt, ra = pinned((n_local, 1080, 1920, 3), torch.uint8)
+        ra[...] = np.random.default_rng(1000 + 10 * rank + i).integers(0, 256, size=ra.shape, dtype=np.uint8)
+        lt, la = pinned((n_local, 1080, 1920), torch.uint8)
+        la[...] = synthetic_labels(n_local, 1080, 1920, seed=200 + rank + i, block=64)
+        raw.append((rt, ra, lt, la))
+    for i in range(3):
+        st.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
+        st.infer_metric(n_local, nat.BN_MOVING)
+
+    def feed_streams():
+        for i in range(T_STREAM):
+            st.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_w0 = time.time()
+    s0.record(stream)
+    fth = threading.Thread(target=feed_streams, daemon=True)
+    fth.start()
+    for i in range(T_STREAM):
+        st.infer_metric(n_local, nat.BN_MOVING)
+    s1.record(stream)
+    fth.join()
+    barrier()
+    ms_streams = max(s0.elapsed_time(s1), 1000.0 * (time.time() - t_w0))
+    if world > 1:
+        t = torch.tensor([ms_streams], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_streams = float(t[0])
+    infer_streams = {'frames_per_sec': T_STREAM * n_local * world / (ms_streams / 1000.0), 'streams': n_local * world,
+                     'frames_per_stream': T_STREAM, 'source': '1080x1920 u8 BGR frames + 1080p teacher label maps (pinned host)',
+                     'includes': 'H2D, on-device cv2-exact resize to 512x1024 + BGR->RGB, frozen inference, argmax, '
+                                 'per-batch confusion matrix, D2H of int32 label maps'}
+    mark('stream-sharded inference done')
+
     # ---- per-kernel-group device times (separate short pass so the events do not perturb the numbers above)
     prof = None
     infer = None
@@ -360,6 +402,7 @@ def run_ours(args, rank, world, local_rank):
                          'kernel_groups_ms_per_step': {k: round(v['ms'] / 3, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])},
                          'kernel_groups_gbs': {k: round(v['algo_bytes'] / (v['ms'] * 1e-3) / 1e9, 1) for k, v in prof.items() if v['ms'] > 0}},
             'infer': infer,
+            'infer_streams': infer_streams,
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
