@@ -279,6 +279,17 @@ class SemanticNetwork(object):
         per variable np.packbits(mask), then per variable params[mask].astype(float16)."""
         return self.student.pack_delta()
 
+    def apply_delta(self, blob):
+        """Client side of the model stream (an extension: the reference rebuilds a TF session from a whole frozen graph
+        at every update, run.py:401-411, and only SIZES the delta file): applies the bytes of delta_bytes() /
+        `<save_dir>_mask.dat` to the resident model; returns the number of updated coordinates.  BatchNorm moving
+        statistics are not in the delta -- the client keeps the ones of its last full hand-off."""
+        self.process_lock.acquire()
+        try:
+            return self.student.apply_delta(blob)
+        finally:
+            self.process_lock.release()
+
     def get_train_mask(self, train_strategy):
         names = self.student.trainable_names
         shapes = self.student.var_shapes

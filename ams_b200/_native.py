@@ -58,6 +58,7 @@ _SIGNATURES = {
     'ams_train_forward_backward': (_i, [_vp, C.POINTER(_ll), C.POINTER(_d)]),
     'ams_gradient_arena': (_vp, [_vp, C.POINTER(_ll)]),
     'ams_apply_optimizer': (_i, [_vp, _f, _i, _f]),
+    'ams_apply_delta': (_i, [_vp, _vp, _ll, C.POINTER(_ll)]),
     'ams_get_logits': (_i, [_vp, _vp, _ll]),
     'ams_get_gradients': (_i, [_vp, _vp]),
     'ams_num_layers': (_i, [_vp]),

@@ -571,6 +571,29 @@ int ams_pack_delta(ams_net* h, uint8_t* out, long long cap, long long* out_len) 
     return 0;
 }
 
+int ams_apply_delta(ams_net* h, const uint8_t* blob, long long len, long long* out_updated) {
+    NET(h);
+    AMS_REQUIRE(blob && len >= net->mask_bytes, "delta shorter than its mask section");
+    const int nblocks = pack_delta_blocks(net->n_train);
+    AMS_CUDA_CHECK(cudaMemcpyAsync(net->pack_bits, blob, net->mask_bytes, cudaMemcpyHostToDevice, net->stream));
+    if (unpack_delta_mask(net->pack_bits, net->segs_dev, static_cast<int>(net->trainable_order.size()), net->n_train, net->mask_bytes,
+                          net->mask, net->pack_counts, nblocks, net->pack_kept, net->stream)) return -1;
+    unsigned long long kept = 0;
+    AMS_CUDA_CHECK(cudaMemcpyAsync(&kept, net->pack_kept, sizeof(kept), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->mask_all_ones = false;
+    AMS_REQUIRE(len == net->mask_bytes + 2 * static_cast<long long>(kept), "delta length does not match its mask (" +
+                std::to_string(len) + " bytes for " + std::to_string(kept) + " selected coordinates)");
+    if (kept) {
+        AMS_CUDA_CHECK(cudaMemcpyAsync(net->pack_vals, blob + net->mask_bytes, 2 * kept, cudaMemcpyHostToDevice, net->stream));
+        if (unpack_delta_values(net->params, net->mask, net->n_train, net->pack_counts, nblocks, net->pack_vals, net->stream)) return -1;
+        AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    }
+    net->weights_dirty = true; net->fold_dirty = true;
+    if (out_updated) *out_updated = static_cast<long long>(kept);
+    return 0;
+}
+
 int ams_get_logits(ams_net* h, float* host, long long count) {
     NET(h);
     auto it = net->plans.find(net->last_n);

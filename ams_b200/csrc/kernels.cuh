@@ -179,6 +179,11 @@ int pack_delta(const float* params, const uint8_t* mask, const VarSeg* segs_dev,
                long long mask_bytes, uint8_t* out_bits, __half* out_vals, unsigned int* block_counts,
                int nblocks_alloc, unsigned long long* kept_out, cudaStream_t s);
 int pack_delta_blocks(long long n);
+// inverse (client side): bits -> byte mask (+ per-block offsets and the kept count), then fp16 values -> params[mask]
+int unpack_delta_mask(const uint8_t* bits, const VarSeg* segs_dev, int nseg, long long n, long long mask_bytes, uint8_t* mask,
+                      unsigned int* block_counts, int nblocks, unsigned long long* kept_out, cudaStream_t s);
+int unpack_delta_values(float* params, const uint8_t* mask, long long n, const unsigned int* block_offsets, int nblocks,
+                        const __half* vals, cudaStream_t s);
 
 // fp32 HWIO 1x1 weights -> bf16 [Cout][Cin] (forward B operand) and bf16 [Cin][ldb] (dgrad B operand)
 struct WeightCast { const float* w; bf16* w_fwd; bf16* w_bwd; int Cin, Cout, ld_fwd, ld_bwd; int row0, rows; };

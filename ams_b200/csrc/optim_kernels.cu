@@ -256,6 +256,68 @@ int pack_delta(const float* params, const uint8_t* mask, const VarSeg* segs_dev,
     return 0;
 }
 
+// ---- inverse of pack_delta: the client side of the model stream (the reference only SIZES the delta, run.py:316-336)
+__global__ void __launch_bounds__(256)
+unpack_bits_kernel(const uint8_t* __restrict__ bits, const VarSeg* __restrict__ segs, int nseg, long long total_bytes,
+                   uint8_t* __restrict__ mask) {
+    pdl_entry();
+    const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= total_bytes) return;
+    int lo = 0, hi = nseg - 1;                       // last segment with bit_byte_offset <= b
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].bit_byte_offset <= b) lo = mid; else hi = mid - 1;
+    }
+    const VarSeg s = segs[lo];
+    const long long e0 = (b - s.bit_byte_offset) * 8;
+    const unsigned int byte = bits[b];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const long long e = e0 + k;
+        if (e < s.size) mask[s.offset + e] = (byte >> (7 - k)) & 1u;      // np.unpackbits: big-endian bit order
+    }
+}
+__global__ void __launch_bounds__(256)
+unpack_scatter_kernel(float* __restrict__ params, const uint8_t* __restrict__ mask, long long n,
+                      const unsigned int* __restrict__ offsets, const __half* __restrict__ vals) {
+    pdl_entry();
+    __shared__ unsigned int s_w[8];
+    const long long base = static_cast<long long>(blockIdx.x) * kPackBlock;
+    bool keep[4]; unsigned int c = 0;
+    for (int k = 0; k < 4; ++k) {
+        const long long i = base + threadIdx.x * 4 + k;
+        keep[k] = (i < n) && mask[i];
+        c += keep[k];
+    }
+    unsigned int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    unsigned int wbase = 0;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) wbase += s_w[w];
+    unsigned int pos = offsets[blockIdx.x] + wbase + inc - c;
+    for (int k = 0; k < 4; ++k) {
+        if (keep[k]) params[base + threadIdx.x * 4 + k] = __half2float(vals[pos++]);
+    }
+}
+
+int unpack_delta_mask(const uint8_t* bits, const VarSeg* segs_dev, int nseg, long long n, long long mask_bytes, uint8_t* mask,
+                      unsigned int* block_counts, int nblocks, unsigned long long* kept_out, cudaStream_t s) {
+    AMS_LAUNCH((unpack_bits_kernel), static_cast<int>(ceil_div_ll(mask_bytes, 256)), 256, 0, s, bits, segs_dev, nseg, mask_bytes, mask);
+    AMS_LAUNCH((pack_count_kernel), nblocks, 256, 0, s, mask, n, block_counts);
+    AMS_LAUNCH((pack_scan_kernel), 1, 32, 0, s, block_counts, nblocks, kept_out);
+    return 0;
+}
+int unpack_delta_values(float* params, const uint8_t* mask, long long n, const unsigned int* block_offsets, int nblocks,
+                        const __half* vals, cudaStream_t s) {
+    AMS_LAUNCH((unpack_scatter_kernel), nblocks, 256, 0, s, params, mask, n, block_offsets, vals);
+    return 0;
+}
+
 int cast_weights(const WeightCast* table_dev, int n_layers, int max_elems, cudaStream_t s) {
     dim3 grid(ceil_div(max_elems, 256), n_layers);
     AMS_LAUNCH((cast_weights_kernel), grid, 256, 0, s, table_dev);

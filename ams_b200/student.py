@@ -224,6 +224,14 @@ class Student:
         return buf.tobytes()
 
     # ------------------------------------------------------------------ data-parallel hooks
+    def apply_delta(self, blob):
+        """Client side: apply a delta produced by pack_delta() to the resident parameters; returns the number of updated
+        coordinates."""
+        buf = np.frombuffer(bytes(blob), dtype=np.uint8)
+        n = C.c_longlong()
+        nat.check(self._L.ams_apply_delta(self._h, _ptr(buf), len(buf), C.byref(n)), 'apply_delta')
+        return int(n.value)
+
     def train_forward_backward(self):
         nv, ls = C.c_longlong(), C.c_double()
         nat.check(self._L.ams_train_forward_backward(self._h, C.byref(nv), C.byref(ls)), 'train_forward_backward')

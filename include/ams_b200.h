@@ -111,6 +111,11 @@ int ams_select_topk(ams_net* net, double coord_frac, long long* out_kept, float*
 /* model delta wire format -- run.py:316-328: per variable np.packbits(mask), then per variable
  * params[mask].astype(float16).  Returns the byte length (and fills out_buf when capacity suffices). */
 int ams_pack_delta(ams_net* net, uint8_t* out_buf, long long capacity, long long* out_len);
+/* Client side of the model stream (the reference only sizes the delta file, run.py:316-336, and
+ * ships a whole frozen graph per update, :339, :401-411): applies a delta produced by ams_pack_delta to the resident
+ * parameters -- coordinates whose mask bit is set take the fp16 value (widened to fp32), all others are untouched.
+ * BatchNorm moving statistics are not part of the delta.  The handle's mask becomes the delta's mask. */
+int ams_apply_delta(ams_net* net, const uint8_t* delta, long long length, long long* out_updated);
 
 /* ---- data-parallel hooks (no reference counterpart: the reference is single-GPU) */
 /* forward+backward only; gradients stay in the device gradient arena as sums over the LOCAL valid pixels

@@ -101,3 +101,22 @@ def test_synthetic_checkpoint_layout():
 def test_low_res_and_colormap():
     assert (_low_res(512), _low_res(1024), _low_res(256)) == (33, 65, 17)
     assert colormap().shape == (256, 3) and list(colormap()[13]) == [0, 0, 142]
+
+
+def test_oracle_delta_pack_apply_round_trip():
+    """pack_delta -> apply_delta is the identity on the mask and an fp16 round trip on the selected values; everything
+    else keeps the receiver's value (the client side of the model stream)."""
+    import numpy as np
+    import student_oracle as so
+    rng = np.random.default_rng(3)
+    shapes = [(3, 3, 3, 32), (32,), (1, 1, 32, 16), (16,), (7,), (1, 1, 5, 3)]
+    server = [rng.normal(size=s).astype(np.float32) for s in shapes]
+    client = [rng.normal(size=s).astype(np.float32) for s in shapes]
+    masks = [rng.random(size=s) < 0.3 for s in shapes]
+    blob = so.pack_delta(masks, server)
+    new, got_masks = so.apply_delta(client, blob)
+    for m, g, s_, c, n in zip(masks, got_masks, server, client, new):
+        assert np.array_equal(m, g)
+        assert np.array_equal(n[m], s_[m].astype(np.float16).astype(np.float32))
+        assert np.array_equal(n[~m], c[~m])
+    assert len(blob) == sum((m.size + 7) // 8 for m in masks) + 2 * sum(int(m.sum()) for m in masks)

@@ -289,6 +289,41 @@ def test_selection_and_delta_bit_exact():
     st.close()
 
 
+def test_client_applies_streamed_delta_bit_exact():
+    """Server: two masked steps + 5 % selection + pack_delta.  Client (another handle holding the pre-phase checkpoint):
+    ams_apply_delta.  The client's parameters equal the oracle's apply_delta bit for bit, i.e. the server's values through
+    fp16 on the selected coordinates and the old values elsewhere; a truncated delta is rejected."""
+    spec, V, fr = make_checkpoint()
+    labels = so.synthetic_labels(N, H, W, seed=2, block=16)
+    server = load_student(spec, V, list(range(19)))
+    names = server.trainable_names
+    server.snapshot_before()
+    server.enqueue(fr, labels)
+    server.train_step(1e-3, masked=True)
+    server.select_topk(0.05)
+    server.enqueue(fr, labels)
+    server.train_step(1e-3, masked=True)
+    blob = server.pack_delta()
+    after = server.split_trainable(server.get_trainable_flat())
+    client = load_student(spec, V, list(range(19)))
+    before = client.split_trainable(client.get_trainable_flat())
+    updated = client.apply_delta(blob)
+    got = client.split_trainable(client.get_trainable_flat())
+    ref, masks = so.apply_delta([before[n_] for n_ in names], blob)
+    assert updated == sum(int(m.sum()) for m in masks)
+    for n_, r, m in zip(names, ref, masks):
+        assert np.array_equal(got[n_], r), n_
+        assert np.array_equal(got[n_][m], after[n_][m].astype(np.float16).astype(np.float32)), n_
+    client.enqueue(fr, labels)
+    pred, cm, _ = client.infer_metric(N, nat.BN_MOVING)                      # the updated client runs
+    assert pred.shape == (N, H, W) and cm.sum() > 0
+    with pytest.raises(nat.NativeError):
+        client.apply_delta(blob[:-2])
+    log('client delta apply: %d coordinates updated from %d bytes, bit-exact vs the oracle' % (updated, len(blob)))
+    server.close()
+    client.close()
+
+
 def test_voc_graph_runs_and_matches_layout():
     spec, V, fr = make_checkpoint('pascalvoc2012')
     st = load_student(spec, V)
