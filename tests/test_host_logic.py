@@ -120,3 +120,33 @@ def test_oracle_delta_pack_apply_round_trip():
         assert np.array_equal(n[m], s_[m].astype(np.float16).astype(np.float32))
         assert np.array_equal(n[~m], c[~m])
     assert len(blob) == sum((m.size + 7) // 8 for m in masks) + 2 * sum(int(m.sum()) for m in masks)
+
+
+def test_orchestration_controllers_follow_run_py():
+    """ASR / ATR / scheduling arithmetic of the reference's server loop (run.py:279-308, :593-598)."""
+    import numpy as np
+    from ams_b200 import run
+    # ASR: phi above 0.6 lowers the send rate by up to 0.2 per phase, clipped to [0.1, 1]
+    assert abs(run.asr_update(0.5, [0.6]) - 0.5) < 1e-12
+    assert abs(run.asr_update(0.5, [0.9, 0.9]) - (0.5 - 0.2 * np.tanh(6.0))) < 1e-12
+    assert run.asr_update(0.15, [1.0]) == 0.1 and run.asr_update(0.95, [0.0]) == 1.0
+    # ATR: hibernate below 0.25, grow by 2 s up to 6x, wake above 0.35 and reset
+    hib, period = run.atr_update(False, 10, 10, [0.2, 0.2])
+    assert hib and period == 12
+    for _ in range(40):
+        hib, period = run.atr_update(hib, period, 10, [0.2])
+    assert hib and period == 60
+    hib, period = run.atr_update(hib, period, 10, [0.3])            # between the thresholds: keeps hibernating
+    assert hib and period == 60
+    hib, period = run.atr_update(hib, period, 10, [0.5])
+    assert not hib and period == 10
+    assert run.reschedule([0, 10, 20, 30, 40], 20, 60, 12) == [0, 10, 20, 32, 44, 56]
+    ev = run.simple_event_list(300, 10, 250, False)
+    assert ev[:3] == [0, 100, 110] and ev[-1] == 290
+    assert run.simple_event_list(300, 10, 250, True) == [0, 250, 260, 270, 280, 290]
+    a, b = run.SyntheticSource(64, 128, fps=2), run.SyntheticSource(64, 128, fps=2)
+    a.seek(5); b.seek(5)
+    fa, ga = a.read(); fb, gb = b.read()
+    assert np.array_equal(fa, fb) and np.array_equal(ga, gb) and fa.shape == (64, 128, 3) and ga.dtype == np.uint8
+    f = run.parse_flags(['--mode', 'simple', '--height', '64', '--enable_ASR'])
+    assert f.mode == 'simple' and f.height == 64 and f.enable_ASR and not f.enable_ATR and f.iter == 200

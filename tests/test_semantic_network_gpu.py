@@ -103,3 +103,49 @@ def test_facade_end_to_end(tmp_path):
         SemanticNetwork(meta_dir=out + '_tf', class_weights_exp=cw, height=H, frozen=True)
     client.close_model()
     net.close_model()
+
+
+def test_orchestration_server_and_client_on_synthetic_video(tmp_path):
+    """ams_b200.run: the reference's server loop (sampling, memory, phases, ASR, delta accounting, hand-off) and client
+    loop (scheduled model loads, per-frame mIoU) on a synthetic camera; the delta file equals the host writer of
+    run.py:316-328 byte for byte and a client that applies it holds the server's fp16-rounded coordinates."""
+    pytest.importorskip('cv2')
+    from ams_b200 import run
+    spec, V, frames, prefix = _checkpoint(tmp_path)
+    flags = run.default_flags()
+    flags.output_dir = os.path.join(str(tmp_path), 'out') + os.sep
+    os.makedirs(flags.output_dir)
+    flags.student_checkpoint = prefix
+    flags.input_video = 'synthetic-0.mp4'
+    flags.height, flags.batch_size, flags.iter, flags.memory_len = H, 2, 3, 8
+    flags.train_strategy, flags.coord_fraction, flags.enable_ASR = 'coord_desc_auto', '0.05', True
+    logs = []
+    src = run.SyntheticSource(90, 160, fps=2, seed=1)
+    out = run.train_model(flags, src, 0, 12, 1, '0', 'syn', 12, [0, 4, 8], 1, log=logs.append)
+    assert out['update_count'] == 2 and out['model_update_times'] == [0, 4.0, 8.0]
+    assert len(out['samples']) == 12 and sum(out['samples']) > 0 and all(b > 0 for b in out['downlink_bits'])
+    assert any('Send rate updated' in l for l in logs)
+    final = run.get_save_dir(flags, 'syn_results')
+    for suffix in ('_fps_client.npy', '_bw_uplink.npy', '_bw_downlink.npy', '_model_update_times.npy', '_update.txt'):
+        assert os.path.exists(final + suffix), suffix
+    down, up, count, interval, sent = [int(x) for x in open(final + '_update.txt').read().split()]
+    assert (count, interval, sent) == (2, 12, sum(out['samples'])) and down == sum(out['downlink_bits'])
+    # the delta file of the first update: packbits masks then fp16 values, as run.py writes it from curr_mask / train_params
+    t, blob = out['deltas'][0]
+    path = run.get_save_dir(flags, 'syn_0') + '_mask.dat'
+    assert open(path, 'rb').read() == blob and os.path.exists(path + '.gz')
+    # client: loads the model in force at each second, predicts every frame
+    res = run.infer_output(flags, run.SyntheticSource(90, 160, fps=2, seed=1), 0, 12, '0', 'syn', 12, [0, 4, 8], log=logs.append)
+    assert len(res['miou']) == 24 and np.isfinite(res['loss']).all() and len(res['miou_mem']) == 24
+    assert os.path.exists(final + '_mious.npy') and os.path.exists(final + '_mioucats.npy')
+    # in-place update of a resident client from the streamed bytes == the server's coordinates through fp16
+    cw = class_weights(12)
+    client = SemanticNetwork(meta_dir=run.get_save_dir(flags, 'syn_0') + '_final', class_weights_exp=cw, height=H, gpu_id='0', frozen=True)
+    before = client.student.split_trainable(client.student.get_trainable_flat())
+    n_upd = client.apply_delta(blob)
+    after = client.student.split_trainable(client.student.get_trainable_flat())
+    ref, masks = so.apply_delta([before[n] for n in client.student.trainable_names], blob)
+    assert n_upd == sum(int(m.sum()) for m in masks) > 0
+    for n, r in zip(client.student.trainable_names, ref):
+        assert np.array_equal(after[n], r), n
+    client.close_model()
