@@ -682,9 +682,18 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
             const int n0 = co_tile * p.block_n + c0;
             if (ci < p.Cin) {
+                if (n0 + 16 <= p.Cout && (reinterpret_cast<uintptr_t>(o + n0) & 15) == 0) {
+                    // 64 contiguous bytes per thread: four 128-bit stores (two full sectors) instead of 16 scalar ones
+                    float4* o4 = reinterpret_cast<float4*>(o + n0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (n0 + j < p.Cout) o[n0 + j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 4; ++j)
+                        o4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                            __uint_as_float(r[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < p.Cout) o[n0 + j] = __uint_as_float(r[j]);
+                }
             }
         }
     }
@@ -710,6 +719,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int Ci
     const int s0 = warp_per_item ? lane : 0, ds = warp_per_item ? 32 : 1;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if ((Cout & 3) == 0) {
+#pragma unroll 8
         for (int s = s0; s < splits; s += ds) {
             const float4 v = *reinterpret_cast<const float4*>(ws + s * split_stride + i4);
             acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
