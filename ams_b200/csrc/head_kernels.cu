@@ -46,6 +46,7 @@ __device__ __forceinline__ void warp_agg_hist(int* s_hist, int bin, bool active)
 
 // block = 256 threads = 256 consecutive x; each thread walks RY rows
 constexpr int kRY = 16;
+template <int CM>      // class slots held in registers: 8 / 16 / 21 (loops over unused slots would still cost issue slots)
 __global__ void __launch_bounds__(256)
 head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ HeadConst g,
                   const uint8_t* __restrict__ labels, int32_t* __restrict__ pred, HeadStats* __restrict__ st) {
@@ -67,7 +68,7 @@ head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ Head
     int xlo = 0, xhi = 0; float xl = 0.f;
     src_index(x_ok ? x : 0, g.sx, g.w, xlo, xhi, xl);
     const float* base = logits + static_cast<long long>(n) * g.h * g.w * g.ldl;
-    float top[kMaxC], bot[kMaxC];
+    float top[CM], bot[CM];
     int cur_lo = -1, cur_hi = -1;
     double loss_acc = 0.0; int valid_acc = 0;
     for (int y = y0; y < min(y0 + kRY, g.H); ++y) {
@@ -78,7 +79,7 @@ head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ Head
             const float* rt = base + static_cast<long long>(ylo) * g.w * g.ldl;
             const float* rbp = base + static_cast<long long>(yhi) * g.w * g.ldl;
 #pragma unroll
-            for (int c = 0; c < kMaxC; ++c) {
+            for (int c = 0; c < CM; ++c) {
                 if (c < g.cc) {
                     const int ch = g.cls[c];
                     top[c] = lerp_rn(__ldg(rt + xlo * g.ldl + ch), __ldg(rt + xhi * g.ldl + ch), xl);
@@ -87,9 +88,9 @@ head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ Head
             }
         }
         float best = 0.f; int arg = 0;
-        float v[kMaxC];
+        float v[CM];
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
+        for (int c = 0; c < CM; ++c) {
             if (c < g.cc) {
                 v[c] = lerp_rn(top[c], bot[c], yl);
                 if (c == 0 || v[c] > best) { best = v[c]; arg = c; }
@@ -105,7 +106,7 @@ head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ Head
             if (valid) {
                 float sum = 0.f, picked = 0.f;
 #pragma unroll
-                for (int c = 0; c < kMaxC; ++c) {
+                for (int c = 0; c < CM; ++c) {
                     if (c < g.cc) {
                         sum += expf(v[c] - best);
                         if (c == lab) picked = v[c];
@@ -162,12 +163,15 @@ label_confmat_kernel(const uint8_t* __restrict__ before, const uint8_t* __restri
 // ------------------------------------------------------------------------------------------ training head
 // pass 1: one block per output row (n, y).  g[x][c] = softmax - onehot at valid pixels (else 0);
 //         rowbuf[n][y][ix][c] = sum_x wx(x, ix) * g[x][c];  row_loss / row_valid partials.
+template <int CM>
 __global__ void __launch_bounds__(256)
 head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadConst g,
                  const uint8_t* __restrict__ labels, float* __restrict__ rowbuf, double* __restrict__ row_loss,
                  int* __restrict__ row_valid) {
     pdl_entry();
-    extern __shared__ float s_g[];                 // [W][cc]
+    extern __shared__ float s_g[];                 // [W][cc], then the per-x source taps: int xlo[W], float xl[W]
+    int* s_xlo = reinterpret_cast<int*>(s_g + static_cast<size_t>(g.W) * g.cc);
+    float* s_xl = reinterpret_cast<float*>(s_xlo + g.W);
     __shared__ int s_lut[256];
     __shared__ double s_loss[8];
     __shared__ int s_valid[8];
@@ -183,16 +187,18 @@ head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadC
     for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
         const int lab = s_lut[labels[(static_cast<long long>(n) * g.H + y) * g.W + x]];
         float* gx = s_g + x * g.cc;
+        int xlo, xhi; float xl;
+        src_index(x, g.sx, g.w, xlo, xhi, xl);
+        s_xlo[x] = xlo | (xhi << 16);
+        s_xl[x] = xl;
         if (lab < 0) {
             for (int c = 0; c < g.cc; ++c) gx[c] = 0.f;
             continue;
         }
-        int xlo, xhi; float xl;
-        src_index(x, g.sx, g.w, xlo, xhi, xl);
-        float v[kMaxC];
+        float v[CM];
         float best = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
+        for (int c = 0; c < CM; ++c) {
             if (c < g.cc) {
                 const int ch = g.cls[c];
                 const float t = lerp_rn(__ldg(rt + xlo * g.ldl + ch), __ldg(rt + xhi * g.ldl + ch), xl);
@@ -203,7 +209,7 @@ head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadC
         }
         float sum = 0.f, picked = 0.f;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
+        for (int c = 0; c < CM; ++c) {
             if (c < g.cc) {
                 v[c] = expf(v[c] - best);
                 sum += v[c];
@@ -211,7 +217,7 @@ head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadC
         }
         const float inv = 1.f / sum;
 #pragma unroll
-        for (int c = 0; c < kMaxC; ++c) {
+        for (int c = 0; c < CM; ++c) {
             if (c < g.cc) {
                 const float p = v[c] * inv;
                 if (c == lab) picked = p;
@@ -239,8 +245,9 @@ head_rows_kernel(const float* __restrict__ logits, const __grid_constant__ HeadC
         xa = max(xa, 0); xb = min(xb, g.W - 1);
         float acc = 0.f;
         for (int x = xa; x <= xb; ++x) {
-            int xlo, xhi; float xl;
-            src_index(x, g.sx, g.w, xlo, xhi, xl);
+            const int packed = s_xlo[x];
+            const int xlo = packed & 0xffff, xhi = packed >> 16;
+            const float xl = s_xl[x];
             float wgt = 0.f;
             if (xlo == ix) wgt += 1.f - xl;
             if (xhi == ix) wgt += xl;
@@ -338,7 +345,9 @@ int head_infer(const float* logits, const HeadGeom& g, const uint8_t* labels, in
     HeadConst c;
     if (make_const(g, &c)) return -1;
     dim3 grid(ceil_div(g.W, 256), ceil_div(g.H, kRY), g.N);
-    AMS_LAUNCH((head_infer_kernel), grid, 256, 0, s, logits, c, labels, pred, st);
+    if (g.class_count <= 8) AMS_LAUNCH((head_infer_kernel<8>), grid, 256, 0, s, logits, c, labels, pred, st);
+    else if (g.class_count <= 16) AMS_LAUNCH((head_infer_kernel<16>), grid, 256, 0, s, logits, c, labels, pred, st);
+    else AMS_LAUNCH((head_infer_kernel<kMaxC>), grid, 256, 0, s, logits, c, labels, pred, st);
     return 0;
 }
 
@@ -369,14 +378,18 @@ int head_loss_backward(const float* logits, const HeadGeom& g, const uint8_t* la
     off = (off + 1) & ~size_t(1);                                  // 8-byte align the doubles
     double* row_loss = reinterpret_cast<double*>(rowbuf + off);
     int* row_valid = reinterpret_cast<int*>(row_loss + rows);
-    const size_t smem = static_cast<size_t>(g.W) * g.class_count * sizeof(float);
+    const size_t smem = static_cast<size_t>(g.W) * (g.class_count + 2) * sizeof(float);     // gradients + cached x taps
+    AMS_REQUIRE(smem <= 200 * 1024 && g.w < 65536, "row too wide for the head kernel");
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        AMS_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(head_rows_kernel<kMaxC>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         smem_set = smem;
     }
-    AMS_REQUIRE(smem <= 200 * 1024, "row too wide for the head kernel");
-    AMS_LAUNCH((head_rows_kernel), static_cast<int>(rows), 256, smem, s, logits, c, labels, rowbuf, row_loss, row_valid);
+    if (g.class_count <= 8) AMS_LAUNCH((head_rows_kernel<8>), static_cast<int>(rows), 256, smem, s, logits, c, labels, rowbuf, row_loss, row_valid);
+    else if (g.class_count <= 16) AMS_LAUNCH((head_rows_kernel<16>), static_cast<int>(rows), 256, smem, s, logits, c, labels, rowbuf, row_loss, row_valid);
+    else AMS_LAUNCH((head_rows_kernel<kMaxC>), static_cast<int>(rows), 256, smem, s, logits, c, labels, rowbuf, row_loss, row_valid);
     AMS_LAUNCH((head_finalize_kernel), 1, 256, 0, s, row_loss, row_valid, static_cast<int>(rows), st, loss_out);
     const long long total = static_cast<long long>(g.N) * g.h * g.w * g.ldl;
     AMS_LAUNCH((head_cols_kernel), static_cast<int>(ceil_div_ll(total, 256)), 256, 0, s, rowbuf, c, st, dl_f32, dl_bf16);
