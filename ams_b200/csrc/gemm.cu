@@ -857,7 +857,8 @@ static void wgrad_shape(int Cin, int Cout, long long M, int num_sms, int* ci_til
     *boxes_b = ceil_div(bn, 64);
     *k_blocks = int(ceil_div_ll(M, BLOCK_K));
     const int tiles = (*ci_tiles) * (*co_tiles);
-    int want = std::max(1, num_sms / tiles);               // about one CTA per SM: fewer, longer split-K runs
+    static const int wg_mult = [] { const char* e = getenv("AMS_WGRAD_CTAS_PER_SM"); return e ? atoi(e) : 1; }();
+    int want = std::max(1, wg_mult * num_sms / tiles);     // about one CTA per SM: fewer, longer split-K runs
     int max_splits = std::max(1, *k_blocks / 8);           // at least 8 k-blocks (512 pixels) per CTA
     int s = std::min(want, max_splits);
     *kb_per_split = ceil_div(*k_blocks, s);
