@@ -264,7 +264,8 @@ DwTile pick_tile(const Conv2dGeom& g, size_t smem_cap) {
     return best;
 }
 
-constexpr size_t kFwdSmemCap = 72 * 1024;
+static size_t env_kb(const char* name, size_t dflt_kb) { const char* e = getenv(name); return (e ? size_t(atoi(e)) : dflt_kb) * 1024; }
+static const size_t kFwdSmemCap = env_kb("AMS_DWF_SMEM_KB", 72);
 
 template <int S, int D, int CB>
 int launch_fwd(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
@@ -611,7 +612,7 @@ DwBwdTile pick_bwd_tile(const Conv2dGeom& g, size_t smem_cap) {
     return best;
 }
 
-constexpr size_t kBwdSmemCap = 100 * 1024;
+static const size_t kBwdSmemCap = env_kb("AMS_DWB_SMEM_KB", 100);
 
 template <int S, int D, int CB, int PADX>
 int launch_bwd(const DwBwdParams& p, const DwBwdTile& t, cudaStream_t s) {
