@@ -418,7 +418,7 @@ static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels,
     if (metric) {
         const int cc = net->cfg.class_count;
         if (out_cm) for (int i = 0; i < cc; ++i) for (int j = 0; j < cc; ++j) out_cm[i * cc + j] = hs.confmat[i * kMaxClasses + j];
-        if (out_loss) *out_loss = hs.n_valid > 0 ? static_cast<float>(hs.loss_sum / static_cast<double>(hs.n_valid)) : NAN;
+        if (out_loss) *out_loss = hs.n_valid > 0 ? static_cast<float>((static_cast<double>(hs.loss_fixed) / kLossFixedScale) / static_cast<double>(hs.n_valid)) : NAN;
     }
     return 0;
 }
@@ -910,7 +910,7 @@ int ams_op_head_infer(const float* logits, int n, int h, int w_, int ldl, int H,
     cudaStreamSynchronize(as_stream(stream));
     cudaFree(st);
     if (confmat) for (int i = 0; i < cc; ++i) for (int j = 0; j < cc; ++j) confmat[i * cc + j] = hs.confmat[i * kMaxClasses + j];
-    if (loss_sum) *loss_sum = hs.loss_sum;
+    if (loss_sum) *loss_sum = static_cast<double>(hs.loss_fixed) / kLossFixedScale;
     if (n_valid) *n_valid = hs.n_valid;
     return rc;
 }

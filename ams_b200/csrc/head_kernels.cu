@@ -126,7 +126,8 @@ head_infer_kernel(const float* __restrict__ logits, const __grid_constant__ Head
             double l = 0.0; int vv = 0;
             for (int i = 0; i < 8; ++i) { l += s_loss[i]; vv += s_valid[i]; }
             if (vv) {
-                atomicAdd(&st->loss_sum, l);
+                atomicAdd(reinterpret_cast<unsigned long long*>(&st->loss_fixed),
+                          static_cast<unsigned long long>(__double2ll_rn(l * kLossFixedScale)));
                 atomicAdd(reinterpret_cast<unsigned long long*>(&st->n_valid), static_cast<unsigned long long>(vv));
             }
         }
@@ -314,7 +315,7 @@ head_cols_kernel(const float* __restrict__ rowbuf, const __grid_constant__ HeadC
 __global__ void head_reset_kernel(HeadStats* st) {
     pdl_entry();
     for (int i = threadIdx.x; i < kMaxClasses * kMaxClasses; i += blockDim.x) st->confmat[i] = 0;
-    if (threadIdx.x == 0) { st->loss_sum = 0.0; st->n_valid = 0; }
+    if (threadIdx.x == 0) { st->loss_sum = 0.0; st->n_valid = 0; st->loss_fixed = 0; }
 }
 
 int make_const(const HeadGeom& g, HeadConst* c) {

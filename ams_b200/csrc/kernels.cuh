@@ -131,9 +131,11 @@ struct HeadGeom {
 };
 struct HeadStats {               // device, zeroed by head_reset()
     long long confmat[kMaxClasses * kMaxClasses];
-    double loss_sum;
+    double loss_sum;             // training head: written by the fixed-order finalize
     long long n_valid;
+    long long loss_fixed;        // inference metric: sum of per-CTA losses in 2^-36 fixed point (integer atomics: deterministic)
 };
+constexpr double kLossFixedScale = 68719476736.0;   // 2^36
 int head_reset(HeadStats* st, cudaStream_t s);
 // pred int32 [N,H,W] (may be null); labels u8 [N,H,W] or null; st accumulates confmat / loss / n_valid
 int head_infer(const float* logits, const HeadGeom& g, const uint8_t* labels, int32_t* pred, HeadStats* st,

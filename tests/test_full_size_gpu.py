@@ -70,10 +70,11 @@ def test_frozen_inference_is_batch_size_independent_and_integer_exact(world):
     pred8, cm8, loss8 = st.infer_metric(B, nat.BN_MOVING)
     logits8 = st.get_logits(B).copy()
     st.enqueue(fr, lab)
-    pred8b, cm8b, _ = st.infer_metric(B, nat.BN_MOVING)              # graph capture / replay path
+    pred8b, cm8b, loss8b = st.infer_metric(B, nat.BN_MOVING)         # graph capture / replay path
     st.enqueue(fr, lab)
-    pred8c, cm8c, _ = st.infer_metric(B, nat.BN_MOVING)
+    pred8c, cm8c, loss8c = st.infer_metric(B, nat.BN_MOVING)
     assert np.array_equal(pred8, pred8b) and np.array_equal(pred8, pred8c) and np.array_equal(cm8, cm8b) and np.array_equal(cm8, cm8c)
+    assert loss8 == loss8b == loss8c                                  # integer (fixed-point) atomics: order-independent
     cm_sum = np.zeros_like(cm8)
     for i in range(B):
         st.enqueue(fr[i:i + 1], lab[i:i + 1])
