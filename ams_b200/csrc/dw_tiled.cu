@@ -362,7 +362,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
             const int k = i / CB, c = i - k * CB;
             reinterpret_cast<float*>(smem)[i] = p.w[k * p.C + c_base + c];
         }
-        constexpr int U = 2;
+        constexpr int U = 4;
         int ly = (lane_px * p.mg_w) >> 16, lx = lane_px - ly * p.owp;
         const int step_y = p.st_y, step_x = p.st_x;
         uint32_t sdst = tile_smem + (lane_px * CB + c8 * 8) * 2;
