@@ -58,6 +58,13 @@ _SIGNATURES = {
     'ams_train_forward_backward': (_i, [_vp, C.POINTER(_ll), C.POINTER(_d)]),
     'ams_gradient_arena': (_vp, [_vp, C.POINTER(_ll)]),
     'ams_apply_optimizer': (_i, [_vp, _f, _i, _f]),
+    'ams_train_step_async': (_i, [_vp, _f, _i, _vp]),
+    'ams_step_terms_device': (_vp, [_vp]),
+    'ams_apply_optimizer_device': (_i, [_vp, _f, _i, _vp]),
+    'ams_syncbn_init': (_i, [_vp, _i, _i, _vp, _i]),
+    'ams_syncbn_connect': (_i, [_vp, _vp, _i]),
+    'ams_syncbn_enable': (_i, [_vp, _i]),
+    'ams_syncbn_status': (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     'ams_apply_delta': (_i, [_vp, _vp, _ll, C.POINTER(_ll)]),
     'ams_get_logits': (_i, [_vp, _vp, _ll]),
     'ams_get_gradients': (_i, [_vp, _vp]),

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstring>
 
 #include "net.cuh"
@@ -168,6 +169,9 @@ void ams_destroy(ams_net* h) {
     for (auto& q : net->slots) { if (q.frames) cudaFree(q.frames); if (q.labels) cudaFree(q.labels); if (q.consumed) cudaEventDestroy(q.consumed); }
     if (net->raw_frames) cudaFree(net->raw_frames);
     if (net->raw_labels) cudaFree(net->raw_labels);
+    for (void* m : net->syncbn_mapped) if (m) cudaIpcCloseMemHandle(m);
+    if (net->syncbn_recv) cudaFree(net->syncbn_recv);
+    if (net->syncbn_dev) cudaFree(net->syncbn_dev);
     void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->before, net->delta_scratch, net->mask, net->moving,
                     net->bnpool, net->wpool, net->select_sc, net->head_st, net->cast_table, net->segs_dev, net->pack_bits,
                     net->pack_vals, net->pack_counts, net->pack_kept};
@@ -452,12 +456,12 @@ int ams_confmat_labels(ams_net* h, const uint8_t* before, const uint8_t* after, 
     return rc;
 }
 
-static int apply_optimizer(Net* net, float lr, int masked, float grad_scale) {
+static int apply_optimizer(Net* net, float lr, int masked, float grad_scale, const double* scale_terms = nullptr) {
     // TF1 Adam: alpha = lr * sqrt(1 - beta2^t) / (1 - beta1^t), all in fp32
     const float alpha = lr * std::sqrt(1.0f - net->beta2_power) / (1.0f - net->beta1_power);
     const uint8_t* mask = (masked && !net->mask_all_ones) ? net->mask : nullptr;
     net->prof.begin(net->stream, "adam_masked", (mask ? 29.0 : 28.0) * net->n_train);
-    const int rc_adam = adam_masked(net->params, net->grads, grad_scale, net->adam_m, net->adam_v, mask, net->n_train, alpha,
+    const int rc_adam = adam_masked(net->params, net->grads, grad_scale, scale_terms, net->adam_m, net->adam_v, mask, net->n_train, alpha,
                                     1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, net->stream);
     net->prof.end(net->stream);
     if (rc_adam) return -1;
@@ -472,6 +476,7 @@ int ams_train_forward_backward(ams_net* h, long long* out_n_valid, double* out_l
     Plan* p = nullptr;
     if (net_dequeue(net, &p, true)) return -1;
     if (net_train_fwd_bwd(net, p, false)) return -1;
+    if (!out_n_valid && !out_loss_sum) return 0;          // asynchronous form: the terms stay on the device (ams_step_terms_device)
     HeadStats hs;
     AMS_CUDA_CHECK(cudaMemcpyAsync(&hs, net->head_st, sizeof(HeadStats), cudaMemcpyDeviceToHost, net->stream));
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
@@ -488,6 +493,103 @@ void* ams_gradient_arena(ams_net* h, long long* count) {
 int ams_apply_optimizer(ams_net* h, float lr, int masked, float grad_scale) {
     NET(h);
     return apply_optimizer(net, lr, masked, grad_scale);
+}
+
+void* ams_step_terms_device(ams_net* h) {
+    Net* net = reinterpret_cast<Net*>(h);
+    if (!net) return nullptr;
+    return reinterpret_cast<char*>(net->head_st) + offsetof(HeadStats, terms);
+}
+int ams_apply_optimizer_device(ams_net* h, float lr, int masked, float* out_loss_pinned) {
+    NET(h);
+    const double* terms = reinterpret_cast<const double*>(reinterpret_cast<const char*>(net->head_st) + offsetof(HeadStats, terms));
+    if (apply_optimizer(net, lr, masked, 1.0f, terms)) return -1;
+    if (out_loss_pinned) {
+        if (head_mean_loss_from_terms(net->head_st, net->stream)) return -1;
+        AMS_CUDA_CHECK(cudaMemcpyAsync(out_loss_pinned, reinterpret_cast<const char*>(net->head_st) + offsetof(HeadStats, dp_loss),
+                                       sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    }
+    return 0;
+}
+int ams_train_step_async(ams_net* h, float lr, int masked, float* out_loss_pinned) {
+    NET(h);
+    Plan* p = nullptr;
+    if (net_dequeue(net, &p, true)) return -1;
+    if (net_train_fwd_bwd(net, p, true)) return -1;
+    if (apply_optimizer(net, lr, masked, 1.0f)) return -1;
+    if (out_loss_pinned) AMS_CUDA_CHECK(cudaMemcpyAsync(out_loss_pinned, p->loss_dev, sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    return 0;
+}
+
+// ---- global-batch BatchNorm for data parallel: statistics exchanged through NVLink peer memory (kernels.cuh SyncBn)
+static void drop_train_graphs(Net* net) {
+    // the captured steps hold the BN kernels' parameters (with / without the exchange context): capture again
+    cudaStreamSynchronize(net->stream);
+    for (auto& kv : net->plans) {
+        Plan* p = kv.second.get();
+        for (int k = 0; k < 2; ++k) {
+            if (p->train_graph[k]) { cudaGraphExecDestroy(p->train_graph[k]); p->train_graph[k] = nullptr; }
+            p->train_graph_dtype[k] = -1;
+        }
+        if (p->train_runs < 0) p->train_runs = 1;
+    }
+}
+int ams_syncbn_init(ams_net* h, int world, int rank, void* out_ipc_handle, int handle_capacity) {
+    NET(h);
+    AMS_REQUIRE(world >= 1 && world <= kSyncBnMaxWorld && rank >= 0 && rank < world, "world must be 1..8, rank inside it");
+    AMS_REQUIRE(handle_capacity >= static_cast<int>(sizeof(cudaIpcMemHandle_t)), "handle buffer too small (64 bytes)");
+    AMS_REQUIRE(!net->syncbn_recv, "ams_syncbn_init was already called on this handle");
+    SyncBn& sb = net->syncbn_host;
+    sb = SyncBn{};
+    sb.world = world; sb.rank = rank; sb.epoch = 0; sb.error = 0;
+    sb.words_per_src = net->n_bnpool / 6 * 8;
+    sb.timeout_ns = 2000000000ull;
+    if (const char* e = getenv("AMS_SYNCBN_TIMEOUT_MS")) sb.timeout_ns = static_cast<unsigned long long>(atoll(e)) * 1000000ull;
+    const size_t bytes = static_cast<size_t>(2) * world * sb.words_per_src * sizeof(unsigned long long);
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&net->syncbn_recv), bytes));
+    AMS_CUDA_CHECK(cudaMemset(net->syncbn_recv, 0, bytes));
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&net->syncbn_dev), sizeof(SyncBn)));
+    AMS_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hd;
+    AMS_CUDA_CHECK(cudaIpcGetMemHandle(&hd, net->syncbn_recv));
+    memcpy(out_ipc_handle, &hd, sizeof(hd));
+    return 0;
+}
+int ams_syncbn_connect(ams_net* h, const void* all_handles, int count) {
+    NET(h);
+    AMS_REQUIRE(net->syncbn_recv, "call ams_syncbn_init first");
+    SyncBn& sb = net->syncbn_host;
+    AMS_REQUIRE(count == sb.world, "one handle per rank");
+    for (int r = 0; r < sb.world; ++r) {
+        if (r == sb.rank) { sb.peer[r] = net->syncbn_recv; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, static_cast<const char*>(all_handles) + static_cast<size_t>(r) * sizeof(hd), sizeof(hd));
+        void* ptr = nullptr;
+        AMS_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+        net->syncbn_mapped[r] = ptr;
+        sb.peer[r] = static_cast<unsigned long long*>(ptr);
+    }
+    AMS_CUDA_CHECK(cudaMemcpy(net->syncbn_dev, &sb, sizeof(sb), cudaMemcpyHostToDevice));
+    drop_train_graphs(net);
+    net->syncbn_enabled = true;
+    return 0;
+}
+int ams_syncbn_enable(ams_net* h, int on) {
+    NET(h);
+    AMS_REQUIRE(!on || net->syncbn_dev, "ams_syncbn_connect has not been called");
+    if (net->syncbn_enabled != (on != 0)) { drop_train_graphs(net); net->syncbn_enabled = on != 0; }
+    return 0;
+}
+int ams_syncbn_status(ams_net* h, unsigned int* out_epoch, unsigned int* out_error) {
+    NET(h);
+    SyncBn sb{};
+    if (net->syncbn_dev) {
+        AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+        AMS_CUDA_CHECK(cudaMemcpy(&sb, net->syncbn_dev, sizeof(sb), cudaMemcpyDeviceToHost));
+    }
+    if (out_epoch) *out_epoch = sb.epoch;
+    if (out_error) *out_error = sb.error;
+    return 0;
 }
 
 int ams_train_step(ams_net* h, float lr, int masked, float* out_loss) {
@@ -952,7 +1054,7 @@ int ams_op_select(float* after, const float* before, long long n, double coord_f
 int ams_op_adam(float* p, const float* g, float* m, float* v, const uint8_t* mask, long long n, float lr, float b1p, float b2p,
                 void* stream) {
     const float alpha = lr * std::sqrt(1.0f - b2p) / (1.0f - b1p);
-    return adam_masked(p, g, 1.0f, m, v, mask, n, alpha, 1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, as_stream(stream));
+    return adam_masked(p, g, 1.0f, nullptr, m, v, mask, n, alpha, 1.0f - 0.9f, 1.0f - 0.999f, 1e-8f, as_stream(stream));
 }
 
 }  // extern "C"

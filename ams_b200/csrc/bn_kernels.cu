@@ -113,13 +113,71 @@ __device__ __forceinline__ bool finalize_sums(const double* __restrict__ partial
     return true;
 }
 
+// ------------------------------------------------------------------------------------ cross-GPU sum of a (s, q) pair
+// Called by ONE thread per channel.  word_off = the layer's offset + 4 * channel.  Push: 4 words (payload 32 bits |
+// epoch << 32) into slot [parity][my rank] of every rank's receive buffer (8-byte stores are single NVLink writes, so a
+// word is either old or complete).  Gather: poll the local slots of every source until their flag equals the epoch, add
+// in rank order.  A peer that never arrives trips the timeout: the error flag is raised (the host checks it) and the
+// local values are kept -- the kernel never hangs.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void syncbn_exchange(SyncBn* sb, long long word_off, double* s, double* q) {
+    const int world = sb->world, rank = sb->rank;
+    const unsigned int ep = sb->epoch;
+    const unsigned long long tag = static_cast<unsigned long long>(ep) << 32;
+    const long long wps = sb->words_per_src;
+    const long long base = static_cast<long long>(ep & 1u) * world * wps + word_off;
+    unsigned long long w[4];
+    w[0] = tag | static_cast<unsigned int>(__double2loint(*s)); w[1] = tag | static_cast<unsigned int>(__double2hiint(*s));
+    w[2] = tag | static_cast<unsigned int>(__double2loint(*q)); w[3] = tag | static_cast<unsigned int>(__double2hiint(*q));
+    for (int p = 0; p < world; ++p) {
+        unsigned long long* dst = sb->peer[(rank + p) % world] + base + static_cast<long long>(rank) * wps;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst + k), "l"(w[k]) : "memory");
+    }
+    if (*reinterpret_cast<volatile unsigned int*>(&sb->error)) return;
+    const unsigned long long t0 = global_timer_ns();
+    double S = 0.0, Q = 0.0;
+    for (int src = 0; src < world; ++src) {
+        const unsigned long long* from = sb->peer[rank] + base + static_cast<long long>(src) * wps;
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned int spins = 0;
+            for (;;) {
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(from + k) : "memory");
+                if (static_cast<unsigned int>(v[k] >> 32) == ep) break;
+                if ((++spins & 255u) == 0u && global_timer_ns() - t0 > sb->timeout_ns) {
+                    atomicExch(&sb->error, 1u);
+                    return;
+                }
+            }
+        }
+        S += __hiloint2double(static_cast<int>(static_cast<unsigned int>(v[1])), static_cast<int>(static_cast<unsigned int>(v[0])));
+        Q += __hiloint2double(static_cast<int>(static_cast<unsigned int>(v[3])), static_cast<int>(static_cast<unsigned int>(v[2])));
+    }
+    *s = S; *q = Q;
+}
+__global__ void syncbn_begin_step_kernel(SyncBn* sb) {
+    pdl_entry();
+    if (threadIdx.x == 0) {
+        unsigned int e = sb->epoch + 1u;
+        if (e == 0u) e = 1u;                  // 0 is the "never written" flag of a fresh buffer
+        sb->epoch = e;
+    }
+}
+
 __global__ void __launch_bounds__(32 * kFinRows)
 bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, int update_moving) {
     pdl_entry();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, q;
     if (!finalize_sums(partial, chunks, L.C, c, &s, &q)) return;
-    const double n = static_cast<double>(L.M);
+    double n = static_cast<double>(L.M);
+    if (L.sync) { syncbn_exchange(L.sync, L.xoff_fwd + 4LL * c, &s, &q); n *= L.sync->world; }
     const double mean = s / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -292,10 +350,15 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L
     double s1, sz;
     if (!finalize_sums(partial, chunks, L.C, c, &s1, &sz)) return;
     const double mean = L.mean[c], rstd = L.rstd[c], gamma = L.gamma[c];
-    const double n = static_cast<double>(L.M);
-    const double s2 = rstd * (sz - mean * s1);           // sum g * xhat
-    d_gamma[c] = static_cast<float>(s2);
+    double n = static_cast<double>(L.M);
+    double s2 = rstd * (sz - mean * s1);                 // sum g * xhat
+    d_gamma[c] = static_cast<float>(s2);                 // LOCAL sums: the gradient allreduce adds the ranks
     d_beta[c] = static_cast<float>(s1);
+    if (L.sync) {
+        syncbn_exchange(L.sync, L.xoff_bwd + 4LL * c, &s1, &sz);
+        n *= L.sync->world;
+        s2 = rstd * (sz - mean * s1);
+    }
     const double A = gamma * rstd;
     const double B = -gamma * rstd * rstd * s2 / n;
     const double Cc = -gamma * rstd * (s1 / n - mean * rstd * s2 / n);
@@ -451,11 +514,21 @@ imgpool_bn_kernel(ImgPoolFwd a) {
         sc = a.bn.gamma[co] * rsqrtf(a.bn.moving_var[co] + a.bn.eps);
         sh = a.bn.beta[co] - a.bn.moving_mean[co] * sc;
     } else {
-        double s = 0.0, q = 0.0;
+        double s = 0.0, q = 0.0, cnt = N;
         for (int n = 0; n < N; ++n) s += a.z[n * Cm + co];
-        const double mean = s / N;
-        for (int n = 0; n < N; ++n) { const double d = a.z[n * Cm + co] - mean; q += d * d; }
-        const double var = q / N;
+        double mean, var;
+        if (a.bn.sync) {
+            // global batch: exchange (sum z, sum z^2); fp64 products of fp32 values are exact
+            for (int n = 0; n < N; ++n) { const double v = a.z[n * Cm + co]; q += v * v; }
+            syncbn_exchange(a.bn.sync, a.bn.xoff_fwd + 4LL * co, &s, &q);
+            cnt *= a.bn.sync->world;
+            mean = s / cnt;
+            var = fmax(q / cnt - mean * mean, 0.0);
+        } else {
+            mean = s / N;
+            for (int n = 0; n < N; ++n) { const double d = a.z[n * Cm + co] - mean; q += d * d; }
+            var = q / N;
+        }
         const float meanf = static_cast<float>(mean), varf = static_cast<float>(var);
         const float rstd = rsqrtf(varf + a.bn.eps);
         sc = a.bn.gamma[co] * rstd;
@@ -463,7 +536,7 @@ imgpool_bn_kernel(ImgPoolFwd a) {
         a.bn.mean[co] = meanf;
         a.bn.rstd[co] = rstd;
         if (a.update_moving) {
-            const float unb = static_cast<float>(var * (static_cast<double>(N) / fmax(N - 1.0, 1.0)));
+            const float unb = static_cast<float>(var * (cnt / fmax(cnt - 1.0, 1.0)));
             const float mm = a.bn.moving_mean[co], mv = a.bn.moving_var[co];
             a.bn.moving_mean[co] = __fsub_rn(mm, __fmul_rn(__fsub_rn(mm, meanf), a.bn.one_minus_decay));
             a.bn.moving_var[co] = __fsub_rn(mv, __fmul_rn(__fsub_rn(mv, unb), a.bn.one_minus_decay));
@@ -487,17 +560,24 @@ imgpool_bn_bwd_kernel(ImgPoolFwd a, float* __restrict__ dact, float* __restrict_
         s1 += g;
         s2 += g * (a.z[n * Cm + co] - mean) * rstd;
     }
-    d_gamma[co] = static_cast<float>(s2);
+    d_gamma[co] = static_cast<float>(s2);                // LOCAL sums: the gradient allreduce adds the ranks
     d_beta[co] = static_cast<float>(s1);
+    double cnt = N;
+    if (a.bn.sync) { syncbn_exchange(a.bn.sync, a.bn.xoff_bwd + 4LL * co, &s1, &s2); cnt *= a.bn.sync->world; }
     for (int n = 0; n < N; ++n) {
         const double xh = (a.z[n * Cm + co] - mean) * rstd;
-        dact[n * Cm + co] = static_cast<float>(gamma * rstd * (dact[n * Cm + co] - s1 / N - xh * s2 / N));
+        dact[n * Cm + co] = static_cast<float>(gamma * rstd * (dact[n * Cm + co] - s1 / cnt - xh * s2 / cnt));
     }
 }
 
 }  // namespace
 
 // ============================================================================================ host
+int syncbn_begin_step(SyncBn* sb, cudaStream_t s) {
+    AMS_LAUNCH((syncbn_begin_step_kernel), 1, 32, 0, s, sb);
+    return 0;
+}
+
 size_t bn_workspace_doubles(long long M, int C) {
     // partials (reduction chunks, or one slab per CTA of a producer kernel with fused statistics) + coef
     const size_t chunks = std::max<size_t>(red_chunks(M, C), 2 * kNumSMs);

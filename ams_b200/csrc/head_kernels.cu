@@ -275,6 +275,8 @@ __global__ void head_finalize_kernel(const double* __restrict__ row_loss, const 
     if (threadIdx.x == 0) {
         st->loss_sum = s_l[0];
         st->n_valid = s_v[0];
+        st->terms[0] = static_cast<double>(s_v[0]);
+        st->terms[1] = s_l[0];
         *loss_out = s_v[0] > 0 ? static_cast<float>(s_l[0] / static_cast<double>(s_v[0])) : __int_as_float(0x7fc00000);
     }
 }
@@ -315,7 +317,13 @@ head_cols_kernel(const float* __restrict__ rowbuf, const __grid_constant__ HeadC
 __global__ void head_reset_kernel(HeadStats* st) {
     pdl_entry();
     for (int i = threadIdx.x; i < kMaxClasses * kMaxClasses; i += blockDim.x) st->confmat[i] = 0;
-    if (threadIdx.x == 0) { st->loss_sum = 0.0; st->n_valid = 0; st->loss_fixed = 0; }
+    if (threadIdx.x == 0) { st->loss_sum = 0.0; st->n_valid = 0; st->loss_fixed = 0; st->terms[0] = 0.0; st->terms[1] = 0.0; }
+}
+
+__global__ void head_mean_loss_kernel(HeadStats* st) {
+    pdl_entry();
+    if (threadIdx.x == 0)
+        st->dp_loss[0] = st->terms[0] > 0.0 ? static_cast<float>(st->terms[1] / st->terms[0]) : __int_as_float(0x7fc00000);
 }
 
 int make_const(const HeadGeom& g, HeadConst* c) {
@@ -338,6 +346,11 @@ int make_const(const HeadGeom& g, HeadConst* c) {
 
 int head_reset(HeadStats* st, cudaStream_t s) {
     AMS_LAUNCH((head_reset_kernel), 1, 256, 0, s, st);
+    return 0;
+}
+
+int head_mean_loss_from_terms(HeadStats* st, cudaStream_t s) {
+    AMS_LAUNCH((head_mean_loss_kernel), 1, 32, 0, s, st);
     return 0;
 }
 

@@ -57,8 +57,27 @@ struct DwBwdFused {
 long long dw_bwd_fused_rows(const Conv2dGeom& g);
 int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s);
 
+// ---- cross-GPU BatchNorm statistics (SURVEY 8e caveat 2: the reference normalises over the WHOLE batch in one process)
+// One exchange per BatchNorm layer and direction, inside the finalize kernels: every rank pushes its per-channel fp64
+// sum pair straight into every peer's receive buffer over NVLink (peer memory mapped through CUDA IPC), as 8-byte words
+// that carry 32 bits of payload and the step's epoch as the arrival flag -- no fence, no separate flag, no host or NCCL
+// call inside the step (the kernels are captured in the step's CUDA graph like all others).  Each rank then adds the
+// world's pairs in rank order, so every rank computes bit-identical statistics.
+constexpr int kSyncBnMaxWorld = 8;
+struct SyncBn {                              // device-resident; kernels get a pointer to it (null = per-replica statistics)
+    int world, rank;
+    unsigned int epoch;                      // bumped once per training step (syncbn_begin_step); flags compare against it
+    unsigned int error;                      // != 0: a wait ran into the timeout (a peer never arrived); later exchanges skip the wait
+    long long words_per_src;                 // 8 * sum of BN channels: forward region, then backward region
+    unsigned long long timeout_ns;
+    unsigned long long* peer[kSyncBnMaxWorld];   // receive buffers [2 epoch parities][world sources][words_per_src]; peer[rank] is local
+};
+int syncbn_begin_step(SyncBn* sb, cudaStream_t s);
+
 // ---- BatchNorm, training mode
 struct BnLayer {            // device pointers into the parameter / state arenas, all [C] fp32
+    SyncBn* sync = nullptr; // != null: batch statistics are summed over the ranks of the data-parallel job
+    long long xoff_fwd = 0, xoff_bwd = 0;      // this layer's word offsets inside a source's region of the receive buffer
     int C;
     long long M;            // N*H*W reduction length
     float eps, one_minus_decay;
@@ -134,9 +153,13 @@ struct HeadStats {               // device, zeroed by head_reset()
     double loss_sum;             // training head: written by the fixed-order finalize
     long long n_valid;
     long long loss_fixed;        // inference metric: sum of per-CTA losses in 2^-36 fixed point (integer atomics: deterministic)
+    double terms[2];             // training head: (n_valid, loss_sum) as doubles -- the pair a data-parallel job sums over ranks in place
+    float dp_loss[2];            // [0] = terms[1] / terms[0] (global mean loss), written by head_mean_loss_from_terms()
 };
 constexpr double kLossFixedScale = 68719476736.0;   // 2^36
 int head_reset(HeadStats* st, cudaStream_t s);
+// st->dp_loss[0] = st->terms[1] / st->terms[0] (NaN when no valid pixel): the data-parallel loss after the terms were summed
+int head_mean_loss_from_terms(HeadStats* st, cudaStream_t s);
 // pred int32 [N,H,W] (may be null); labels u8 [N,H,W] or null; st accumulates confmat / loss / n_valid
 int head_infer(const float* logits, const HeadGeom& g, const uint8_t* labels, int32_t* pred, HeadStats* st,
                cudaStream_t s);
@@ -162,7 +185,8 @@ int colsum_groups(const float* x_f32, const bf16* x_bf16, int ld, long long rows
 size_t colsum_workspace_doubles(int groups, int C);
 
 // ---- optimizer / selection / delta
-int adam_masked(float* p, const float* g, float grad_scale, float* m, float* v, const uint8_t* mask, long long n,
+// scale_terms != null: grad_scale = 1 / scale_terms[0] read on the device (0 when scale_terms[0] <= 0)
+int adam_masked(float* p, const float* g, float grad_scale, const double* scale_terms, float* m, float* v, const uint8_t* mask, long long n,
                 float alpha, float one_minus_b1, float one_minus_b2, float eps, cudaStream_t s);
 struct SelectScratch {           // device
     unsigned int hist[256];

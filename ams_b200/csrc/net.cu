@@ -189,6 +189,12 @@ static BnLayer bn_layer(Net* net, const LayerDef& d, long long M) {
     b.moving_mean = net->moving + d.mm_off; b.moving_var = net->moving + d.mv_off;
     float* pool = net->bnpool + d.bn_off;
     b.scale = pool; b.shift = pool + d.cout; b.mean = pool + 2 * d.cout; b.rstd = pool + 3 * d.cout;
+    if (net->sync_active) {
+        // 4 words per channel and direction; layers laid out in bnpool order, backward region after the forward one
+        b.sync = net->syncbn_dev;
+        b.xoff_fwd = d.bn_off / 6 * 4;
+        b.xoff_bwd = net->n_bnpool / 6 * 4 + b.xoff_fwd;
+    }
     return b;
 }
 static float* fscale(Net* net, const LayerDef& d) { return net->bnpool + d.bn_off + 4 * d.cout; }
@@ -585,8 +591,15 @@ int net_train_fwd_bwd(Net* net, Plan* p, bool normalize) {
     static const bool no_graph = [] { const char* e = getenv("AMS_NO_GRAPH"); return e && e[0] == '1'; }();
     const int k = normalize ? 1 : 0;
     auto eager = [&]() -> int {
-        if (net_forward(net, p, AMS_BN_BATCH, true)) return -1;
-        return net_backward(net, p, normalize);
+        // data parallel with global-batch BatchNorm: bump the exchange epoch, then every BN finalize of this step
+        // (forward and backward) sums its statistics over the ranks through NVLink peer memory
+        net->sync_active = net->syncbn_enabled;
+        int rc = 0;
+        if (net->sync_active) rc = syncbn_begin_step(net->syncbn_dev, net->stream);
+        if (!rc) rc = net_forward(net, p, AMS_BN_BATCH, true);
+        if (!rc) rc = net_backward(net, p, normalize);
+        net->sync_active = false;
+        return rc;
     };
     if (no_graph || net->prof.enabled || p->train_runs < 0) return eager();
     if (p->train_graph[k] && p->train_graph_dtype[k] == p->in_dtype) {

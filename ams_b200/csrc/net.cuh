@@ -125,6 +125,11 @@ struct Net {
     VarSeg* segs_dev = nullptr; long long mask_bytes = 0;
     SelectScratch* select_sc = nullptr;
     HeadStats* head_st = nullptr;
+    // cross-GPU BatchNorm statistics (data parallel, ams_syncbn_*): device context, local receive buffer, mapped peers
+    SyncBn* syncbn_dev = nullptr; SyncBn syncbn_host{}; unsigned long long* syncbn_recv = nullptr;
+    void* syncbn_mapped[kSyncBnMaxWorld] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool syncbn_enabled = false;        // connected and switched on
+    bool sync_active = false;           // true only while a TRAINING step is being enqueued (inference never exchanges)
     uint8_t* pack_bits = nullptr; __half* pack_vals = nullptr; unsigned int* pack_counts = nullptr; unsigned long long* pack_kept = nullptr;
     bool weights_dirty = true, fold_dirty = true;
     HeadGeom head{};

@@ -9,12 +9,16 @@ namespace ams {
 namespace {
 
 __global__ void __launch_bounds__(256)
-adam_masked_kernel(float* __restrict__ p, const float* __restrict__ g, float grad_scale, float* __restrict__ m,
-                   float* __restrict__ v, const uint8_t* __restrict__ mask, long long n, float alpha, float omb1,
-                   float omb2, float eps) {
+adam_masked_kernel(float* __restrict__ p, const float* __restrict__ g, float grad_scale,
+                   const double* __restrict__ scale_terms, float* __restrict__ m, float* __restrict__ v,
+                   const uint8_t* __restrict__ mask, long long n, float alpha, float omb1, float omb2, float eps) {
     pdl_entry();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (scale_terms) {                       // data parallel: 1 / (n_valid summed over ranks), still on the device
+        const double nv = scale_terms[0];
+        grad_scale = nv > 0.0 ? static_cast<float>(1.0 / nv) : 0.f;
+    }
     // TF1 ApplyAdam functor: m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= (m*alpha)/(sqrt(v)+eps)
     const float gi = __fmul_rn(g[i], grad_scale);
     const float mi = __fadd_rn(m[i], __fmul_rn(__fsub_rn(gi, m[i]), omb1));
@@ -219,9 +223,9 @@ cast_weights_kernel(const WeightCast* __restrict__ table) {
 
 }  // namespace
 
-int adam_masked(float* p, const float* g, float grad_scale, float* m, float* v, const uint8_t* mask, long long n,
-                float alpha, float omb1, float omb2, float eps, cudaStream_t s) {
-    AMS_LAUNCH((adam_masked_kernel), static_cast<int>(ceil_div_ll(n, 256)), 256, 0, s, p, g, grad_scale, m, v, mask, n, alpha, omb1, omb2, eps);
+int adam_masked(float* p, const float* g, float grad_scale, const double* scale_terms, float* m, float* v, const uint8_t* mask,
+                long long n, float alpha, float omb1, float omb2, float eps, cudaStream_t s) {
+    AMS_LAUNCH((adam_masked_kernel), static_cast<int>(ceil_div_ll(n, 256)), 256, 0, s, p, g, grad_scale, scale_terms, m, v, mask, n, alpha, omb1, omb2, eps);
     return 0;
 }
 

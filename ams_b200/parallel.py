@@ -6,8 +6,9 @@
     loss left as a SUM over its valid pixels, then ONE exchange step: allreduce(sum) of the flat fp32 gradient arena
     (2,113,043 floats = 8.45 MB, NCCL over NVLink) and of (n_valid, loss_sum); Adam then runs identically on every
     rank with gradients scaled by 1 / global n_valid, which reproduces the reference's `reduce_mean` over all valid
-    pixels of the global batch (utils/graph_utils.py:408).  BatchNorm statistics stay per replica (documented
-    deviation, DESIGN.md).
+    pixels of the global batch (utils/graph_utils.py:408).  BatchNorm batch statistics are summed over the ranks inside
+    the BN finalize kernels through NVLink peer memory (sync_bn=True: the step equals the reference's single-process
+    step on the global batch) or stay per replica (sync_bn=False, a documented deviation).
 torch.distributed is plumbing only; on CPU the same code runs over gloo (tests/test_parallel_gloo.py).
 """
 import torch
@@ -35,23 +36,84 @@ def allreduce_step_terms(grad, n_valid, loss_sum, group=None):
 class _DeviceArena:
     """Zero-copy torch view of a device buffer owned by libams_b200 (CUDA array interface)."""
 
-    def __init__(self, ptr, count):
-        self.__cuda_array_interface__ = {'shape': (count,), 'typestr': '<f4', 'data': (ptr, False), 'version': 2}
+    def __init__(self, ptr, count, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': (count,), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
+
+
+def exchange_ipc_handles(handle, group=None):
+    """All-gather of the 64-byte CUDA IPC handles of the ranks' SyncBN receive buffers -> uint8 [world, 64]."""
+    world = dist.get_world_size(group)
+    mine = torch.from_numpy(handle.copy()).cuda()
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    return torch.stack(out).cpu().numpy()
 
 
 class DataParallelStudent:
-    """One rank of a data-parallel distillation job: wraps a `Student` and the process group."""
+    """One rank of a data-parallel distillation job: wraps a `Student` and the process group.
 
-    def __init__(self, student, group=None):
+    The step is enqueued without any host round trip: forward/backward (CUDA graph), allreduce of the gradient arena
+    and of the (n_valid, loss_sum) pair in place on the device, Adam reading 1 / n_valid from that pair.  The loss of
+    step i lands in a page-locked slot and is read after a later synchronisation (the reference only prints it,
+    SemanticNetwork.py:261).
+
+    sync_bn=True: BatchNorm batch statistics are summed over the ranks inside the BN finalize kernels through NVLink
+    peer memory (ams_syncbn_*), which makes the job equivalent to the reference's single-process step on the global
+    batch; sync_bn=False keeps per-replica statistics (faster, a documented deviation)."""
+
+    def __init__(self, student, group=None, sync_bn=False):
         self.student = student
         self.group = group
         ptr, n = student.gradient_arena()
         self.grad = torch.as_tensor(_DeviceArena(ptr, n), device='cuda')
+        self.terms = torch.as_tensor(_DeviceArena(student.step_terms_ptr(), 2, '<f8'), device='cuda')
+        self._loss_slots = torch.zeros(256, dtype=torch.float32).pin_memory()
+        self._loss_np = self._loss_slots.numpy()
+        self._pending = 0
+        self.sync_bn = False
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        if sync_bn and self.world > 1:
+            rank = dist.get_rank(group)
+            handles = exchange_ipc_handles(student.syncbn_init(self.world, rank), group)
+            student.syncbn_connect(handles)
+            dist.barrier(group=group)             # every rank has mapped every (zeroed) receive buffer before the first push
+            self.sync_bn = True
+
+    def _slot(self):
+        if self._pending >= self._loss_np.size:
+            self.losses()
+        i = self._pending
+        self._pending += 1
+        return self._loss_np[i:i + 1]
+
+    def train_step_async(self, lr, masked):
+        """Enqueue one step; returns nothing.  losses() synchronises and returns the losses of the steps since the last call."""
+        # the library and torch must share one stream (Student.set_stream(torch.cuda.current_stream().cuda_stream)):
+        # the allreduces are ordered after backward and before Adam by stream order alone
+        self.student.train_forward_backward_async()
+        if self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.terms, op=dist.ReduceOp.SUM, group=self.group)
+        self.student.apply_optimizer_device(lr, masked, self._slot())
+
+    def losses(self):
+        self.student.synchronize()
+        out = [float(x) for x in self._loss_np[:self._pending]]
+        self._pending = 0
+        if self.sync_bn:
+            _, err = self.student.syncbn_status()
+            if err:
+                raise RuntimeError('SyncBN exchange timed out: a rank did not reach the same BatchNorm layer (ranks must run '
+                                   'the same sequence of training steps)')
+        return out
 
     def train_step(self, lr, masked):
-        # the library and torch must share one stream (Student.set_stream(torch.cuda.current_stream().cuda_stream)):
-        # the allreduce is ordered after backward and before Adam by stream order alone
-        n_valid, loss_sum = self.student.train_forward_backward()
-        scale, loss = allreduce_step_terms(self.grad, n_valid, loss_sum, self.group)
-        self.student.apply_optimizer(lr, masked, scale)
-        return loss
+        """Synchronous form: returns this step's global mean loss."""
+        self.train_step_async(lr, masked)
+        return self.losses()[-1]
+
+    def close(self):
+        """Ranks leave together: nobody unmaps a receive buffer a peer may still push into."""
+        if self.world > 1:
+            self.student.synchronize()
+            dist.barrier(group=self.group)

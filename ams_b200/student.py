@@ -195,6 +195,12 @@ class Student:
         nat.check(self._L.ams_train_step(self._h, float(lr), 1 if masked else 0, C.byref(loss)), 'train_step')
         return np.float32(loss.value)
 
+    def train_step_async(self, lr, masked, loss_out=None):
+        """The same step without the host round trip: everything is enqueued on the stream; `loss_out` (a 1-element
+        float32 array in page-locked memory, e.g. `torch.empty(1, pin_memory=True).numpy()`) receives the pre-update
+        loss when the stream gets there.  Call synchronize() before reading it."""
+        nat.check(self._L.ams_train_step_async(self._h, float(lr), 1 if masked else 0, _ptr(loss_out)), 'train_step_async')
+
     def set_mask(self, mask_flat):
         if mask_flat is None:
             nat.check(self._L.ams_set_mask(self._h, None))
@@ -236,6 +242,38 @@ class Student:
         nv, ls = C.c_longlong(), C.c_double()
         nat.check(self._L.ams_train_forward_backward(self._h, C.byref(nv), C.byref(ls)), 'train_forward_backward')
         return nv.value, ls.value
+
+    def train_forward_backward_async(self):
+        """Forward/backward enqueued without synchronising; (n_valid, loss_sum) stay on the device (step_terms_ptr)."""
+        nat.check(self._L.ams_train_forward_backward(self._h, None, None), 'train_forward_backward')
+
+    def step_terms_ptr(self):
+        """Device pointer to the two doubles (n_valid, loss_sum) of the last forward/backward."""
+        return self._L.ams_step_terms_device(self._h)
+
+    def apply_optimizer_device(self, lr, masked, loss_out=None):
+        """Adam + mask with the gradient scale 1 / n_valid read from the (allreduced) device terms; `loss_out` as in
+        train_step_async (global mean loss)."""
+        nat.check(self._L.ams_apply_optimizer_device(self._h, float(lr), 1 if masked else 0, _ptr(loss_out)), 'apply_optimizer_device')
+
+    # global-batch BatchNorm statistics over NVLink peer memory (include/ams_b200.h: ams_syncbn_*)
+    def syncbn_init(self, world, rank):
+        buf = np.zeros(64, dtype=np.uint8)
+        nat.check(self._L.ams_syncbn_init(self._h, int(world), int(rank), _ptr(buf), buf.size), 'syncbn_init')
+        return buf
+
+    def syncbn_connect(self, handles):
+        h = np.ascontiguousarray(handles, dtype=np.uint8)
+        assert h.ndim == 2 and h.shape[1] == 64, h.shape
+        nat.check(self._L.ams_syncbn_connect(self._h, _ptr(h), h.shape[0]), 'syncbn_connect')
+
+    def syncbn_enable(self, on):
+        nat.check(self._L.ams_syncbn_enable(self._h, 1 if on else 0), 'syncbn_enable')
+
+    def syncbn_status(self):
+        ep, er = C.c_uint(), C.c_uint()
+        nat.check(self._L.ams_syncbn_status(self._h, C.byref(ep), C.byref(er)), 'syncbn_status')
+        return ep.value, er.value
 
     def gradient_arena(self):
         n = C.c_longlong()

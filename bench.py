@@ -13,7 +13,9 @@ thread through ams_enqueue, D2H of every loss and of the delta) in steps/s.
 Secondary block `infer`: frozen-client frames/s (C1/C3 shape, batch 8, argmax + confusion matrix).
 
 N > 1 (torchrun): data parallel, 8 frames per GPU (weak scaling), NCCL allreduce of the 8.45 MB gradient arena and
-of n_valid, per-replica BatchNorm statistics.  `--impl reference` times the CPU oracle (the port of the
+of (n_valid, loss_sum) on the device, BatchNorm batch statistics summed over the ranks inside the BN kernels through
+NVLink peer memory (global-batch semantics of the reference; --sync-bn 0 = per replica).  No host synchronisation
+inside a phase.  `--impl reference` times the CPU oracle (the port of the
 reference's TF1 path; TensorFlow 1.15 cannot be installed here) on the host cores.
 """
 import argparse
@@ -209,12 +211,28 @@ def run_ours(args, rank, world, local_rank):
     dp = None
     if world > 1:
         from ams_b200.parallel import DataParallelStudent
-        dp = DataParallelStudent(st)
+        dp = DataParallelStudent(st, sync_bn=bool(args.sync_bn))
+    # steps are enqueued without a host round trip (the reference only prints the loss, SemanticNetwork.py:261): the loss
+    # of step i is copied to its page-locked slot when the stream gets there and read after the phase's synchronisation
+    loss_t, loss_np = pinned((max(K, Wm) + 1,), torch.float32)
+    step_no = [0]
 
     def step(masked):
         if dp is None:
-            return st.train_step(LR, masked)
-        return dp.train_step(LR, masked)
+            i = step_no[0] % loss_np.size
+            st.train_step_async(LR, masked, loss_np[i:i + 1])
+            step_no[0] += 1
+        else:
+            dp.train_step_async(LR, masked)
+
+    def drain():
+        """synchronise and return the losses of the steps enqueued since the last drain"""
+        if dp is not None:
+            return dp.losses()
+        st.synchronize()
+        out = [float(x) for x in loss_np[:step_no[0]]]
+        step_no[0] = 0
+        return out
 
     def phase(feed_from_host):
         """one distillation phase of K iterations; returns (delta bytes, kept)"""
@@ -233,6 +251,8 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(K - 1):
             step(True)
         blob = st.pack_delta()
+        losses = drain()
+        assert len(losses) == K and all(np.isfinite(losses)), losses
         if feeder is not None:
             feeder.join()
         return len(blob), kept
@@ -247,6 +267,7 @@ def run_ours(args, rank, world, local_rank):
         _, fa, _, la = host[i % nb]
         st.enqueue(fa, la)
         step(False)
+        drain()
         mark('warm-up step %d done' % i)
     torch.cuda.synchronize()
 
@@ -279,6 +300,25 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = max(f0.elapsed_time(f1), 1000.0 * (time.time() - t_wall0))
     clocks = sampler.stop() if rank == 0 else None
     mark('clock sampler stopped')
+    # ---- N > 1 with global-batch BatchNorm: the same phase with per-replica statistics, to show what the exchange costs
+    ms_replica_bn = None
+    if dp is not None and dp.sync_bn:
+        st.syncbn_enable(False)
+        for i in range(K + 2):
+            _, fa, _, la = host[i % nb]
+            st.enqueue(fa, la)
+        step(False); step(False); drain()                 # eager + capture of the graph without the exchange
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        r0.record(stream)
+        phase(False)
+        r1.record(stream)
+        barrier()
+        ms_replica_bn = r0.elapsed_time(r1)
+        t = torch.tensor([ms_replica_bn], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_replica_bn = float(t[0])
+        mark('per-replica BN phase done')
     if world > 1:
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,6 +370,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- per-kernel-group device times (separate short pass so the events do not perturb the numbers above)
     prof = None
     infer = None
+    if dp is not None and dp.sync_bn:
+        st.syncbn_enable(False)                  # what follows is rank-local
     if rank == 0:
         st.profile_enable(True)
         for i in range(3):
@@ -390,7 +432,10 @@ def run_ours(args, rank, world, local_rank):
                                    'coord_desc_auto 5 % selection at iteration 0 + masked Adam + delta pack at the end',
                        'global_batch': BATCH * world, 'parallelism': 'dp%d' % world if world > 1 else 'single',
                        'l2': 'no explicit flush: each step streams ~3 GB of activations (>> 126 MB L2) and batches are distinct',
-                       'delta_bytes': delta_len, 'kept_coordinates': kept},
+                       'delta_bytes': delta_len, 'kept_coordinates': kept,
+                       'batchnorm': ('global batch: statistics summed over ranks through NVLink peer memory inside the BN kernels'
+                                     if (dp is not None and dp.sync_bn) else ('per replica' if dp is not None else 'single process')),
+                       'host_sync': 'none inside the phase: losses land in page-locked slots, read after the phase'},
             'e2e': {'value': e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d_step, 'd2h_bytes_per_step': 4 + delta_len2 // K,
                     'ms_per_step': ms_e2e / K},
             'gpu_launches': int(launches),
@@ -404,10 +449,15 @@ def run_ours(args, rank, world, local_rank):
             'infer': infer,
             'infer_streams': infer_streams,
         }
+        if ms_replica_bn is not None:
+            line['per_replica_bn'] = {'value': K * world / (ms_replica_bn / 1000.0), 'unit': 'steps/s', 'ms_per_step': ms_replica_bn / K,
+                                      'note': 'same phase with per-replica BatchNorm statistics (not the reference\'s global-batch semantics)'}
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline()
         print(json.dumps(line), flush=True)
     mark('closing')
+    if dp is not None:
+        dp.close()
     st.close()
     mark('closed')
     if world > 1:
@@ -421,6 +471,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sync-bn', type=int, default=1, help='N > 1: 1 = global-batch BatchNorm statistics (reference semantics), 0 = per replica')
     ap.add_argument('--verbose', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -98,6 +98,10 @@ int ams_confmat_labels(ams_net* net, const uint8_t* labels_before, const uint8_t
  * only coordinates with mask==1 are written back (backup -> minimize -> where(mask, new, backup),
  * utils/graph_utils.py:483-493).  out_loss = pre-update loss. */
 int ams_train_step(ams_net* net, float lr, int masked, float* out_loss);
+/* the same step without the host synchronisation: everything is enqueued on the handle's stream and the loss is copied
+ * to out_loss_pinned (page-locked host memory, may be NULL) when the stream gets there -- the reference only prints the
+ * loss (SemanticNetwork.py:261), so a training phase needs no per-step round trip; ams_synchronize() before reading */
+int ams_train_step_async(ams_net* net, float lr, int masked, float* out_loss_pinned);
 /* feed of the 164 mask placeholders (SemanticNetwork.py:255-257) as ONE byte map in trainable-arena order;
  * NULL = all ones */
 int ams_set_mask(ams_net* net, const uint8_t* host_mask);
@@ -121,10 +125,34 @@ int ams_apply_delta(ams_net* net, const uint8_t* delta, long long length, long l
 /* forward+backward only; gradients stay in the device gradient arena as sums over the LOCAL valid pixels
  * (not divided by n_valid) so that ranks can be summed; out_n_valid / out_loss_sum are the local terms */
 int ams_train_forward_backward(ams_net* net, long long* out_n_valid, double* out_loss_sum);
+/* asynchronous form of the exchange step: with both outputs NULL ams_train_forward_backward() does not synchronise and
+ * leaves (n_valid, loss_sum) as two doubles on the device; the host plumbing allreduces that pair in place next to the
+ * gradient arena, and ams_apply_optimizer_device() reads 1 / n_valid from it (0 valid pixels: scale 0, NaN loss).
+ * out_loss_pinned (page-locked, may be NULL) receives the global mean loss when the stream gets there. */
+void* ams_step_terms_device(ams_net* net);
+int ams_apply_optimizer_device(ams_net* net, float lr, int masked, float* out_loss_pinned);
 /* device pointer + length (floats) of the gradient arena, for an NCCL allreduce issued by the host plumbing */
 void* ams_gradient_arena(ams_net* net, long long* count);
 /* Adam + mask with gradients scaled by grad_scale (= 1 / global n_valid) */
 int ams_apply_optimizer(ams_net* net, float lr, int masked, float grad_scale);
+
+/* Global-batch BatchNorm for the data-parallel step.  The reference computes FusedBatchNormV3(is_training=True)
+ * statistics over the whole batch in one process (model.meta; utils/graph_utils.py:457), so a job that splits the
+ * batch over GPUs must sum (sum z, sum z^2) forward and (sum g, sum g*z) backward over the ranks for each of the 54
+ * BatchNorm layers.  Here the BN finalize kernels do that themselves: each rank pushes its fp64 pairs into every
+ * peer's receive buffer over NVLink (CUDA IPC peer memory, 8-byte words carrying payload + epoch flag) and adds the
+ * world's pairs in rank order -- no host or NCCL call inside the step, bit-identical statistics on every rank.
+ *   ams_syncbn_init    allocates this rank's receive buffer and returns its 64-byte cudaIpcMemHandle_t
+ *   ams_syncbn_connect takes the handles of all ranks (rank order, 64 bytes each; exchanged by the host plumbing),
+ *                      maps the peers and switches the exchange on for ams_train_* (never for ams_infer*)
+ *   ams_syncbn_enable  switches it off / on again (e.g. around a rank-local profiling step)
+ *   ams_syncbn_status  synchronises; error != 0 means a peer did not arrive within the timeout (2 s, env
+ *                      AMS_SYNCBN_TIMEOUT_MS) -- the kernels never hang, the step's results are then invalid.
+ * All ranks must run the same sequence of training steps with the same per-rank batch size. */
+int ams_syncbn_init(ams_net* net, int world, int rank, void* out_ipc_handle, int handle_capacity);
+int ams_syncbn_connect(ams_net* net, const void* all_handles, int count);
+int ams_syncbn_enable(ams_net* net, int on);
+int ams_syncbn_status(ams_net* net, unsigned int* out_epoch, unsigned int* out_error);
 
 /* ---- parity hooks */
 int ams_get_logits(ams_net* net, float* host, long long count);       /* low-res `semantic` [n,h,w,num_classes] of the last run */
