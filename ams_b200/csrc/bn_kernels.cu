@@ -124,42 +124,77 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ void syncbn_exchange(SyncBn* sb, long long word_off, double* s, double* q) {
+__device__ __forceinline__ void syncbn_push(SyncBn* sb, int peer, long long slot, unsigned int ep, double s, double q) {
+    const unsigned long long tag = static_cast<unsigned long long>(ep) << 32;
+    unsigned long long* dst = sb->peer[peer] + slot;
+    const unsigned long long w0 = tag | static_cast<unsigned int>(__double2loint(s)), w1 = tag | static_cast<unsigned int>(__double2hiint(s));
+    const unsigned long long w2 = tag | static_cast<unsigned int>(__double2loint(q)), w3 = tag | static_cast<unsigned int>(__double2hiint(q));
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst), "l"(w0) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst + 1), "l"(w1) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst + 2), "l"(w2) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst + 3), "l"(w3) : "memory");
+}
+// poll the 4 words of one source in the LOCAL receive buffer (all four loads in flight per round); false = timed out
+__device__ __forceinline__ bool syncbn_poll(SyncBn* sb, long long slot, unsigned int ep, unsigned long long t0, double* s, double* q) {
+    const unsigned long long* from = sb->peer[sb->rank] + slot;
+    unsigned long long v0, v1, v2, v3;
+    unsigned int spins = 0;
+    for (;;) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v0) : "l"(from) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v1) : "l"(from + 1) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v2) : "l"(from + 2) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v3) : "l"(from + 3) : "memory");
+        if (static_cast<unsigned int>(v0 >> 32) == ep && static_cast<unsigned int>(v1 >> 32) == ep &&
+            static_cast<unsigned int>(v2 >> 32) == ep && static_cast<unsigned int>(v3 >> 32) == ep) break;
+        if ((++spins & 63u) == 0u && global_timer_ns() - t0 > sb->timeout_ns) { atomicExch(&sb->error, 1u); return false; }
+    }
+    *s = __hiloint2double(static_cast<int>(static_cast<unsigned int>(v1)), static_cast<int>(static_cast<unsigned int>(v0)));
+    *q = __hiloint2double(static_cast<int>(static_cast<unsigned int>(v3)), static_cast<int>(static_cast<unsigned int>(v2)));
+    return true;
+}
+// slot of (source rank, word offset) in the receive buffer of the step's epoch parity
+__device__ __forceinline__ long long syncbn_slot(const SyncBn* sb, unsigned int ep, int src, long long word_off) {
+    return (static_cast<long long>(ep & 1u) * sb->world + src) * sb->words_per_src + word_off;
+}
+// one thread per channel does everything (image-pooling BN: two exchanges per step, nothing to parallelise);
+// a[src], b[src] = the pair of every source rank (own values on a timeout: error flag raised)
+__device__ __forceinline__ void syncbn_gather(SyncBn* sb, long long word_off, double s, double q, double* a, double* b) {
     const int world = sb->world, rank = sb->rank;
     const unsigned int ep = sb->epoch;
-    const unsigned long long tag = static_cast<unsigned long long>(ep) << 32;
-    const long long wps = sb->words_per_src;
-    const long long base = static_cast<long long>(ep & 1u) * world * wps + word_off;
-    unsigned long long w[4];
-    w[0] = tag | static_cast<unsigned int>(__double2loint(*s)); w[1] = tag | static_cast<unsigned int>(__double2hiint(*s));
-    w[2] = tag | static_cast<unsigned int>(__double2loint(*q)); w[3] = tag | static_cast<unsigned int>(__double2hiint(*q));
-    for (int p = 0; p < world; ++p) {
-        unsigned long long* dst = sb->peer[(rank + p) % world] + base + static_cast<long long>(rank) * wps;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(dst + k), "l"(w[k]) : "memory");
-    }
+    for (int p = 0; p < world; ++p) syncbn_push(sb, (rank + p) % world, syncbn_slot(sb, ep, rank, word_off), ep, s, q);
+    for (int src = 0; src < world; ++src) { a[src] = s; b[src] = q; }
     if (*reinterpret_cast<volatile unsigned int*>(&sb->error)) return;
     const unsigned long long t0 = global_timer_ns();
-    double S = 0.0, Q = 0.0;
-    for (int src = 0; src < world; ++src) {
-        const unsigned long long* from = sb->peer[rank] + base + static_cast<long long>(src) * wps;
-        unsigned long long v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            unsigned int spins = 0;
-            for (;;) {
-                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(from + k) : "memory");
-                if (static_cast<unsigned int>(v[k] >> 32) == ep) break;
-                if ((++spins & 255u) == 0u && global_timer_ns() - t0 > sb->timeout_ns) {
-                    atomicExch(&sb->error, 1u);
-                    return;
-                }
-            }
+    for (int src = 0; src < world; ++src)
+        if (!syncbn_poll(sb, syncbn_slot(sb, ep, src, word_off), ep, t0, &a[src], &b[src])) return;
+}
+// Block form for the finalize kernels (32 channels x 32 row lanes, every thread of the block calls it): the lead lanes
+// (row lane 0) hold the channel's pair; row lane r < world pushes it to peer r and polls source r, so the exchange costs
+// one NVLink store + one polling round whatever the world size; the lead lanes then add the sources in rank order.
+__device__ __forceinline__ void syncbn_exchange_block(SyncBn* sb, long long layer_off, int c, int C, bool lead, double* s, double* q) {
+    __shared__ double x_s[kSyncBnMaxWorld + 1][32], x_q[kSyncBnMaxWorld + 1][32];
+    __shared__ int x_fail;
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int world = sb->world, rank = sb->rank;
+    const unsigned int ep = sb->epoch;
+    if (threadIdx.x == 0) x_fail = *reinterpret_cast<volatile unsigned int*>(&sb->error) ? 1 : 0;
+    if (lead) { x_s[kSyncBnMaxWorld][cl] = *s; x_q[kSyncBnMaxWorld][cl] = *q; }
+    __syncthreads();
+    if (rl < world && c < C) {
+        const long long off = layer_off + 4LL * c;
+        syncbn_push(sb, rl, syncbn_slot(sb, ep, rank, off), ep, x_s[kSyncBnMaxWorld][cl], x_q[kSyncBnMaxWorld][cl]);
+        if (!x_fail) {
+            double a = 0.0, b = 0.0;
+            if (!syncbn_poll(sb, syncbn_slot(sb, ep, rl, off), ep, global_timer_ns(), &a, &b)) atomicExch(&x_fail, 1);
+            x_s[rl][cl] = a; x_q[rl][cl] = b;
         }
-        S += __hiloint2double(static_cast<int>(static_cast<unsigned int>(v[1])), static_cast<int>(static_cast<unsigned int>(v[0])));
-        Q += __hiloint2double(static_cast<int>(static_cast<unsigned int>(v[3])), static_cast<int>(static_cast<unsigned int>(v[2])));
     }
-    *s = S; *q = Q;
+    __syncthreads();
+    if (lead && !x_fail) {
+        double S = 0.0, Q = 0.0;
+        for (int src = 0; src < world; ++src) { S += x_s[src][cl]; Q += x_q[src][cl]; }
+        *s = S; *q = Q;
+    }
 }
 __global__ void syncbn_begin_step_kernel(SyncBn* sb) {
     pdl_entry();
@@ -175,9 +210,10 @@ bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, in
     pdl_entry();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, q;
-    if (!finalize_sums(partial, chunks, L.C, c, &s, &q)) return;
+    const bool lead = finalize_sums(partial, chunks, L.C, c, &s, &q);
     double n = static_cast<double>(L.M);
-    if (L.sync) { syncbn_exchange(L.sync, L.xoff_fwd + 4LL * c, &s, &q); n *= L.sync->world; }
+    if (L.sync) { syncbn_exchange_block(L.sync, L.xoff_fwd, c, L.C, lead, &s, &q); n *= L.sync->world; }
+    if (!lead) return;
     const double mean = s / n;
     double var = q / n - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -348,17 +384,15 @@ bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L
     pdl_entry();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s1, sz;
-    if (!finalize_sums(partial, chunks, L.C, c, &s1, &sz)) return;
-    const double mean = L.mean[c], rstd = L.rstd[c], gamma = L.gamma[c];
+    const bool lead = finalize_sums(partial, chunks, L.C, c, &s1, &sz);
+    const double s1_local = s1, sz_local = sz;
     double n = static_cast<double>(L.M);
-    double s2 = rstd * (sz - mean * s1);                 // sum g * xhat
-    d_gamma[c] = static_cast<float>(s2);                 // LOCAL sums: the gradient allreduce adds the ranks
-    d_beta[c] = static_cast<float>(s1);
-    if (L.sync) {
-        syncbn_exchange(L.sync, L.xoff_bwd + 4LL * c, &s1, &sz);
-        n *= L.sync->world;
-        s2 = rstd * (sz - mean * s1);
-    }
+    if (L.sync) { syncbn_exchange_block(L.sync, L.xoff_bwd, c, L.C, lead, &s1, &sz); n *= L.sync->world; }
+    if (!lead) return;
+    const double mean = L.mean[c], rstd = L.rstd[c], gamma = L.gamma[c];
+    d_gamma[c] = static_cast<float>(rstd * (sz_local - mean * s1_local));    // LOCAL sums: the gradient allreduce adds the ranks
+    d_beta[c] = static_cast<float>(s1_local);
+    const double s2 = rstd * (sz - mean * s1);           // sum g * xhat over the (global) batch
     const double A = gamma * rstd;
     const double B = -gamma * rstd * rstd * s2 / n;
     const double Cc = -gamma * rstd * (s1 / n - mean * rstd * s2 / n);
@@ -518,12 +552,18 @@ imgpool_bn_kernel(ImgPoolFwd a) {
         for (int n = 0; n < N; ++n) s += a.z[n * Cm + co];
         double mean, var;
         if (a.bn.sync) {
-            // global batch: exchange (sum z, sum z^2); fp64 products of fp32 values are exact
-            for (int n = 0; n < N; ++n) { const double v = a.z[n * Cm + co]; q += v * v; }
-            syncbn_exchange(a.bn.sync, a.bn.xoff_fwd + 4LL * co, &s, &q);
-            cnt *= a.bn.sync->world;
-            mean = s / cnt;
-            var = fmax(q / cnt - mean * mean, 0.0);
+            // global batch: every rank's (sum, centred sum of squares) -> pooled mean / variance (Chan et al.)
+            const double mean_l = s / N;
+            for (int n = 0; n < N; ++n) { const double d = a.z[n * Cm + co] - mean_l; q += d * d; }
+            double ss[kSyncBnMaxWorld], qq[kSyncBnMaxWorld];
+            syncbn_gather(a.bn.sync, a.bn.xoff_fwd + 4LL * co, s, q, ss, qq);
+            const int world = a.bn.sync->world;
+            cnt *= world;
+            double S = 0.0, M2 = 0.0;
+            for (int r = 0; r < world; ++r) S += ss[r];
+            mean = S / cnt;
+            for (int r = 0; r < world; ++r) { const double d = ss[r] / N - mean; M2 += qq[r] + N * d * d; }
+            var = M2 / cnt;
         } else {
             mean = s / N;
             for (int n = 0; n < N; ++n) { const double d = a.z[n * Cm + co] - mean; q += d * d; }
@@ -563,7 +603,14 @@ imgpool_bn_bwd_kernel(ImgPoolFwd a, float* __restrict__ dact, float* __restrict_
     d_gamma[co] = static_cast<float>(s2);                // LOCAL sums: the gradient allreduce adds the ranks
     d_beta[co] = static_cast<float>(s1);
     double cnt = N;
-    if (a.bn.sync) { syncbn_exchange(a.bn.sync, a.bn.xoff_bwd + 4LL * co, &s1, &s2); cnt *= a.bn.sync->world; }
+    if (a.bn.sync) {
+        double ss[kSyncBnMaxWorld], qq[kSyncBnMaxWorld];
+        syncbn_gather(a.bn.sync, a.bn.xoff_bwd + 4LL * co, s1, s2, ss, qq);
+        const int world = a.bn.sync->world;
+        cnt *= world;
+        s1 = 0.0; s2 = 0.0;
+        for (int r = 0; r < world; ++r) { s1 += ss[r]; s2 += qq[r]; }
+    }
     for (int n = 0; n < N; ++n) {
         const double xh = (a.z[n * Cm + co] - mean) * rstd;
         dact[n * Cm + co] = static_cast<float>(gamma * rstd * (dact[n * Cm + co] - s1 / cnt - xh * s2 / cnt));

@@ -61,7 +61,7 @@ class DataParallelStudent:
     peer memory (ams_syncbn_*), which makes the job equivalent to the reference's single-process step on the global
     batch; sync_bn=False keeps per-replica statistics (faster, a documented deviation)."""
 
-    def __init__(self, student, group=None, sync_bn=False):
+    def __init__(self, student, group=None, sync_bn=False, strict=True):
         self.student = student
         self.group = group
         ptr, n = student.gradient_arena()
@@ -72,12 +72,26 @@ class DataParallelStudent:
         self._pending = 0
         self.sync_bn = False
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.sync_bn_error = None
         if sync_bn and self.world > 1:
+            # strict=False: if peer memory cannot be mapped on ANY rank (no P2P / IPC in this container) all ranks agree
+            # to fall back to per-replica statistics and say so in sync_bn_error
             rank = dist.get_rank(group)
             handles = exchange_ipc_handles(student.syncbn_init(self.world, rank), group)
-            student.syncbn_connect(handles)
-            dist.barrier(group=group)             # every rank has mapped every (zeroed) receive buffer before the first push
-            self.sync_bn = True
+            try:
+                student.syncbn_connect(handles)
+            except Exception as e:                       # noqa: BLE001 -- reported, and re-raised when strict
+                self.sync_bn_error = str(e)
+            okf = torch.tensor([0 if self.sync_bn_error else 1], device='cuda')
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN, group=group)     # also: every rank has mapped every zeroed buffer
+            if int(okf.item()) == 1:
+                self.sync_bn = True
+            else:
+                if not self.sync_bn_error:
+                    student.syncbn_enable(False)
+                    self.sync_bn_error = 'a peer rank could not map the receive buffers'
+                if strict:
+                    raise RuntimeError('SyncBN peer-memory setup failed: ' + self.sync_bn_error)
 
     def _slot(self):
         if self._pending >= self._loss_np.size:

@@ -211,7 +211,7 @@ def run_ours(args, rank, world, local_rank):
     dp = None
     if world > 1:
         from ams_b200.parallel import DataParallelStudent
-        dp = DataParallelStudent(st, sync_bn=bool(args.sync_bn))
+        dp = DataParallelStudent(st, sync_bn=bool(args.sync_bn), strict=False)
     # steps are enqueued without a host round trip (the reference only prints the loss, SemanticNetwork.py:261): the loss
     # of step i is copied to its page-locked slot when the stream gets there and read after the phase's synchronisation
     loss_t, loss_np = pinned((max(K, Wm) + 1,), torch.float32)
@@ -434,7 +434,9 @@ def run_ours(args, rank, world, local_rank):
                        'l2': 'no explicit flush: each step streams ~3 GB of activations (>> 126 MB L2) and batches are distinct',
                        'delta_bytes': delta_len, 'kept_coordinates': kept,
                        'batchnorm': ('global batch: statistics summed over ranks through NVLink peer memory inside the BN kernels'
-                                     if (dp is not None and dp.sync_bn) else ('per replica' if dp is not None else 'single process')),
+                                     if (dp is not None and dp.sync_bn) else
+                                     ('per replica' + (' (peer-memory setup failed: %s)' % dp.sync_bn_error if dp.sync_bn_error else '')
+                                      if dp is not None else 'single process')),
                        'host_sync': 'none inside the phase: losses land in page-locked slots, read after the phase'},
             'e2e': {'value': e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d_step, 'd2h_bytes_per_step': 4 + delta_len2 // K,
                     'ms_per_step': ms_e2e / K},
