@@ -543,7 +543,7 @@ int ams_syncbn_init(ams_net* h, int world, int rank, void* out_ipc_handle, int h
     sb = SyncBn{};
     sb.world = world; sb.rank = rank; sb.epoch = 0; sb.error = 0;
     sb.words_per_src = net->n_bnpool / 6 * 8;
-    sb.timeout_ns = 2000000000ull;
+    sb.timeout_ns = 10000000000ull;
     if (const char* e = getenv("AMS_SYNCBN_TIMEOUT_MS")) sb.timeout_ns = static_cast<unsigned long long>(atoll(e)) * 1000000ull;
     const size_t bytes = static_cast<size_t>(2) * world * sb.words_per_src * sizeof(unsigned long long);
     AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&net->syncbn_recv), bytes));

@@ -33,6 +33,10 @@ def allreduce_step_terms(grad, n_valid, loss_sum, group=None):
     return 1.0 / nv, ls / nv
 
 
+class SyncBnError(RuntimeError):
+    """A rank did not reach the same BatchNorm layer within the timeout (raised on EVERY rank of the group)."""
+
+
 class _DeviceArena:
     """Zero-copy torch view of a device buffer owned by libams_b200 (CUDA array interface)."""
 
@@ -114,12 +118,20 @@ class DataParallelStudent:
         self.student.synchronize()
         out = [float(x) for x in self._loss_np[:self._pending]]
         self._pending = 0
-        if self.sync_bn:
+        if self.sync_bn and self.world > 1:
             _, err = self.student.syncbn_status()
-            if err:
-                raise RuntimeError('SyncBN exchange timed out: a rank did not reach the same BatchNorm layer (ranks must run '
-                                   'the same sequence of training steps)')
+            flag = torch.tensor([int(err)], dtype=torch.int32, device='cuda')
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)      # every rank learns about it: same control flow
+            if int(flag.item()):
+                raise SyncBnError('SyncBN exchange timed out: a rank did not reach the same BatchNorm layer (ranks must run '
+                                  'the same sequence of training steps); the statistics of this phase are invalid')
         return out
+
+    def disable_sync_bn(self, reason):
+        """Fall back to per-replica statistics (call on every rank, e.g. after SyncBnError)."""
+        self.student.syncbn_enable(False)
+        self.sync_bn = False
+        self.sync_bn_error = reason
 
     def train_step(self, lr, masked):
         """Synchronous form: returns this step's global mean loss."""

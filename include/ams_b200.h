@@ -146,7 +146,7 @@ int ams_apply_optimizer(ams_net* net, float lr, int masked, float grad_scale);
  *   ams_syncbn_connect takes the handles of all ranks (rank order, 64 bytes each; exchanged by the host plumbing),
  *                      maps the peers and switches the exchange on for ams_train_* (never for ams_infer*)
  *   ams_syncbn_enable  switches it off / on again (e.g. around a rank-local profiling step)
- *   ams_syncbn_status  synchronises; error != 0 means a peer did not arrive within the timeout (2 s, env
+ *   ams_syncbn_status  synchronises; error != 0 means a peer did not arrive within the timeout (10 s, env
  *                      AMS_SYNCBN_TIMEOUT_MS) -- the kernels never hang, the step's results are then invalid.
  * All ranks must run the same sequence of training steps with the same per-rank batch size. */
 int ams_syncbn_init(ams_net* net, int world, int rank, void* out_ipc_handle, int handle_capacity);

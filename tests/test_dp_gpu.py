@@ -23,7 +23,8 @@ def _free_port():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs on one box')
 def test_dp_syncbn_matches_single_process_global_batch():
-    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+    world = 8 if torch.cuda.device_count() >= 8 else (4 if torch.cuda.device_count() >= 4 else 2)      # powers of two: exact doubling
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
            '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dp_worker.py')]
     env = dict(os.environ, AMS_SYNCBN_TIMEOUT_MS='5000')
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
