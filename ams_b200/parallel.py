@@ -65,13 +65,19 @@ class DataParallelStudent:
     peer memory (ams_syncbn_*), which makes the job equivalent to the reference's single-process step on the global
     batch; sync_bn=False keeps per-replica statistics (faster, a documented deviation)."""
 
-    def __init__(self, student, group=None, sync_bn=False, strict=True):
+    def __init__(self, student, group=None, sync_bn=False, strict=True, tensors=None):
         self.student = student
         self.group = group
-        ptr, n = student.gradient_arena()
-        self.grad = torch.as_tensor(_DeviceArena(ptr, n), device='cuda')
-        self.terms = torch.as_tensor(_DeviceArena(student.step_terms_ptr(), 2, '<f8'), device='cuda')
-        self._loss_slots = torch.zeros(256, dtype=torch.float32).pin_memory()
+        if tensors is not None:
+            # (gradient arena, terms) supplied by the caller: the gloo / CPU test of this class's host logic
+            self.grad, self.terms = tensors
+        else:
+            ptr, n = student.gradient_arena()
+            self.grad = torch.as_tensor(_DeviceArena(ptr, n), device='cuda')
+            self.terms = torch.as_tensor(_DeviceArena(student.step_terms_ptr(), 2, '<f8'), device='cuda')
+        self._loss_slots = torch.zeros(256, dtype=torch.float32)
+        if torch.cuda.is_available():
+            self._loss_slots = self._loss_slots.pin_memory()
         self._loss_np = self._loss_slots.numpy()
         self._pending = 0
         self.sync_bn = False

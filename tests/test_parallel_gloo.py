@@ -71,6 +71,62 @@ def test_two_rank_exchange_equals_single_process(tmp_path):
     assert np.abs(r0 - ref).max() < 2e-5 * denom
 
 
+class _StubStudent:
+    """Host-side stand-in for `Student`: the 'device' arena and terms are CPU tensors, the kernels are two lines."""
+
+    def __init__(self, rank):
+        self.rank = rank
+        self.grad = torch.zeros(6, dtype=torch.float32)
+        self.terms = torch.zeros(2, dtype=torch.float64)
+        self.params = torch.ones(6, dtype=torch.float32)
+        self.step = 0
+
+    def train_forward_backward_async(self):
+        self.step += 1
+        self.grad[:] = torch.arange(6, dtype=torch.float32) * (self.rank + 1) * self.step
+        self.terms[0], self.terms[1] = 10.0 * (self.rank + 1), 3.0 * (self.rank + 1) * self.step
+
+    def apply_optimizer_device(self, lr, masked, loss_out):
+        scale = 1.0 / float(self.terms[0]) if float(self.terms[0]) > 0 else 0.0
+        self.params -= lr * self.grad * scale
+        loss_out[0] = float(self.terms[1] / self.terms[0])
+
+    def synchronize(self):
+        pass
+
+
+def _dp_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from ams_b200.parallel import DataParallelStudent
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    st = _StubStudent(rank)
+    dp = DataParallelStudent(st, tensors=(st.grad, st.terms))
+    for _ in range(3):
+        dp.train_step_async(0.5, False)
+    losses = dp.losses()
+    assert dp.losses() == []                                        # drained
+    one = dp.train_step(0.5, False)                                 # synchronous form returns this step's loss
+    np.save(os.path.join(out_dir, 'dp%d.npy' % rank), np.concatenate([st.params.numpy(), np.array(losses + [one], np.float32)]))
+    dp.close()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_student_host_logic(tmp_path):
+    """order of the exchange step (backward -> allreduce(grad), allreduce(terms) -> Adam reading the global terms), loss
+    slots filled per step and drained by losses(), identical state on both ranks"""
+    world = 2
+    mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (np.load(os.path.join(tmp_path, 'dp%d.npy' % r)) for r in range(2))
+    assert np.array_equal(a, b)
+    # global terms: n = 10 + 20, loss_sum = 3 s + 6 s -> loss = 0.3 s; gradient sum = arange * 3 s, scaled by 1/30
+    want_p = np.ones(6, np.float32)
+    for s_ in (1, 2, 3, 4):
+        want_p = want_p - np.float32(0.5) * (np.arange(6, dtype=np.float32) * 3 * s_) * np.float32(1.0 / 30.0)
+    assert np.allclose(a[:6], want_p, rtol=1e-6)
+    assert np.allclose(a[6:], [0.3, 0.6, 0.9, 1.2], rtol=1e-6)
+
+
 def test_shard_streams_partition():
     from ams_b200.parallel import shard_streams
     for world in (1, 2, 4, 8):
