@@ -21,8 +21,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 H, W, B = 192, 384, 2
-CLASSES = list(range(19))
 LR = 1e-3
+# argv[1]: 'cityscapes' (19-class graph, every class) or 'pascalvoc2012' (config C4: 21-class graph, BN decay 0.98,
+# class vector of reference experiment 40, exp_configs.py:152-154)
+TAG = sys.argv[1] if len(sys.argv) > 1 else 'cityscapes'
+NUM_CLASSES = 21 if TAG == 'pascalvoc2012' else 19
+CLASSES = [0, 7, 12, 15] if TAG == 'pascalvoc2012' else list(range(19))
 
 
 def rel(a, b):
@@ -45,14 +49,14 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
 
-    ckpt = synthetic_checkpoint('cityscapes', 1)
+    ckpt = synthetic_checkpoint(TAG, 1)
     steps = 4
     frames = [synthetic_frames(B * world, H, W, seed=10 + i) for i in range(steps)]
     labels = [synthetic_labels(B * world, H, W, seed=10 + i, block=16) for i in range(steps)]
     moving_names = [k for k in ckpt if k.endswith('moving_mean:0') or k.endswith('moving_variance:0')]
 
     def make():
-        st = Student(19, H, W, CLASSES, device=local, queue_capacity=steps + 2)
+        st = Student(NUM_CLASSES, H, W, CLASSES, device=local, queue_capacity=steps + 2)
         st.set_stream(stream.cuda_stream)
         for k, v in ckpt.items():
             st.set_tensor(k, v)
@@ -98,7 +102,7 @@ def main():
         n_bad_g = int(np.count_nonzero(g_dup != np.float32(world) * g1))
         n_bad_m = int(np.count_nonzero(mv_dup[is_mean] != mv1[is_mean]))
         loss_same = (loss_dup == ls1 / nv1)
-        print('[dp] duplicate frames on %d ranks vs one GPU: %d of %d gradient coordinates differ, %d of %d moving means '
+        print('[dp] ' + TAG + ': duplicate frames on %d ranks vs one GPU: %d of %d gradient coordinates differ, %d of %d moving means '
               'differ, loss identical: %s' % (world, n_bad_g, g1.size, n_bad_m, int(is_mean.sum()), loss_same), flush=True)
         ok &= n_bad_g == 0 and n_bad_m == 0 and bool(loss_same)
         ref = make()
@@ -109,7 +113,7 @@ def main():
         ref.close()
         e_mv, e_g = rel(mv_sync, mv_ref), rel(g_sync, g_ref)
         r_mv, r_g = rel(mv_rep, mv_ref), rel(g_rep, g_ref)
-        print('[dp] global batch %d @ %dx%d on %d GPUs vs one GPU: moving stats rel-L2 %.3e (per-replica BN: %.3e), '
+        print('[dp] ' + TAG + ': global batch %d @ %dx%d on %d GPUs vs one GPU: moving stats rel-L2 %.3e (per-replica BN: %.3e), '
               'gradients rel-L2 %.3e (per-replica BN: %.3e), loss %.6f vs %.6f (per-replica %.6f)'
               % (B * world, H, W, world, e_mv, r_mv, e_g, r_g, loss_sync, loss_ref, loss_rep), flush=True)
         ok &= e_mv < 2e-3 and abs(loss_sync - loss_ref) < 1e-3 * abs(loss_ref)

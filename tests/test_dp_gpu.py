@@ -22,10 +22,11 @@ def _free_port():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs on one box')
-def test_dp_syncbn_matches_single_process_global_batch():
+@pytest.mark.parametrize('tag', ['cityscapes', 'pascalvoc2012'])
+def test_dp_syncbn_matches_single_process_global_batch(tag):
     world = 8 if torch.cuda.device_count() >= 8 else (4 if torch.cuda.device_count() >= 4 else 2)      # powers of two: exact doubling
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world), '--master-addr', '127.0.0.1',
-           '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dp_worker.py')]
+           '--master-port', str(_free_port()), os.path.join(ROOT, 'tests', 'dp_worker.py'), tag]
     env = dict(os.environ, AMS_SYNCBN_TIMEOUT_MS='5000')
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     for line in r.stdout.splitlines():
