@@ -6,18 +6,27 @@
 // checkpoints/*/model.meta and their gradients; inference-mode patch BN of utils/graph_utils.py:362-369.
 #include "kernels.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace ams {
 namespace {
 
 constexpr int kRedThreads = 256;
 constexpr int kFlush = 16;          // fp32 run length before flushing into fp64
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// Measured (tools/ab_step.py, gpurun_out/ab_r1*.jsonl): 2 chunks per SM with 4 rows of each tensor in flight per thread
+// beats 6 chunks x 2 rows by 0.2 ms per step (5.90 -> 5.71 ms) -- every chunk costs a [2][C] fp64 partial row that is
+// written here and read again by the finalize, so memory-level parallelism has to come from the loads, not from CTAs.
+static const int kRedChunksPerSM = env_int("AMS_RED_CHUNKS_PER_SM", 2);
+static const int kBwdRedUnroll = env_int("AMS_BWD_RED_UNROLL", 4);
+
 int red_chunks(long long M, int C) {
-    // enough blocks to fill the machine (several CTAs per SM: these passes are latency-bound on the small layers) while
-    // every thread still walks >= 8 rows; the finalize reads the partial rows coalesced, so many rows are cheap
+    // enough blocks to fill the machine while every thread still walks >= 8 rows (see kRedChunksPerSM)
     const int c8 = C / 8;
     const int rows_per_block = std::max(1, kRedThreads / std::min(c8, kRedThreads));
-    const long long want = std::min<long long>(6 * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8));
+    const long long want = std::min<long long>(static_cast<long long>(kRedChunksPerSM) * kNumSMs, M / (static_cast<long long>(rows_per_block) * 8));
     return static_cast<int>(std::max<long long>(1, want));
 }
 
@@ -301,6 +310,8 @@ __device__ __forceinline__ float act_mask(float g, float yhat, int act) {
     return g;
 }
 
+// U = rows in flight per thread and tensor (2 or 4 independent 128-bit loads each of dy and z); HAS2 = a second gradient
+template <int U, bool HAS2>
 __global__ void __launch_bounds__(kRedThreads)
 bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
                      const float* __restrict__ scale, const float* __restrict__ shift, int act, long long M, int C,
@@ -325,28 +336,28 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                 float fs[8], fq[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { fs[q] = 0.f; fq[q] = 0.f; }
-                for (int it = 0; it < kFlush / 2 && r < r_end; ++it) {
-                    uint4 rg[2], rz[2], rg2[2];
+                for (int it = 0; it < kFlush / U && r < r_end; ++it) {
+                    uint4 rg[U], rz[U], rg2[HAS2 ? U : 1];
                     int nv = 0;
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         const long long rr = r + u * RB;
                         if (rr < r_end) {
                             rg[u] = ldg_stream(dy + rr * C + c8 * 8);
                             rz[u] = ldg_stream(z + rr * C + c8 * 8);
-                            if (dy2) rg2[u] = ldg_stream(dy2 + rr * C + c8 * 8);
+                            if (HAS2) rg2[HAS2 ? u : 0] = ldg_stream(dy2 + rr * C + c8 * 8);
                             nv = u + 1;
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         if (u < nv) {
                             float g[8], v[8];
                             unpack8(rg[u], g);
                             unpack8(rz[u], v);
-                            if (dy2) {
+                            if (HAS2) {
                                 float g2[8];
-                                unpack8(rg2[u], g2);
+                                unpack8(rg2[HAS2 ? u : 0], g2);
 #pragma unroll
                                 for (int q = 0; q < 8; ++q) g[q] += g2[q];
                             }
@@ -358,7 +369,7 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                             }
                         }
                     }
-                    r += 2 * RB;
+                    r += U * RB;
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { ds[q] += fs[q]; dq[q] += fq[q]; }
@@ -636,6 +647,14 @@ static size_t red_smem(int C) {
     return static_cast<size_t>(kRedThreads / tpr) * 2 * C * sizeof(double);
 }
 
+static int launch_bwd_reduce(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, int chunks, long long rpc,
+                             size_t smem, double* ws, cudaStream_t s) {
+    if (dy2) AMS_LAUNCH((bn_bwd_reduce_kernel<2, true>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    else if (kBwdRedUnroll == 4) AMS_LAUNCH((bn_bwd_reduce_kernel<4, false>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    else AMS_LAUNCH((bn_bwd_reduce_kernel<2, false>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    return 0;
+}
+
 int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double* ws, cudaStream_t s) {
     AMS_REQUIRE(L.C % 8 == 0, "BN channels must be a multiple of 8");
     const int chunks = red_chunks(L.M, L.C);
@@ -671,7 +690,7 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     const long long rpc = ceil_div_ll(L.M, chunks);
     const size_t smem = red_smem(L.C);
     float* coef = reinterpret_cast<float*>(ws + static_cast<size_t>(chunks) * 2 * L.C);
-    AMS_LAUNCH((bn_bwd_reduce_kernel), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    if (launch_bwd_reduce(dy, dy2, z, L, act, chunks, rpc, smem, ws, s)) return -1;
     AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, d_gamma, d_beta, coef);
     const int rib = 256 / std::min(L.C / 8, 256);
     AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(L.M, rib * kEwRows)), 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, static_cast<int>(L.M), L.C, dz_out);
@@ -682,7 +701,7 @@ int bn_backward_reduce(const bf16* dy, const bf16* z, const BnLayer& L, int act,
                        double* ws, cudaStream_t s) {
     const int chunks = red_chunks(L.M, L.C);
     const long long rpc = ceil_div_ll(L.M, chunks);
-    AMS_LAUNCH((bn_bwd_reduce_kernel), chunks, kRedThreads, red_smem(L.C), s, dy, nullptr, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    if (launch_bwd_reduce(dy, nullptr, z, L, act, chunks, rpc, red_smem(L.C), ws, s)) return -1;
     AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, d_gamma, d_beta, coef);
     return 0;
 }

@@ -112,8 +112,8 @@ __device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restric
     }
 }
 
-template <int S, int D, int CB>
-__global__ void __launch_bounds__(dw_threads(CB), 3)
+template <int S, int D, int CB, int MINB>
+__global__ void __launch_bounds__(dw_threads(CB), MINB)
 dw_fwd_tiled_kernel(const DwFwdParams p) {
     pdl_entry();
     extern __shared__ __align__(16) uint8_t smem[];
@@ -267,15 +267,22 @@ DwTile pick_tile(const Conv2dGeom& g, size_t smem_cap) {
 static size_t env_kb(const char* name, size_t dflt_kb) { const char* e = getenv(name); return (e ? size_t(atoi(e)) : dflt_kb) * 1024; }
 static const size_t kFwdSmemCap = env_kb("AMS_DWF_SMEM_KB", 72);
 
-template <int S, int D, int CB>
-int launch_fwd(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
+// resident CTAs per SM the forward kernel is compiled for: 3 (80 registers, a few spills) or 2 (128 registers, none)
+static const int kFwdMinBlocks = [] { const char* e = getenv("AMS_DWF_MINB"); return (e && atoi(e) == 2) ? 2 : 3; }();
+
+template <int S, int D, int CB, int MINB>
+int launch_fwd_mb(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
-        AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_fwd_tiled_kernel<S, D, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute(dw_fwd_tiled_kernel<S, D, CB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr = true;
     }
-    AMS_LAUNCH((dw_fwd_tiled_kernel<S, D, CB>), static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s, p);
+    AMS_LAUNCH((dw_fwd_tiled_kernel<S, D, CB, MINB>), static_cast<unsigned>(t.blocks), dw_threads(CB), t.smem, s, p);
     return 0;
+}
+template <int S, int D, int CB>
+int launch_fwd(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
+    return kFwdMinBlocks == 2 ? launch_fwd_mb<S, D, CB, 2>(p, t, s) : launch_fwd_mb<S, D, CB, 3>(p, t, s);
 }
 template <int S, int D>
 int launch_fwd_cb(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
