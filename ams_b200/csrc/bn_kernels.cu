@@ -244,7 +244,8 @@ bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, in
 
 // Elementwise passes: a thread owns one 8-channel group (its per-channel parameters live in registers) and walks kEwRows
 // rows of the block's row range with all loads issued before the arithmetic; block = min(C/8, 256) channel groups x rows.
-constexpr int kEwRows = 4;
+static const int kEwRowsKnob = env_int("AMS_EW_ROWS", 4);      // rows per thread of the elementwise passes: 2, 4 or 8
+template <int kEwRows>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                 const bf16* __restrict__ residual, bf16* __restrict__ y, int M, int C) {
@@ -417,6 +418,7 @@ __device__ __forceinline__ void load8f(const float* p, float* o) {
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
+template <int kEwRows>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
@@ -647,9 +649,20 @@ static size_t red_smem(int C) {
     return static_cast<size_t>(kRedThreads / tpr) * 2 * C * sizeof(double);
 }
 
+static int launch_bwd_apply(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, const float* coef, int act, int rib,
+                            bf16* dz_out, cudaStream_t s) {
+    const int rows = kEwRowsKnob == 2 ? 2 : (kEwRowsKnob == 8 ? 8 : 4);
+    const int grid = static_cast<int>(ceil_div_ll(L.M, rib * rows)), M = static_cast<int>(L.M);
+    if (rows == 2) AMS_LAUNCH((bn_bwd_apply_kernel<2>), grid, 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, M, L.C, dz_out);
+    else if (rows == 8) AMS_LAUNCH((bn_bwd_apply_kernel<8>), grid, 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, M, L.C, dz_out);
+    else AMS_LAUNCH((bn_bwd_apply_kernel<4>), grid, 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, M, L.C, dz_out);
+    return 0;
+}
+
 static int launch_bwd_reduce(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, int chunks, long long rpc,
                              size_t smem, double* ws, cudaStream_t s) {
     if (dy2) AMS_LAUNCH((bn_bwd_reduce_kernel<2, true>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
+    else if (kBwdRedUnroll == 8) AMS_LAUNCH((bn_bwd_reduce_kernel<8, false>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     else if (kBwdRedUnroll == 4) AMS_LAUNCH((bn_bwd_reduce_kernel<4, false>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     else AMS_LAUNCH((bn_bwd_reduce_kernel<2, false>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     return 0;
@@ -674,7 +687,11 @@ int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, in
 int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y, long long M,
              int C, cudaStream_t s) {
     const int rib = 256 / std::min(C / 8, 256);
-    AMS_LAUNCH((bn_apply_kernel), static_cast<int>(ceil_div_ll(M, rib * kEwRows)), 256, 0, s, z, scale, shift, act, residual, y, static_cast<int>(M), C);
+    const int rows = kEwRowsKnob == 2 ? 2 : (kEwRowsKnob == 8 ? 8 : 4);
+    const int grid = static_cast<int>(ceil_div_ll(M, rib * rows));
+    if (rows == 2) AMS_LAUNCH((bn_apply_kernel<2>), grid, 256, 0, s, z, scale, shift, act, residual, y, static_cast<int>(M), C);
+    else if (rows == 8) AMS_LAUNCH((bn_apply_kernel<8>), grid, 256, 0, s, z, scale, shift, act, residual, y, static_cast<int>(M), C);
+    else AMS_LAUNCH((bn_apply_kernel<4>), grid, 256, 0, s, z, scale, shift, act, residual, y, static_cast<int>(M), C);
     return 0;
 }
 
@@ -693,7 +710,7 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     if (launch_bwd_reduce(dy, dy2, z, L, act, chunks, rpc, smem, ws, s)) return -1;
     AMS_LAUNCH((bn_bwd_finalize_kernel), ceil_div(L.C, 32), 32 * kFinRows, 0, s, ws, chunks, L, d_gamma, d_beta, coef);
     const int rib = 256 / std::min(L.C / 8, 256);
-    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(L.M, rib * kEwRows)), 256, 0, s, dy, dy2, z, L.scale, L.shift, coef, act, static_cast<int>(L.M), L.C, dz_out);
+    if (launch_bwd_apply(dy, dy2, z, L, coef, act, rib, dz_out, s)) return -1;
     return 0;
 }
 
@@ -714,7 +731,7 @@ int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer
 
 int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s) {
     const int rib = 256 / std::min(L.C / 8, 256);
-    AMS_LAUNCH((bn_bwd_apply_kernel), static_cast<int>(ceil_div_ll(L.M, rib * kEwRows)), 256, 0, s, dy_masked, nullptr, z, L.scale, L.shift, coef, 0, static_cast<int>(L.M), L.C, dz_out);
+    if (launch_bwd_apply(dy_masked, nullptr, z, L, coef, 0, rib, dz_out, s)) return -1;
     return 0;
 }
 
