@@ -80,6 +80,7 @@ class DataParallelStudent:
             self._loss_slots = self._loss_slots.pin_memory()
         self._loss_np = self._loss_slots.numpy()
         self._pending = 0
+        self._backlog = []              # losses drained early because the slot ring was full
         self.sync_bn = False
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.sync_bn_error = None
@@ -105,7 +106,7 @@ class DataParallelStudent:
 
     def _slot(self):
         if self._pending >= self._loss_np.size:
-            self.losses()
+            self._backlog = self.losses()            # ring full: synchronise once, keep what was read
         i = self._pending
         self._pending += 1
         return self._loss_np[i:i + 1]
@@ -122,8 +123,9 @@ class DataParallelStudent:
 
     def losses(self):
         self.student.synchronize()
-        out = [float(x) for x in self._loss_np[:self._pending]]
+        out = self._backlog + [float(x) for x in self._loss_np[:self._pending]]
         self._pending = 0
+        self._backlog = []
         if self.sync_bn and self.world > 1:
             _, err = self.student.syncbn_status()
             flag = torch.tensor([int(err)], dtype=torch.int32, device='cuda')
