@@ -207,3 +207,46 @@ def test_resize_oracle_matches_cv2_live_when_available():
         assert np.array_equal(ro.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), (sh, sw, dh, dw)
         assert np.array_equal(ro.resize_nearest_u8(lab, dw, dh), cv2.resize(lab, (dw, dh), interpolation=cv2.INTER_NEAREST))
         assert np.array_equal(ro.ingest_frame(img, dh, dw), cv2.cvtColor(cv2.resize(img, (dw, dh)), cv2.COLOR_BGR2RGB))
+
+
+def test_syncbn_exchange_arithmetic_equals_single_process_batchnorm():
+    """The cross-rank arithmetic of the data-parallel BN kernels (oracle/syncbn_oracle.py restates it) against torch
+    autograd on the concatenated batch: statistics, Bessel-corrected variance, dz on every shard, d_gamma / d_beta after
+    the gradient allreduce."""
+    import syncbn_oracle as sb
+    rng = np.random.default_rng(3)
+    world, rows, C, eps = 4, 37, 24, 1e-3
+    z = [rng.normal(0.3, 1.7, size=(rows, C)).astype(np.float32) for _ in range(world)]
+    dy = [rng.normal(0.0, 1.0, size=(rows, C)).astype(np.float32) for _ in range(world)]
+    gamma = rng.uniform(0.5, 1.5, size=C).astype(np.float32)
+    beta = rng.normal(0, 0.1, size=C).astype(np.float32)
+    mean, var, rstd, unb = sb.global_stats([sb.forward_sums(x) for x in z], rows, eps)
+    zt = torch.tensor(np.concatenate(z), dtype=torch.float64, requires_grad=True)
+    gt = torch.tensor(gamma, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+    m = zt.mean(0)
+    v = ((zt - m) ** 2).mean(0)
+    y = (zt - m) / torch.sqrt(v + eps) * gt + bt
+    y.backward(torch.tensor(np.concatenate(dy), dtype=torch.float64))
+    n = rows * world
+    assert np.allclose(mean, m.detach().numpy(), rtol=1e-6, atol=1e-7)
+    assert np.allclose(var, v.detach().numpy(), rtol=1e-5) and np.allclose(unb, v.detach().numpy() * n / (n - 1), rtol=1e-5)
+    pairs = [sb.backward_sums(g, x) for g, x in zip(dy, z)]
+    dgs, dbs = np.zeros(C, np.float64), np.zeros(C, np.float64)
+    for r in range(world):
+        A, B, Cc, dg, db = sb.backward_coefficients(pairs, pairs[r], rows, mean, rstd, gamma)
+        dz = A * dy[r] + B * z[r] + Cc
+        assert np.allclose(dz, zt.grad.numpy()[r * rows:(r + 1) * rows], rtol=2e-4, atol=2e-5)
+        dgs += dg
+        dbs += db
+    assert np.allclose(dgs, gt.grad.numpy(), rtol=2e-4, atol=1e-4) and np.allclose(dbs, bt.grad.numpy(), rtol=1e-5, atol=1e-5)
+    # duplicated shards: all sums double and so does n -> statistics bit-identical to one shard alone (the exact GPU test)
+    one = sb.global_stats([sb.forward_sums(z[0])], rows, eps)
+    two = sb.global_stats([sb.forward_sums(z[0])] * 2, rows, eps)
+    assert np.array_equal(one[0], two[0]) and np.array_equal(one[1], two[1]) and np.array_equal(one[2], two[2])
+    # image-pooling BN: pooled (sum, centred sum of squares) == statistics over the concatenated batch dimension
+    zp = [rng.normal(1.0, 2.0, size=(3, C)) for _ in range(world)]
+    loc = [(x.sum(0), ((x - x.mean(0)) ** 2).sum(0)) for x in zp]
+    pm, pv = sb.pooled_mean_var(loc, 3)
+    allz = np.concatenate(zp)
+    assert np.allclose(pm, allz.mean(0), rtol=1e-12) and np.allclose(pv, allz.var(0), rtol=1e-10)
