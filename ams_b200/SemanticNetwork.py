@@ -154,6 +154,8 @@ class SemanticNetwork(object):
         self.saver.restore_vars(None, checkpoint, self.filter)
         self.mask = None
         self._mask_on_device = None
+        self._fill_thr = None
+        self._stop_feeders = False
         print("Semantic Network is ready!!!")
 
     # ------------------------------------------------------------------ checkpoint surface
@@ -211,11 +213,19 @@ class SemanticNetwork(object):
         batch_thr = threading.Thread(target=self._fill_batch, args=(batch_deque, frame_deque, label_deque,
                                                                     num_of_iterations,))
         batch_thr.start()
+        self._stop_feeders = False
         try:
             self._train(batch_deque, num_of_iterations, train_strategy)
+        except BaseException:
+            # stop both feeder threads and drop what they staged: the next predict_input must not dequeue training batches
+            self._stop_feeders = True
+            batch_thr.join()
+            if self._fill_thr is not None:
+                self._fill_thr.join()
+            self.student.queue_clear()
+            raise
         finally:
-            if self.process_lock.locked():
-                self.process_lock.release()
+            self.process_lock.release()          # held by THIS call since the acquire above; _train never releases it
 
     def _split(self, flat, dtype=None):
         out = OrderedDict()
@@ -237,6 +247,7 @@ class SemanticNetwork(object):
     def _train(self, batch_deque, num_of_iterations, train_strategy):
         signal_deque = deque()
         fill_thr = threading.Thread(target=self._fill_queue, args=(batch_deque, num_of_iterations, signal_deque))
+        self._fill_thr = fill_thr
         fill_thr.start()
         masked = 'coord_desc_' in train_strategy
         assert not masked or self.masked_gradients, "coord_desc_* strategies need masked_gradients=True at build time"
@@ -272,7 +283,6 @@ class SemanticNetwork(object):
             _after_train = self.saver.save_vars(None, self.save_vars, self.filter)
             self.train_params = [_after_train[name] for name in _after_train.keys()]
             self.curr_mask = [np.ones_like(_after_train[name], dtype=bool) for name in _after_train.keys()]
-        self.process_lock.release()
 
     def delta_bytes(self):
         """The `<save_dir>_mask.dat` payload run.py:316-328 writes, packed on the device (masked strategies):
@@ -286,6 +296,8 @@ class SemanticNetwork(object):
         statistics are not in the delta -- the client keeps the ones of its last full hand-off."""
         self.process_lock.acquire()
         try:
+            # the delta's mask becomes the device mask: whatever this object uploaded before is no longer there
+            self._mask_on_device = None
             return self.student.apply_delta(blob)
         finally:
             self.process_lock.release()
@@ -337,6 +349,8 @@ class SemanticNetwork(object):
 
     def _fill_batch(self, batch_deque, frame_deque, label_deque, number_of_batches):
         for batch_index in range(number_of_batches):
+            if self._stop_feeders:
+                return
             image_batch, label_batch = mini_batch(frame_deque, label_deque, [self.height, self.height * 2], self.scale,
                                                   self.mini_batch_size, 1, flip=False)
             assert np.shape(label_batch) == (1, self.mini_batch_size, self.height, self.height * 2)
@@ -347,6 +361,8 @@ class SemanticNetwork(object):
         for batch_index in range(number_of_batches):
             batch = None
             while batch is None:
+                if self._stop_feeders:
+                    return
                 try:
                     batch = batch_deque.popleft()
                 except IndexError:

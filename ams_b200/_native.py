@@ -46,6 +46,7 @@ _SIGNATURES = {
     'ams_enqueue': (_i, [_vp, _vp, _i, _vp, _i]),
     'ams_enqueue_raw': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i]),
     'ams_queue_size': (_i, [_vp]),
+    'ams_queue_clear': (_i, [_vp]),
     'ams_infer': (_i, [_vp, _i, _vp]),
     'ams_infer_metric': (_i, [_vp, _i, _vp, _vp, C.POINTER(_f)]),
     'ams_confmat_labels': (_i, [_vp, _vp, _vp, _ll, _vp]),
@@ -79,7 +80,7 @@ _SIGNATURES = {
     'ams_layout_layer_info': (_i, [_i, _i, _i, C.c_char_p, _i] + [C.POINTER(_i)] * 6 + [C.POINTER(_f)] * 2 + [C.POINTER(_i)]),
     'ams_debug_dw_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
     'ams_debug_dw_bwd_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
-    'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _vp]),
+    'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     'ams_op_resize_u8': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),

@@ -123,7 +123,8 @@ ams_net* ams_create(const ams_config* cfg) {
     for (const LayerDef& d : net->layers) {
         if (d.kind != kConv1x1 && d.kind != kLogits) continue;
         WeightCast t;
-        t.w = net->params + d.w_off; t.w_fwd = net->wpool + d.wfwd_off; t.w_bwd = net->wpool + d.wbwd_off;
+        t.w = net->params + d.w_off; t.w_fwd = reinterpret_cast<act_t*>(net->wpool + d.wfwd_off); t.w_bwd = reinterpret_cast<bf16*>(net->wpool + d.wbwd_off);
+        t.w_lo = d.wlo_off >= 0 ? reinterpret_cast<act_t*>(net->wpool + d.wlo_off) : nullptr;
         t.Cin = d.cin; t.Cout = d.cout; t.ld_fwd = d.ld_fwd; t.ld_bwd = d.ld_bwd; t.row0 = d.k_rows0; t.rows = d.k_rows;
         table.push_back(t);
         net->cast_max = std::max(net->cast_max, d.k_rows * d.cout);
@@ -362,6 +363,20 @@ int ams_queue_size(ams_net* h) {
     NET(h);
     std::unique_lock<std::mutex> lk(net->qmu);
     return static_cast<int>(net->filled.size());
+}
+int ams_queue_clear(ams_net* h) {
+    NET(h);
+    int dropped = 0;
+    {
+        std::unique_lock<std::mutex> lk(net->qmu);
+        while (!net->filled.empty()) {
+            net->free_slots.push_back(net->filled.front());       // fully staged (ams_enqueue synchronises its copy stream): reusable at once
+            net->filled.pop_front();
+            ++dropped;
+        }
+    }
+    net->qcv.notify_all();
+    return dropped;
 }
 
 static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels, int64_t* out_cm, float* out_loss) {
@@ -678,14 +693,18 @@ int ams_apply_delta(ams_net* h, const uint8_t* blob, long long len, long long* o
     AMS_REQUIRE(blob && len >= net->mask_bytes, "delta shorter than its mask section");
     const int nblocks = pack_delta_blocks(net->n_train);
     AMS_CUDA_CHECK(cudaMemcpyAsync(net->pack_bits, blob, net->mask_bytes, cudaMemcpyHostToDevice, net->stream));
+    // the bits are unpacked into a SCRATCH byte map and the length is validated before any state of the handle changes:
+    // a truncated or corrupt delta must leave the training mask and the parameters as they were
+    uint8_t* scratch_mask = reinterpret_cast<uint8_t*>(net->delta_scratch);          // n_train floats >= n_train bytes
     if (unpack_delta_mask(net->pack_bits, net->segs_dev, static_cast<int>(net->trainable_order.size()), net->n_train, net->mask_bytes,
-                          net->mask, net->pack_counts, nblocks, net->pack_kept, net->stream)) return -1;
+                          scratch_mask, net->pack_counts, nblocks, net->pack_kept, net->stream)) return -1;
     unsigned long long kept = 0;
     AMS_CUDA_CHECK(cudaMemcpyAsync(&kept, net->pack_kept, sizeof(kept), cudaMemcpyDeviceToHost, net->stream));
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
-    net->mask_all_ones = false;
     AMS_REQUIRE(len == net->mask_bytes + 2 * static_cast<long long>(kept), "delta length does not match its mask (" +
                 std::to_string(len) + " bytes for " + std::to_string(kept) + " selected coordinates)");
+    AMS_CUDA_CHECK(cudaMemcpyAsync(net->mask, scratch_mask, net->n_train, cudaMemcpyDeviceToDevice, net->stream));
+    net->mask_all_ones = false;
     if (kept) {
         AMS_CUDA_CHECK(cudaMemcpyAsync(net->pack_vals, blob + net->mask_bytes, 2 * kept, cudaMemcpyHostToDevice, net->stream));
         if (unpack_delta_values(net->params, net->mask, net->n_train, net->pack_counts, nblocks, net->pack_vals, net->stream)) return -1;
@@ -734,7 +753,8 @@ int ams_get_activation(ams_net* h, int index, int which, uint16_t* host, long lo
     AMS_REQUIRE(index >= 0 && index < static_cast<int>(net->layers.size()), "bad layer index");
     Plan* p = it->second.get();
     const LayerDef& d = net->layers[index];
-    const bf16* src = which == 0 ? p->buf[index].y : (which == 1 ? p->buf[index].z : p->buf[index].g);
+    const void* src = which == 0 ? static_cast<const void*>(p->buf[index].y)
+                                 : (which == 1 ? static_cast<const void*>(p->buf[index].z) : static_cast<const void*>(p->buf[index].g));
     AMS_REQUIRE(src != nullptr, "layer has no such buffer");
     const long long M = static_cast<long long>(p->N) * d.out_h * d.out_w;
     if (which == 0 && p->last_was_train && p->lazy_y[index]) {
@@ -811,12 +831,13 @@ int ams_layout_layer_info(int nc, int variant, int index, char* name, int cap, i
 // =============================================================================================== op-level hooks
 int ams_op_conv1x1(const void* a, const void* w, int M, int N, int K, const float* scale, const float* shift,
                    const float* rowbias, int rows_per_image, const void* residual, int act, void* out, int out_fp32, int ldc,
-                   void* stream) {
+                   int grad_types, const void* w_lo, void* stream) {
     GemmDesc d;
-    d.A = static_cast<const bf16*>(a); d.lda = K; d.B = static_cast<const bf16*>(w); d.ldb = K;
+    d.A = a; d.lda = K; d.B = w; d.ldb = K; d.B_lo = w_lo;
+    if (grad_types) { d.a_fp16 = 0; d.b_fp16 = 0; d.out_fp16 = 0; }     // data-gradient GEMM: bf16 gradient x bf16 weights -> bf16
     d.M = M; d.N = N; d.K = K; d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32; d.scale = scale; d.shift = shift;
     d.rowbias = rowbias; d.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
-    d.residual = static_cast<const bf16*>(residual); d.ldr = N; d.act = act;
+    d.residual = residual; d.ldr = N; d.act = act;
     int dev = 0; cudaGetDevice(&dev);
     int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     GemmPlan pl;
@@ -828,7 +849,7 @@ int ams_op_wgrad(const void* x, int cin, const void* dz, int cout, long long M, 
     int dev = 0; cudaGetDevice(&dev);
     int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     WgradDesc d;
-    d.X = static_cast<const bf16*>(x); d.ldx = cin; d.Cin = cin; d.dZ = static_cast<const bf16*>(dz); d.ldz = cout; d.Cout = cout;
+    d.X = x; d.ldx = cin; d.Cin = cin; d.dZ = dz; d.ldz = cout; d.Cout = cout;      // X fp16 activations, dZ bf16 gradients
     d.M = M; d.dW = dw; d.lddw = cout;
     const size_t wsf = wgrad_workspace_floats(cin, cout, M, sms);
     float* ws = nullptr;
@@ -852,8 +873,8 @@ static Conv2dGeom make_geom(int n, int h, int w, int c, int stride, int dil) {
 
 int ams_op_depthwise(const void* in, const float* w, int n, int h, int w_, int c, int stride, int dil, const float* scale,
                      const float* shift, int act, void* out, void* stream) {
-    return dw_conv_fwd_tiled(static_cast<const bf16*>(in), w, make_geom(n, h, w_, c, stride, dil), nullptr, nullptr, 0, scale,
-                             shift, act, static_cast<bf16*>(out), nullptr, nullptr, as_stream(stream));
+    return dw_conv_fwd_tiled(static_cast<const act_t*>(in), w, make_geom(n, h, w_, c, stride, dil), nullptr, nullptr, 0, scale,
+                             shift, act, static_cast<act_t*>(out), nullptr, nullptr, as_stream(stream));
 }
 
 __global__ void sum_rows_kernel(const double* __restrict__ partial, int rows, int n, double* __restrict__ out) {
@@ -872,8 +893,8 @@ int ams_op_depthwise_fused(const void* in, const float* w, int n, int h, int w_,
     const long long rows = dw_tiled_stats_rows(g);
     if (stats_out) AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), static_cast<size_t>(rows) * 2 * c * sizeof(double)));
     int got = 0;
-    int rc = dw_conv_fwd_tiled(static_cast<const bf16*>(in), w, g, in_scale, in_shift, in_act, nullptr, nullptr, 0,
-                               static_cast<bf16*>(out), ws, &got, as_stream(stream));
+    int rc = dw_conv_fwd_tiled(static_cast<const act_t*>(in), w, g, in_scale, in_shift, in_act, nullptr, nullptr, 0,
+                               static_cast<act_t*>(out), ws, &got, as_stream(stream));
     if (!rc && stats_out) {
         sum_rows_kernel<<<ceil_div(2 * c, 128), 128, 0, as_stream(stream)>>>(ws, got, 2 * c, stats_out);
         if (cudaGetLastError() != cudaSuccess) rc = -1;
@@ -899,8 +920,8 @@ int ams_op_depthwise_bwd_fused(const void* g, const void* z, const float* scale,
     AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&wsf), static_cast<size_t>(rows) * 9 * c * sizeof(float)));
     AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&wsd), static_cast<size_t>(rows) * 2 * c * sizeof(double)));
     DwBwdFused f;
-    f.g = static_cast<const bf16*>(g); f.z = static_cast<const bf16*>(z); f.scale = scale; f.shift = shift; f.act = act; f.coef = coef;
-    f.zin = static_cast<const bf16*>(zin); f.in_scale = in_scale; f.in_shift = in_shift; f.in_act = in_act; f.w = w;
+    f.g = static_cast<const bf16*>(g); f.z = static_cast<const act_t*>(z); f.scale = scale; f.shift = shift; f.act = act; f.coef = coef;
+    f.zin = static_cast<const act_t*>(zin); f.in_scale = in_scale; f.in_shift = in_shift; f.in_act = in_act; f.w = w;
     f.gout = static_cast<bf16*>(gout); f.dw = dw; f.dw_partial = wsf; f.dw_partial_floats = static_cast<size_t>(rows) * 9 * c;
     f.bn_partial = wsd;
     int got = 0;
@@ -922,7 +943,7 @@ int ams_op_depthwise_bwd(const void* x, const void* dz, const float* w, int n, i
         const size_t wsf = dw_bwd_workspace_floats(g);
         float* ws = nullptr;
         AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&ws), wsf * sizeof(float)));
-        int rc = dw_conv_bwd_filter(static_cast<const bf16*>(x), static_cast<const bf16*>(dz), g, dw, ws, wsf, as_stream(stream));
+        int rc = dw_conv_bwd_filter(static_cast<const act_t*>(x), static_cast<const bf16*>(dz), g, dw, ws, wsf, as_stream(stream));
         cudaStreamSynchronize(as_stream(stream));
         cudaFree(ws);
         return rc;
@@ -942,7 +963,7 @@ int ams_op_stem(const void* frames, int dtype, int n, int h, int w_, const float
     int Hp, Wp, Ho, Wo, pt, pl;
     stem_geom(h, w_, &Hp, &Wp, &Ho, &Wo, &pt, &pl);
     return stem_conv_fwd(frames, dtype == AMS_FRAMES_U8, n, h, w_, Hp, Wp, Ho, Wo, pt, pl, 127.5f, 0.007843137718737125f, 1.0f, w,
-                         scale, shift, static_cast<bf16*>(out), as_stream(stream));
+                         scale, shift, static_cast<act_t*>(out), as_stream(stream));
 }
 
 int ams_op_stem_bwd(const void* frames, int dtype, int n, int h, int w_, const void* dz, float* dw, void* stream) {
@@ -966,9 +987,9 @@ int ams_op_bn_train(const void* z, long long M, int C, const float* gamma, const
     BnLayer L;
     L.C = C; L.M = M; L.eps = eps; L.one_minus_decay = 0.f; L.gamma = gamma; L.beta = beta;
     L.moving_mean = tmp + 2 * C; L.moving_var = tmp + 3 * C; L.mean = mean; L.rstd = rstd; L.scale = tmp; L.shift = tmp + C;
-    int rc = bn_forward_stats(static_cast<const bf16*>(z), L, 0, ws, as_stream(stream));
-    if (!rc) rc = bn_apply(static_cast<const bf16*>(z), L.scale, L.shift, act, static_cast<const bf16*>(residual),
-                           static_cast<bf16*>(y), M, C, as_stream(stream));
+    int rc = bn_forward_stats(static_cast<const act_t*>(z), L, 0, ws, as_stream(stream));
+    if (!rc) rc = bn_apply(static_cast<const act_t*>(z), L.scale, L.shift, act, static_cast<const act_t*>(residual),
+                           static_cast<act_t*>(y), M, C, as_stream(stream));
     cudaStreamSynchronize(as_stream(stream));
     cudaFree(tmp); cudaFree(ws);
     return rc;
@@ -982,8 +1003,8 @@ int ams_op_bn_backward(const void* dy, const void* z, long long M, int C, const 
     BnLayer L;
     L.C = C; L.M = M; L.eps = eps; L.one_minus_decay = 0.f; L.gamma = gamma; L.beta = beta;
     L.moving_mean = tmp + 4 * C; L.moving_var = tmp + 5 * C; L.mean = tmp + 2 * C; L.rstd = tmp + 3 * C; L.scale = tmp; L.shift = tmp + C;
-    int rc = bn_forward_stats(static_cast<const bf16*>(z), L, 0, ws, as_stream(stream));
-    if (!rc) rc = bn_backward(static_cast<const bf16*>(dy), nullptr, static_cast<const bf16*>(z), L, act, static_cast<bf16*>(dz),
+    int rc = bn_forward_stats(static_cast<const act_t*>(z), L, 0, ws, as_stream(stream));
+    if (!rc) rc = bn_backward(static_cast<const bf16*>(dy), nullptr, static_cast<const act_t*>(z), L, act, static_cast<bf16*>(dz),
                               dgamma, dbeta, ws, as_stream(stream));
     cudaStreamSynchronize(as_stream(stream));
     cudaFree(tmp); cudaFree(ws);

@@ -32,7 +32,7 @@ int red_chunks(long long M, int C) {
 
 // partial[chunk][0][c] = sum z, partial[chunk][1][c] = sum z^2 over the rows of the chunk
 __global__ void __launch_bounds__(kRedThreads)
-bn_stats_kernel(const bf16* __restrict__ z, long long M, int C, long long rows_per_chunk, double* __restrict__ partial) {
+bn_stats_kernel(const act_t* __restrict__ z, long long M, int C, long long rows_per_chunk, double* __restrict__ partial) {
     pdl_entry();
     extern __shared__ double s_acc[];                     // [rows_in_block][2][C]
     const int c8n = C >> 3;
@@ -65,7 +65,7 @@ bn_stats_kernel(const bf16* __restrict__ z, long long M, int C, long long rows_p
                     for (int u = 0; u < 4; ++u) {
                         if (u < nv) {
                             float v[8];
-                            unpack8(raw[u], v);
+                            unpack8h(raw[u], v);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) { fs[q] += v[q]; fq[q] = fmaf(v[q], v[q], fq[q]); }
                         }
@@ -247,8 +247,8 @@ bn_finalize_kernel(const double* __restrict__ partial, int chunks, BnLayer L, in
 static const int kEwRowsKnob = env_int("AMS_EW_ROWS", 4);      // rows per thread of the elementwise passes: 2, 4 or 8
 template <int kEwRows>
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                const bf16* __restrict__ residual, bf16* __restrict__ y, int M, int C) {
+bn_apply_kernel(const act_t* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                const act_t* __restrict__ residual, act_t* __restrict__ y, int M, int C) {
     pdl_entry();
     const int c8n = C >> 3;
     const int tpr = min(c8n, 256), rib = 256 / tpr;
@@ -279,16 +279,16 @@ bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ scale, con
             const int r = r0 + u * rib;
             if (r < M) {
                 float v[8];
-                unpack8(vz[u], v);
+                unpack8h(vz[u], v);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = act_apply(fmaf(v[q], sc[q], sh[q]), act);
                 if (residual) {
                     float f[8];
-                    unpack8(vr[u], f);
+                    unpack8h(vr[u], f);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] += f[q];
                 }
-                stg_stream(y + static_cast<long long>(r) * C + c0, pack8(v));
+                stg_stream(y + static_cast<long long>(r) * C + c0, pack8h(v));
             }
         }
     }
@@ -314,7 +314,7 @@ __device__ __forceinline__ float act_mask(float g, float yhat, int act) {
 // U = rows in flight per thread and tensor (2 or 4 independent 128-bit loads each of dy and z); HAS2 = a second gradient
 template <int U, bool HAS2>
 __global__ void __launch_bounds__(kRedThreads)
-bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
+bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, const act_t* __restrict__ z,
                      const float* __restrict__ scale, const float* __restrict__ shift, int act, long long M, int C,
                      long long rows_per_chunk, double* __restrict__ partial) {
     pdl_entry();
@@ -355,7 +355,7 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ dy2, 
                         if (u < nv) {
                             float g[8], v[8];
                             unpack8(rg[u], g);
-                            unpack8(rz[u], v);
+                            unpack8h(rz[u], v);
                             if (HAS2) {
                                 float g2[8];
                                 unpack8(rg2[HAS2 ? u : 0], g2);
@@ -420,7 +420,7 @@ __device__ __forceinline__ void load8f(const float* p, float* o) {
 
 template <int kEwRows>
 __global__ void __launch_bounds__(256)
-bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __restrict__ z,
+bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const act_t* __restrict__ z,
                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
                     int act, int M, int C, bf16* dz_out) {
     pdl_entry();
@@ -451,7 +451,7 @@ bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __
             if (r < M) {
                 float g[8], v[8];
                 unpack8(vg[u], g);
-                unpack8(vz[u], v);
+                unpack8h(vz[u], v);
                 if (dy2) {
                     float g2[8];
                     unpack8(vg2[u], g2);
@@ -474,7 +474,7 @@ bn_bwd_apply_kernel(const bf16* dy, const bf16* __restrict__ dy2, const bf16* __
 // per block; a second tiny kernel adds the splits in fixed order (deterministic).
 constexpr int kColsumSplits = 32;
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb, int ld, long long rpg, int C,
+colsum_partial_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb, const act_t* __restrict__ xh, int ld, long long rpg, int C,
                       double* __restrict__ partial) {
     pdl_entry();
     __shared__ double s_red[4][64];
@@ -489,7 +489,7 @@ colsum_partial_kernel(const float* __restrict__ xf, const bf16* __restrict__ xb,
         float run = 0.f;
         int cnt = 0;
         for (long long r = r0 + lr; r < r1; r += 4) {
-            run += xf ? xf[r * ld + c] : __bfloat162float(xb[r * ld + c]);
+            run += xf ? xf[r * ld + c] : (xb ? __bfloat162float(xb[r * ld + c]) : __half2float(xh[r * ld + c]));
             if (++cnt == 32) { acc += run; run = 0.f; cnt = 0; }
         }
         acc += run;
@@ -649,7 +649,7 @@ static size_t red_smem(int C) {
     return static_cast<size_t>(kRedThreads / tpr) * 2 * C * sizeof(double);
 }
 
-static int launch_bwd_apply(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, const float* coef, int act, int rib,
+static int launch_bwd_apply(const bf16* dy, const bf16* dy2, const act_t* z, const BnLayer& L, const float* coef, int act, int rib,
                             bf16* dz_out, cudaStream_t s) {
     const int rows = kEwRowsKnob == 2 ? 2 : (kEwRowsKnob == 8 ? 8 : 4);
     const int grid = static_cast<int>(ceil_div_ll(L.M, rib * rows)), M = static_cast<int>(L.M);
@@ -659,7 +659,7 @@ static int launch_bwd_apply(const bf16* dy, const bf16* dy2, const bf16* z, cons
     return 0;
 }
 
-static int launch_bwd_reduce(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, int chunks, long long rpc,
+static int launch_bwd_reduce(const bf16* dy, const bf16* dy2, const act_t* z, const BnLayer& L, int act, int chunks, long long rpc,
                              size_t smem, double* ws, cudaStream_t s) {
     if (dy2) AMS_LAUNCH((bn_bwd_reduce_kernel<2, true>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
     else if (kBwdRedUnroll == 8) AMS_LAUNCH((bn_bwd_reduce_kernel<8, false>), chunks, kRedThreads, smem, s, dy, dy2, z, L.scale, L.shift, act, L.M, L.C, rpc, ws);
@@ -668,7 +668,7 @@ static int launch_bwd_reduce(const bf16* dy, const bf16* dy2, const bf16* z, con
     return 0;
 }
 
-int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double* ws, cudaStream_t s) {
+int bn_forward_stats(const act_t* z, const BnLayer& L, int update_moving, double* ws, cudaStream_t s) {
     AMS_REQUIRE(L.C % 8 == 0, "BN channels must be a multiple of 8");
     const int chunks = red_chunks(L.M, L.C);
     const long long rpc = ceil_div_ll(L.M, chunks);
@@ -684,7 +684,7 @@ int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, in
     return 0;
 }
 
-int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y, long long M,
+int bn_apply(const act_t* z, const float* scale, const float* shift, int act, const act_t* residual, act_t* y, long long M,
              int C, cudaStream_t s) {
     const int rib = 256 / std::min(C / 8, 256);
     const int rows = kEwRowsKnob == 2 ? 2 : (kEwRowsKnob == 8 ? 8 : 4);
@@ -701,7 +701,7 @@ int bn_fold_frozen(const float* gamma, const float* beta, const float* mm, const
     return 0;
 }
 
-int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, bf16* dz_out, float* d_gamma,
+int bn_backward(const bf16* dy, const bf16* dy2, const act_t* z, const BnLayer& L, int act, bf16* dz_out, float* d_gamma,
                 float* d_beta, double* ws, cudaStream_t s) {
     const int chunks = red_chunks(L.M, L.C);
     const long long rpc = ceil_div_ll(L.M, chunks);
@@ -714,7 +714,7 @@ int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L
     return 0;
 }
 
-int bn_backward_reduce(const bf16* dy, const bf16* z, const BnLayer& L, int act, float* coef, float* d_gamma, float* d_beta,
+int bn_backward_reduce(const bf16* dy, const act_t* z, const BnLayer& L, int act, float* coef, float* d_gamma, float* d_beta,
                        double* ws, cudaStream_t s) {
     const int chunks = red_chunks(L.M, L.C);
     const long long rpc = ceil_div_ll(L.M, chunks);
@@ -729,16 +729,16 @@ int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer
     return 0;
 }
 
-int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s) {
+int bn_backward_apply(const bf16* dy_masked, const act_t* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s) {
     const int rib = 256 / std::min(L.C / 8, 256);
     if (launch_bwd_apply(dy_masked, nullptr, z, L, coef, 0, rib, dz_out, s)) return -1;
     return 0;
 }
 
-int colsum_groups(const float* xf, const bf16* xb, int ld, long long rows_per_group, int groups, int C, float scale,
+int colsum_groups(const float* xf, const bf16* xb, const act_t* xh, int ld, long long rows_per_group, int groups, int C, float scale,
                   float* out, double* workspace, cudaStream_t s) {
     dim3 grid(groups, ceil_div(C, 64), kColsumSplits);
-    AMS_LAUNCH((colsum_partial_kernel), grid, 256, 0, s, xf, xb, ld, rows_per_group, C, workspace);
+    AMS_LAUNCH((colsum_partial_kernel), grid, 256, 0, s, xf, xb, xh, ld, rows_per_group, C, workspace);
     AMS_LAUNCH((colsum_final_kernel), ceil_div(groups * C, 128), 128, 0, s, workspace, groups, C, scale, out);
     return 0;
 }
@@ -746,7 +746,7 @@ size_t colsum_workspace_doubles(int groups, int C) { return static_cast<size_t>(
 
 int imgpool_forward(const ImgPoolFwd& a, cudaStream_t s) {
     // pooled[n][c] = mean over HW of feat
-    if (colsum_groups(nullptr, a.feat, a.Cin, a.HW, a.N, a.Cin, 1.f / static_cast<float>(a.HW), a.pooled, a.ws, s)) return -1;
+    if (colsum_groups(nullptr, nullptr, a.feat, a.Cin, a.HW, a.N, a.Cin, 1.f / static_cast<float>(a.HW), a.pooled, a.ws, s)) return -1;
     AMS_LAUNCH((small_fc_kernel), ceil_div(a.N * a.Cmid, 256), 256, 0, s, a.pooled, a.w_pool, a.N, a.Cin, a.Cmid, a.z);
     AMS_LAUNCH((imgpool_bn_kernel), ceil_div(a.Cmid, 256), 256, 0, s, a);
     AMS_LAUNCH((small_fc_kernel), ceil_div(a.N * a.Cout, 256), 256, 0, s, a.act, a.w_proj_top, a.N, a.Cmid, a.Cout, a.bias_img);
@@ -756,7 +756,7 @@ int imgpool_forward(const ImgPoolFwd& a, cudaStream_t s) {
 int imgpool_backward(const ImgPoolBwd& b, cudaStream_t s) {
     const ImgPoolFwd& a = b.f;
     float* dact = b.dbias + static_cast<size_t>(a.N) * a.Cout;       // caller allocates N*(Cout+Cmid) floats
-    if (colsum_groups(nullptr, b.dz_proj, a.Cout, a.HW, a.N, a.Cout, 1.f, b.dbias, a.ws, s)) return -1;
+    if (colsum_groups(nullptr, b.dz_proj, nullptr, a.Cout, a.HW, a.N, a.Cout, 1.f, b.dbias, a.ws, s)) return -1;
     // d act = relu'(act) * dbias * w_proj_top^T ;  d w_proj_top = act^T dbias
     AMS_LAUNCH((small_fc_t_kernel), ceil_div(a.N * a.Cmid * 32, 256), 256, 0, s, b.dbias, a.w_proj_top, a.act, a.N, a.Cmid, a.Cout, 1.f, dact);
     AMS_LAUNCH((small_outer_kernel), ceil_div(a.Cmid * a.Cout, 256), 256, 0, s, a.act, b.dbias, a.N, a.Cmid, a.Cout, b.d_w_proj_top);

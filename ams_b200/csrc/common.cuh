@@ -86,6 +86,31 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 __device__ __forceinline__ uint4 pack8(const float* f) {
     return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
+// ----------------------------------------------------------------------------- fp16 pack / unpack
+// Forward activations and the 1x1-conv weight operands are stored in IEEE fp16 (10-bit mantissa: 8x finer than
+// bf16 for the same bytes; post-BN/ReLU6 values live in [0, 6], raw conv outputs stay far below 65504 and the
+// conversion saturates instead of producing inf).  Gradient tensors keep bf16 (range matters there, not precision).
+__device__ __forceinline__ float h16_lo(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v & 0xffffu))); }
+__device__ __forceinline__ float h16_hi(uint32_t v) { return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16))); }
+__device__ __forceinline__ float2 h16x2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+__device__ __forceinline__ uint32_t pack_h16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
+    const float2 a = h16x2(v.x), b = h16x2(v.y), c = h16x2(v.z), d = h16x2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8h(const float* f) {
+    return make_uint4(pack_h16(f[0], f[1]), pack_h16(f[2], f[3]), pack_h16(f[4], f[5]), pack_h16(f[6], f[7]));
+}
+// compile-time choice of the 16-bit storage type: H = true fp16 (activations), false bf16 (gradients)
+template <bool H> __device__ __forceinline__ float2 unpack2t(uint32_t v) { return H ? h16x2(v) : make_float2(bf16_lo(v), bf16_hi(v)); }
+template <bool H> __device__ __forceinline__ uint32_t pack2t(float lo, float hi) { return H ? pack_h16(lo, hi) : pack_bf16(lo, hi); }
+template <bool H> __device__ __forceinline__ void unpack8t(const uint4& v, float* f) { if (H) unpack8h(v, f); else unpack8(v, f); }
+template <bool H> __device__ __forceinline__ uint4 pack8t(const float* f) { return H ? pack8h(f) : pack8(f); }
+
 // streaming 128-bit loads/stores (read-once / write-once tensors: keep them out of L1)
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     uint4 r;

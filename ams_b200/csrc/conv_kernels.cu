@@ -36,7 +36,7 @@ __device__ __forceinline__ void stem_pixel(const T* in, const StemGeom& g, int n
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ w, const float* __restrict__ scale,
-                const float* __restrict__ shift, bf16* __restrict__ out) {
+                const float* __restrict__ shift, act_t* __restrict__ out) {
     pdl_entry();
     __shared__ float sw[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
@@ -71,8 +71,8 @@ stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ 
         for (int j = 0; j < 16; ++j)
             acc[j] = fminf(fmaxf(fmaf(acc[j], scale[half * 16 + j], shift[half * 16 + j]), 0.f), 6.f);
     }
-    bf16* o = out + pix * 32 + half * 16;
-    stg256(o, pack8(acc), pack8(acc + 8));
+    act_t* o = out + pix * 32 + half * 16;
+    stg256(o, pack8h(acc), pack8h(acc + 8));
 }
 
 // filter gradient: a block owns `rows_per_block` output rows; per segment of 64 output pixels it stages the three
@@ -155,8 +155,8 @@ reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ ou
 // thread = 8 channels x TW consecutive output pixels along W; sliding window over the needed input columns
 template <int S, int D, int TW>
 __global__ void __launch_bounds__(256)
-dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGeom g, const float* __restrict__ scale,
-              const float* __restrict__ shift, int act, bf16* __restrict__ out) {
+dw_fwd_kernel(const act_t* __restrict__ in, const float* __restrict__ w, Conv2dGeom g, const float* __restrict__ scale,
+              const float* __restrict__ shift, int act, act_t* __restrict__ out) {
     pdl_entry();
     const int C8 = g.C >> 3;
     const int WG = (g.Wo + TW - 1) / TW;
@@ -189,7 +189,7 @@ dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGe
             wk[kx][0] = a.x; wk[kx][1] = a.y; wk[kx][2] = a.z; wk[kx][3] = a.w;
             wk[kx][4] = b.x; wk[kx][5] = b.y; wk[kx][6] = b.z; wk[kx][7] = b.w;
         }
-        const bf16* row = in + ((static_cast<long long>(n) * g.H + iy) * g.W) * g.C + c0;
+        const act_t* row = in + ((static_cast<long long>(n) * g.H + iy) * g.W) * g.C + c0;
 #pragma unroll
         for (int j = 0; j < NCOLS; ++j) {
             // does any (t, kx) use column j?  t*S + kx*D == j
@@ -200,7 +200,7 @@ dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGe
             const int ix = ix0 + j;
             if (ix < 0 || ix >= g.W) continue;
             float v[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * g.C)), v);
+            unpack8h(__ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * g.C)), v);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int tt = j - kx * D;
@@ -225,7 +225,7 @@ dw_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, Conv2dGe
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[t][q] = act_apply(fmaf(acc[t][q], sc[q], sh[q]), act);
         }
-        stg_stream(out + ((static_cast<long long>(n) * g.Ho + oy) * g.Wo + ox) * g.C + c0, pack8(acc[t]));
+        stg_stream(out + ((static_cast<long long>(n) * g.Ho + oy) * g.Wo + ox) * g.C + c0, pack8h(acc[t]));
     }
 }
 
@@ -278,7 +278,7 @@ dw_bwd_data_kernel(const bf16* __restrict__ dz, const float* __restrict__ w, Con
 constexpr int kDwfTW = 4;
 template <int S, int D>
 __global__ void __launch_bounds__(256, 2)
-dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Conv2dGeom g, float* __restrict__ partial,
+dw_bwd_filter_kernel(const act_t* __restrict__ x, const bf16* __restrict__ dz, Conv2dGeom g, float* __restrict__ partial,
                      int strips_per_block) {
     pdl_entry();
     extern __shared__ float s_red[];                       // [rows_in_block][tpr][73]
@@ -318,7 +318,7 @@ dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Co
             for (int ky = 0; ky < 3; ++ky) {
                 const int iy = oy * S - g.pad_top + ky * D;
                 if (iy < 0 || iy >= g.H) continue;
-                const bf16* row = x + ((static_cast<long long>(n) * g.H + iy) * g.W) * g.C + c0;
+                const act_t* row = x + ((static_cast<long long>(n) * g.H + iy) * g.W) * g.C + c0;
 #pragma unroll
                 for (int j = 0; j < NCOLS; ++j) {
                     bool used = false;
@@ -328,7 +328,7 @@ dw_bwd_filter_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dz, Co
                     const int ix = ix0 + j;
                     if (ix < 0 || ix >= g.W) continue;
                     float v[8];
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * g.C)), v);
+                    unpack8h(__ldg(reinterpret_cast<const uint4*>(row + static_cast<long long>(ix) * g.C)), v);
 #pragma unroll
                     for (int kx = 0; kx < 3; ++kx) {
                         const int tt = j - kx * D;
@@ -372,7 +372,7 @@ int dw_strips_per_block(const Conv2dGeom& g) {
 // ============================================================================================ host
 int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
                   int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w, const float* scale,
-                  const float* shift, bf16* out, cudaStream_t s) {
+                  const float* shift, act_t* out, cudaStream_t s) {
     StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
     const long long total = static_cast<long long>(N) * Ho * Wo * 2;
     if (in_is_u8)
@@ -401,8 +401,8 @@ int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int 
     return 0;
 }
 
-int dw_conv_fwd(const bf16* in, const float* w, const Conv2dGeom& g, const float* scale, const float* shift, int act,
-                bf16* out, cudaStream_t s) {
+int dw_conv_fwd(const act_t* in, const float* w, const Conv2dGeom& g, const float* scale, const float* shift, int act,
+                act_t* out, cudaStream_t s) {
     AMS_REQUIRE(g.C % 8 == 0, "depthwise channels must be a multiple of 8");
     constexpr int TW = 4;
     const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, TW) * (g.C / 8);
@@ -429,7 +429,7 @@ size_t dw_bwd_workspace_floats(const Conv2dGeom& g) {
     return static_cast<size_t>(ceil_div_ll(total, dw_strips_per_block(g))) * 9 * g.C;
 }
 
-int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
+int dw_conv_bwd_filter(const act_t* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
                        size_t workspace_floats, cudaStream_t s) {
     AMS_REQUIRE(g.C % 8 == 0 && g.C / 8 <= 256, "depthwise channels must be a multiple of 8, at most 2048");
     const long long total = static_cast<long long>(g.N) * g.Ho * ceil_div(g.Wo, kDwfTW);

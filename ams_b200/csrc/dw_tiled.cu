@@ -46,11 +46,12 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ float2 unpack2(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
+__device__ __forceinline__ float2 unpack2(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }      // bf16 pair (gradients)
+__device__ __forceinline__ float2 unpack2h(uint32_t v) { return h16x2(v); }                                 // fp16 pair (activations)
 
 // ------------------------------------------------------------------------------------------------ forward
 struct DwFwdParams {
-    const bf16* in; bf16* out; const float* w;            // w [9][C] fp32
+    const act_t* in; act_t* out; const float* w;          // w [9][C] fp32
     int N, H, W, C, Ho, Wo, pad_top, pad_left;
     const float* in_scale; const float* in_shift; int in_act;      // != null: act(in*scale+shift) applied while staging
     const float* out_scale; const float* out_shift; int out_act;   // != null: folded BN + act applied to the result
@@ -62,7 +63,7 @@ struct DwFwdParams {
 // Stage rows [0,ih) x cols [0,iwp) x CB channels of `img` (image-relative origin gy0,gx0; outside the image = 0) as bf16
 // [ih][iwp][CB]; optional per-channel affine + activation on the way (exactly the bn_apply arithmetic, rounded to bf16).
 template <int CB, int THREADS>
-__device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restrict__ img /* + channel chunk */, int C, int H,
+__device__ __forceinline__ void stage_tile(uint32_t sbase, const act_t* __restrict__ img /* + channel chunk */, int C, int H,
                                            int W, int gy0, int gx0, int ih, int iwp, const float* __restrict__ scale,
                                            const float* __restrict__ shift, int act, int c_chunk0, int mg_w, int step_y,
                                            int step_x) {
@@ -75,7 +76,7 @@ __device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restric
     }
     int ly = (lane_px * mg_w) >> 16, lx = lane_px - ly * iwp;
     uint32_t sdst = sbase + (lane_px * CB + c8 * 8) * 2;
-    const bf16* src = img + c8 * 8;
+    const act_t* src = img + c8 * 8;
     // software pipeline: the loads of batch k+1 are in flight while batch k is transformed and stored
     uint4 v[U], vn[U];
     int st[U], stn[U];                                  // 0 = past the tile, 1 = outside the image (zero), 2 = loaded
@@ -100,10 +101,10 @@ __device__ __forceinline__ void stage_tile(uint32_t sbase, const bf16* __restric
             if (st[u]) {
                 if (scale && st[u] == 2) {
                     float f[8];
-                    unpack8(v[u], f);
+                    unpack8h(v[u], f);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) f[q] = act_apply(fmaf(f[q], sc[q], sh[q]), act);
-                    v[u] = pack8(f);
+                    v[u] = pack8h(f);
                 }
                 sts128(sdst + u * (PXT * CB * 2), v[u]);
             }
@@ -167,7 +168,7 @@ dw_fwd_tiled_kernel(const DwFwdParams p) {
                 for (int kx = 0; kx < 3; ++kx) used = used || ((j - kx * D) >= 0 && (j - kx * D) % S == 0 && (j - kx * D) / S < kStrip);
                 if (!used) continue;
                 const uint2 raw = lds64(rowp + j * (CB * 2));
-                const float2 v0 = unpack2(raw.x), v1 = unpack2(raw.y);
+                const float2 v0 = unpack2h(raw.x), v1 = unpack2h(raw.y);
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int tt = j - kx * D;
@@ -180,7 +181,7 @@ dw_fwd_tiled_kernel(const DwFwdParams p) {
         }
         const int oy = oy0 + r;
         if (oy >= p.Ho) continue;
-        bf16* orow = p.out + ((static_cast<long long>(n) * p.Ho + oy) * p.Wo) * p.C + c0;
+        act_t* orow = p.out + ((static_cast<long long>(n) * p.Ho + oy) * p.Wo) * p.C + c0;
 #pragma unroll
         for (int a = 0; a < kStrip; ++a) {
             const int lx = s * kStrip + a, ox = ox0 + lx;
@@ -190,10 +191,10 @@ dw_fwd_tiled_kernel(const DwFwdParams p) {
 #pragma unroll
                 for (int q = 0; q < kCh; ++q) f[q] = act_apply(fmaf(f[q], osc[q], osh[q]), p.out_act);
             }
-            const uint2 pk = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
+            const uint2 pk = make_uint2(pack_h16(f[0], f[1]), pack_h16(f[2], f[3]));
             *reinterpret_cast<uint2*>(orow + static_cast<long long>(ox) * p.C) = pk;
             if (p.stats) {
-                const float2 r0 = unpack2(pk.x), r1 = unpack2(pk.y);
+                const float2 r0 = unpack2h(pk.x), r1 = unpack2h(pk.y);
                 fadd2(ssum[0], r0); fadd2(ssum[1], r1);
                 ffma2(ssq[0], r0, r0); ffma2(ssq[1], r1, r1);
             }
@@ -306,10 +307,10 @@ int launch_fwd_cb(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
 // so the normalised input, the depthwise dz and the unmasked dX never exist in HBM: 3 tensor reads + 1 write
 // instead of 9 reads + 4 writes (bn_bwd reduce/apply + dw_bwd_filter + dw_bwd_data + next bn_bwd reduce).
 struct DwBwdParams {
-    const bf16* g; const bf16* z;                 // [N,Ho,Wo,C] gradient wrt act(BN(z)) and the raw depthwise output
+    const bf16* g; const act_t* z;                // [N,Ho,Wo,C] gradient wrt act(BN(z)) (bf16) and the raw depthwise output (fp16)
     const float* scale; const float* shift; int act;          // the depthwise layer's BN (activation mask)
     const float* coef;                            // [3][C]: A, B, Cc of its BN backward
-    const bf16* zin;                              // [N,H,W,C] raw output of the producer (or its activation if in_scale == null)
+    const act_t* zin;                             // [N,H,W,C] raw output of the producer (or its activation if in_scale == null)
     const float* in_scale; const float* in_shift; int in_act;
     const float* w;                               // [9][C]
     bf16* gout;                                   // [N,H,W,C]
@@ -406,7 +407,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
                             // two channels at a time: packed fp32x2 FMAs, scalar compare/select for the activation mask
-                            const float2 z2 = unpack2(zw[h]);
+                            const float2 z2 = unpack2h(zw[h]);
                             float2 gm = unpack2(gw[h]);
                             float2 yh = sh2[h];
                             ffma2(yh, z2, sc2[h]);
@@ -452,7 +453,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
         if (iy >= p.H) continue;
         const int lx0 = s * kStrip;
         // the producer's output at the strip's 4 pixels -> x (activated, bf16-rounded) and the activation mask
-        const bf16* zrow = p.zin + ((static_cast<long long>(n) * p.H + iy) * p.W + ix0 + lx0) * p.C + c0;
+        const act_t* zrow = p.zin + ((static_cast<long long>(n) * p.H + iy) * p.W + ix0 + lx0) * p.C + c0;
         uint2 zraw[kStrip];
         bool pvalid[kStrip];
 #pragma unroll
@@ -465,7 +466,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
         uint32_t mask = 0;                                  // bit a*4+q: gradient passes at pixel a, channel q
 #pragma unroll
         for (int a = 0; a < kStrip; ++a) {
-            float f[4] = {bf16_lo(zraw[a].x), bf16_hi(zraw[a].x), bf16_lo(zraw[a].y), bf16_hi(zraw[a].y)};
+            float f[4] = {h16_lo(zraw[a].x), h16_hi(zraw[a].x), h16_lo(zraw[a].y), h16_hi(zraw[a].y)};
             if (p.in_scale) {
 #pragma unroll
                 for (int q = 0; q < kCh; ++q) {
@@ -474,8 +475,8 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
                     if (pass && pvalid[a]) mask |= 1u << (a * 4 + q);
                     f[q] = act_apply(pre, p.in_act);
                 }
-                const uint2 pk = make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
-                x[a][0] = unpack2(pk.x); x[a][1] = unpack2(pk.y);
+                const uint2 pk = make_uint2(pack_h16(f[0], f[1]), pack_h16(f[2], f[3]));      // x as the forward stored it (fp16)
+                x[a][0] = unpack2h(pk.x); x[a][1] = unpack2h(pk.y);
             } else {
                 if (pvalid[a]) mask |= 0xfu << (a * 4);
                 x[a][0] = make_float2(f[0], f[1]); x[a][1] = make_float2(f[2], f[3]);
@@ -527,7 +528,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
             *reinterpret_cast<uint2*>(orow_p + static_cast<long long>(a) * p.C) = pk;
             if (p.bn_partial) {
                 const float2 g0 = unpack2(pk.x), g1 = unpack2(pk.y);
-                const float2 z0 = unpack2(zraw[a].x), z1 = unpack2(zraw[a].y);
+                const float2 z0 = unpack2h(zraw[a].x), z1 = unpack2h(zraw[a].y);
                 fadd2(s1[0], g0); fadd2(s1[1], g1);
                 ffma2(s2[0], g0, z0); ffma2(s2[1], g1, z1);
             }
@@ -666,8 +667,8 @@ long long dw_tiled_stats_rows(const Conv2dGeom& g) {
     return static_cast<long long>(g.N) * t.nty * t.ntx;
 }
 
-int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const float* in_scale, const float* in_shift,
-                      int in_act, const float* out_scale, const float* out_shift, int out_act, bf16* out, double* stats,
+int dw_conv_fwd_tiled(const act_t* in, const float* w, const Conv2dGeom& g, const float* in_scale, const float* in_shift,
+                      int in_act, const float* out_scale, const float* out_shift, int out_act, act_t* out, double* stats,
                       int* stats_rows, cudaStream_t s) {
     AMS_REQUIRE(dw_tiled_supported(g), "tiled depthwise: unsupported channels / stride / dilation");
     const DwTile t = pick_tile(g, kFwdSmemCap);

@@ -75,20 +75,22 @@ uint32_t tmem_cols_for(int n) {
 struct GemmKParams {
     int M, N, K;
     int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc;
+    int b_split;                       // two weight planes per k-block (hi at the stage base, lo one tile further)
     uint32_t tmem_cols;
-    void* out; int ldc; int out_fp32;
+    void* out; int ldc; int out_fp32; int out_fp16, a_bf16, b_bf16;
     const float* scale; const float* shift; const float* rowbias; int rows_per_image;
-    const __nv_bfloat16* residual; int ldr;
+    const void* residual; int ldr;
     int act;
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const GemmKParams p) {
+                   const __grid_constant__ CUtensorMap tmB2, const GemmKParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_a = BLOCK_M * BLOCK_K * 2;
-    const int stage_b = p.block_n * BLOCK_K * 2;
+    const int tile_b = p.block_n * BLOCK_K * 2;
+    const int stage_b = p.b_split ? 2 * tile_b : tile_b;
     uint8_t* smA = smem;
     uint8_t* smB = smem + p.stages * stage_a;
     float* s_scale = reinterpret_cast<float*>(smB + p.stages * stage_b);
@@ -131,13 +133,14 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + stage_b);
                     t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
                     t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
+                    if (p.b_split) t5::tma_load_2d(smB + stage * stage_b + tile_b, &tmB2, &full_bar[stage], kb * BLOCK_K, n_tile * p.block_n);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+        const uint32_t idesc = t5::make_idesc_f16(BLOCK_M, p.block_n, 0, 0, p.a_bf16, p.b_bf16);
         int stage = 0; uint32_t phase = 0; int it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -156,6 +159,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
                         const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
                         t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
+                        if (p.b_split) {
+                            const uint64_t dl = t5::make_smem_desc_sw128(b_addr + tile_b + k * UMMA_K * 2, 16, 1024);
+                            t5::mma_bf16_ss(tmem_d, da, dl, idesc, 1u);
+                        }
                     }
                     t5::mma_commit(&empty_bar[stage]);                    // frees the smem slot when MMAs retire
                     if (kb == p.k_blocks - 1) t5::mma_commit(&tfull_bar[as]);   // accumulator ready
@@ -204,19 +211,19 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int valid = p.N - n0;       // N % 8 == 0 for every bf16 output
                     if (valid <= 0) continue;
                     if (p.residual) {
-                        const __nv_bfloat16* rp = p.residual + m * p.ldr + n0;
+                        const uint16_t* rp = reinterpret_cast<const uint16_t*>(p.residual) + m * p.ldr + n0;
                         float f[8];
-                        unpack8(ldg_stream(rp), f);
+                        if (p.out_fp16) unpack8h(ldg_stream(rp), f); else unpack8(ldg_stream(rp), f);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += f[j];
                         if (valid >= 16) {
-                            unpack8(ldg_stream(rp + 8), f);
+                            if (p.out_fp16) unpack8h(ldg_stream(rp + 8), f); else unpack8(ldg_stream(rp + 8), f);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[8 + j] += f[j];
                         }
                     }
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldc + n0;
-                    const uint4 lo = pack8(v), hi = pack8(v + 8);
+                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + m * p.ldc + n0;
+                    const uint4 lo = p.out_fp16 ? pack8h(v) : pack8(v), hi = p.out_fp16 ? pack8h(v + 8) : pack8(v + 8);
                     if (valid >= 16) {
                         if (st256) stg256(o, lo, hi);
                         else { stg_stream(o, lo); stg_stream(o + 8, hi); }
@@ -252,16 +259,18 @@ struct Gemm2Params {
     int M, N, K;
     int block_n, n_tiles, num_tiles, k_blocks, stages, n_alloc, stage_bufs, nboxes, acc_stages, block_k;
     int b_resident;                              // single B tile (k_blocks == 1, n_tiles == 1): loaded once per CTA
+    int b_split;                                 // two weight planes per B slot: hi at the slot base, lo one tile further
     int linear_out, pitch, cbuf_bytes;          // linear_out: dense padded staging + coalesced copy-out (n_tiles == 1)
-    __nv_bfloat16* out; int ldc;
+    uint16_t* out; int ldc;             // fp16 (kEpiOutF16) or bf16 elements
+    int a_bf16, b_bf16;                 // operand element formats of the instruction descriptor
     uint32_t tmem_cols;
     const float* scale; const float* shift; const float* rowbias; int rows_per_image;
-    const __nv_bfloat16* residual; int ldr;
+    const uint16_t* residual; int ldr;  // same element type as out
     int act;
     double* stats_partial;
 };
 
-enum : int { kEpiAffine = 1, kEpiResidual = 2, kEpiRowBias = 4, kEpiStats = 8 };
+enum : int { kEpiAffine = 1, kEpiResidual = 2, kEpiRowBias = 4, kEpiStats = 8, kEpiOutF16 = 16 };
 
 __device__ __forceinline__ void lds8(const float* p, float* o) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -276,7 +285,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
     return r;
 }
-__device__ __forceinline__ float2 unpack2f(uint32_t v) { return make_float2(bf16_lo(v), bf16_hi(v)); }
 __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&d))
         : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
@@ -289,11 +297,12 @@ __device__ __forceinline__ void fadd2(float2& d, const float2& a) {
 template <int F>
 __global__ void __launch_bounds__(kGemm2Threads, 2)
 gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
+                      const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmC, const Gemm2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stage_a = BLOCK_M * p.block_k * 2;
-    const int stage_b = p.block_n * p.block_k * 2;
+    const int tile_b = p.block_n * p.block_k * 2;
+    const int stage_b = p.b_split ? 2 * tile_b : tile_b;
     const int cbuf_bytes = p.cbuf_bytes;    // TMA mode: nboxes x [128 rows][128 B] swizzled; linear mode: [128 rows][pitch]
     uint8_t* smA = smem;
     uint8_t* smB = smA + p.stages * stage_a;
@@ -340,6 +349,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (p.b_resident) {
                 t5::mbar_arrive_expect_tx(bres_bar, stage_b);
                 t5::tma_load_2d(smB, &tmB, bres_bar, 0, 0);
+                if (p.b_split) t5::tma_load_2d(smB + tile_b, &tmB2, bres_bar, 0, 0);
             }
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int m_tile = t / p.n_tiles, n_tile = t % p.n_tiles;
@@ -347,14 +357,16 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     t5::mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     t5::mbar_arrive_expect_tx(&full_bar[stage], stage_a + (p.b_resident ? 0 : stage_b));
                     t5::tma_load_2d(smA + stage * stage_a, &tmA, &full_bar[stage], kb * p.block_k, m_tile * BLOCK_M);
-                    if (!p.b_resident)
+                    if (!p.b_resident) {
                         t5::tma_load_2d(smB + stage * stage_b, &tmB, &full_bar[stage], kb * p.block_k, n_tile * p.block_n);
+                        if (p.b_split) t5::tma_load_2d(smB + stage * stage_b + tile_b, &tmB2, &full_bar[stage], kb * p.block_k, n_tile * p.block_n);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 0, 0);
+        const uint32_t idesc = t5::make_idesc_f16(BLOCK_M, p.block_n, 0, 0, p.a_bf16, p.b_bf16);
         int stage = 0; uint32_t phase = 0; int it = 0;
         if (p.b_resident) t5::mbar_wait_relaxed(bres_bar, 0);
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -375,6 +387,11 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const uint64_t da = t5::make_smem_desc(a_addr + k * UMMA_K * 2, 16, sbo, ltype);
                         const uint64_t db = t5::make_smem_desc(b_addr + k * UMMA_K * 2, 16, sbo, ltype);
                         t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
+                        if (p.b_split) {
+                            // low weight plane against the same A tile, accumulated into the same TMEM columns
+                            const uint64_t dl = t5::make_smem_desc(b_addr + tile_b + k * UMMA_K * 2, 16, sbo, ltype);
+                            t5::mma_bf16_ss(tmem_d, da, dl, idesc, 1u);
+                        }
                     }
                     t5::mma_commit(&empty_bar[stage]);
                     if (kb == p.k_blocks - 1) t5::mma_commit(&tfull_bar[as]);
@@ -385,6 +402,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9)
+        constexpr bool OH = (F & kEpiOutF16) != 0;    // 16-bit output / residual element type: fp16 or bf16
         const int et = threadIdx.x - 64;              // 0..255
         const int q = warp & 3;                       // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;             // which of the two warps of this quarter
@@ -449,15 +467,15 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         }
                     }
                     if (F & kEpiResidual) {
-                        const __nv_bfloat16* rp = p.residual + m * p.ldr + n0;
+                        const uint16_t* rp = p.residual + m * p.ldr + n0;
                         float f[8];
                         if (n0 < p.N) {
-                            unpack8(ldg_stream(rp), f);
+                            unpack8t<OH>(ldg_stream(rp), f);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) v[k] += f[k];
                         }
                         if (n0 + 8 < p.N) {
-                            unpack8(ldg_stream(rp + 8), f);
+                            unpack8t<OH>(ldg_stream(rp + 8), f);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) v[8 + k] += f[k];
                         }
@@ -470,13 +488,13 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (p.linear_out) {
                     // dense rows of `pitch` bytes (pitch/16 odd => 8 consecutive rows hit 8 different 16-byte bank groups)
                     const uint32_t rowp = cbuf_s + row * p.pitch + c0 * 2;
-                    if (c0 < p.N) sts128(rowp, pack8(v));
-                    if (c0 + 8 < p.N) sts128(rowp + 16, pack8(v + 8));
+                    if (c0 < p.N) sts128(rowp, pack8t<OH>(v));
+                    if (c0 + 8 < p.N) sts128(rowp + 16, pack8t<OH>(v + 8));
                 } else {
                     const uint32_t rowp = cbuf_s + (c0 >> 6) * (BLOCK_M * 128) + row * 128;
                     const int ci = (c0 & 63) >> 3;
-                    sts128(rowp + ((ci ^ (row & 7)) << 4), pack8(v));
-                    sts128(rowp + (((ci + 1) ^ (row & 7)) << 4), pack8(v + 8));
+                    sts128(rowp + ((ci ^ (row & 7)) << 4), pack8t<OH>(v));
+                    sts128(rowp + (((ci + 1) ^ (row & 7)) << 4), pack8t<OH>(v + 8));
                 }
             };
             for (int j = half; j < nchunks; j += 4) {
@@ -507,7 +525,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 4
                         for (int rr = 0; rr < rows_per_slice; ++rr, a += p.pitch) {
                             const uint4 v = lds128(a);
-                            const float2 f0 = unpack2f(v.x), f1 = unpack2f(v.y), f2 = unpack2f(v.z), f3 = unpack2f(v.w);
+                            const float2 f0 = unpack2t<OH>(v.x), f1 = unpack2t<OH>(v.y), f2 = unpack2t<OH>(v.z), f3 = unpack2t<OH>(v.w);
                             fadd2(s2[0], f0); fadd2(s2[1], f1); fadd2(s2[2], f2); fadd2(s2[3], f3);
                             ffma2(q2[0], f0, f0); ffma2(q2[1], f1, f1); ffma2(q2[2], f2, f2); ffma2(q2[3], f3, f3);
                         }
@@ -517,7 +535,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 4
                         for (int rr = r0; rr < r0 + rows_per_slice; ++rr) {
                             const uint4 v = lds128(a0 + rr * 128 + ((ci ^ (rr & 7)) << 4));
-                            const float2 f0 = unpack2f(v.x), f1 = unpack2f(v.y), f2 = unpack2f(v.z), f3 = unpack2f(v.w);
+                            const float2 f0 = unpack2t<OH>(v.x), f1 = unpack2t<OH>(v.y), f2 = unpack2t<OH>(v.z), f3 = unpack2t<OH>(v.w);
                             fadd2(s2[0], f0); fadd2(s2[1], f1); fadd2(s2[2], f2); fadd2(s2[3], f3);
                             ffma2(q2[0], f0, f0); ffma2(q2[1], f1, f1); ffma2(q2[2], f2, f2); ffma2(q2[3], f3, f3);
                         }
@@ -578,6 +596,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 struct WgradKParams {
     int Cin, Cout, block_n, boxes_b, co_tiles, ci_tiles, splits, kb_per_split, k_blocks, stages;
     uint32_t tmem_cols;
+    int convert_x;         // X tiles arrive as fp16 and are rewritten in place as bf16 before the MMAs (see the kernel)
     float* out;            // splits==1: dW [Cin][lddw]; else workspace [split][Cin][Cout]
     int ld_out;
     long long split_stride;
@@ -597,7 +616,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smB + p.stages * stage_b);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* done_bar = empty_bar + kMaxStages;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+    uint64_t* conv_bar = done_bar + 1;                      // [kMaxStages]: X tile of the stage converted to bf16
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(conv_bar + kMaxStages);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -612,7 +632,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (threadIdx.x == 0) {
         t5::tma_prefetch_desc(&tmX);
         t5::tma_prefetch_desc(&tmZ);
-        for (int s = 0; s < p.stages; ++s) { t5::mbar_init(&full_bar[s], 1); t5::mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < p.stages; ++s) { t5::mbar_init(&full_bar[s], 1); t5::mbar_init(&empty_bar[s], 1); t5::mbar_init(&conv_bar[s], 128); }
         t5::mbar_init(done_bar, 1);
         t5::fence_barrier_init();
     }
@@ -641,10 +661,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = t5::make_idesc_bf16(BLOCK_M, p.block_n, 1, 1);
+        // both operands bf16: tcgen05.mma kind::f16 rejects mixed A/B element formats (illegal instruction on sm_100a)
+        const uint32_t idesc = t5::make_idesc_f16(BLOCK_M, p.block_n, 1, 1, 1, 1);
         int stage = 0; uint32_t phase = 0;
         for (int i = 0; i < nkb; ++i) {
-            t5::mbar_wait(&full_bar[stage], phase);
+            t5::mbar_wait(p.convert_x ? &conv_bar[stage] : &full_bar[stage], phase);
             t5::fence_after_thread_sync();
             if (lane == 0) {
                 const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
@@ -664,6 +685,29 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else {
+        if (p.convert_x) {
+            // The activations X are stored in fp16, the gradients dZ in bf16, and the tensor core wants one element format for
+            // both operands: the four (otherwise idle) epilogue warps rewrite each X tile in place as bf16 once its TMA has
+            // landed -- elementwise on 16-byte chunks, so the 128-byte swizzle of the tile is irrelevant -- and hand the stage
+            // to the MMA issuer through conv_bar.  Only the FILTER gradient sees the 8-bit mantissa (a sum over >= 2,145
+            // pixels per weight, so the rounding averages out); the forward path and the data gradients never do.
+            const int et = threadIdx.x - 64;              // 0..127
+            int stage = 0; uint32_t phase = 0;
+            for (int i = 0; i < nkb; ++i) {
+                t5::mbar_wait(&full_bar[stage], phase);
+                const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
+#pragma unroll
+                for (int j = 0; j < (2 * kWgradBoxBytes) / (128 * 16); ++j) {
+                    const uint32_t addr = a_addr + (j * 128 + et) * 16;
+                    float f[8];
+                    unpack8h(lds128(addr), f);
+                    sts128(addr, pack8(f));
+                }
+                t5::fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core's smem reads
+                t5::mbar_arrive(&conv_bar[stage]);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int ci = ci_tile * 128 + row;
@@ -748,6 +792,7 @@ static bool use_v1() {
 
 int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     AMS_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "empty GEMM");
+    AMS_REQUIRE(d.a_fp16 == d.b_fp16, "tcgen05.mma kind::f16 needs the same element format for A and B");
     AMS_REQUIRE(d.lda % 8 == 0 && d.ldb % 8 == 0, "bf16 operand strides must be multiples of 8 elements");
     AMS_REQUIRE(d.out_fp32 || (d.N % 8 == 0 && d.ldc % 8 == 0), "bf16 output needs N, ldc multiples of 8");
     AMS_REQUIRE(!d.out_fp32 || d.ldc % 4 == 0, "fp32 output needs ldc multiple of 4");
@@ -767,36 +812,43 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     }
     npad = plan->block_n * plan->n_tiles;                       // = n_alloc of the kernels
     plan->m_tiles = ceil_div(d.M, BLOCK_M);
-    // small-K layers: a TMA box as wide as the row (32/64-byte swizzle) instead of a mostly out-of-bounds 128-byte box
-    plan->block_k = (plan->v2 && d.K <= 16) ? 16 : ((plan->v2 && d.K <= 32) ? 32 : BLOCK_K);
-    plan->k_blocks = ceil_div(d.K, plan->block_k);
     // v2 runs two CTAs per SM (more epilogue warps in flight): each gets <= 256 TMEM columns and <= ~110 KB smem
     plan->acc_stages = (!plan->v2 || 2 * plan->block_n <= 256) ? 2 : 1;
     plan->tmem_cols = tmem_cols_for(plan->acc_stages * plan->block_n);
     AMS_REQUIRE(plan->tmem_cols <= (plan->v2 ? 256u : 512u), "TMEM overflow");
-    plan->b_resident = (plan->v2 && plan->k_blocks == 1 && plan->n_tiles == 1) ? 1 : 0;
-    const size_t b_tile = size_t(plan->block_n) * plan->block_k * 2;
-    const size_t stage_bytes = size_t(BLOCK_M) * plan->block_k * 2 + (plan->b_resident ? 0 : b_tile);
-    size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 6) * 8 + 16 + (plan->b_resident ? b_tile : 0);
-    size_t budget = kSmemBudget;
-    if (plan->v2) {
-        const int nboxes = ceil_div(plan->block_n, 64);
-        plan->linear_out = (plan->n_tiles == 1 && d.ldc == d.N) ? 1 : 0;
-        plan->pitch = d.N * 2 + (((d.N / 8) % 2 == 0) ? 16 : 0);
-        plan->cbuf_bytes = plan->linear_out ? ((BLOCK_M * plan->pitch + 1023) / 1024) * 1024 : nboxes * BLOCK_M * 128;
-        plan->stage_bufs = (plan->cbuf_bytes <= 16 * 1024) ? 2 : 1;
-        fixed += size_t(plan->stage_bufs) * plan->cbuf_bytes + size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8;
-        budget = 110 * 1024;
+    // small-K layers: a TMA box as wide as the row (32/64-byte swizzle) instead of a mostly out-of-bounds 128-byte box;
+    // a narrower k-block is also the way out when two stages of the widest box do not fit (split weights on N = 256)
+    int block_k = (plan->v2 && d.K <= 16) ? 16 : ((plan->v2 && d.K <= 32) ? 32 : BLOCK_K);
+    for (;; block_k /= 2) {
+        plan->block_k = block_k;
+        plan->k_blocks = ceil_div(d.K, plan->block_k);
+        plan->b_resident = (plan->v2 && plan->k_blocks == 1 && plan->n_tiles == 1) ? 1 : 0;
+        const size_t b_tile = size_t(plan->block_n) * plan->block_k * 2 * (d.B_lo ? 2 : 1);
+        AMS_REQUIRE(!d.B_lo || (size_t(plan->block_n) * plan->block_k * 2) % 512 == 0, "split weights: B tile must be a multiple of 512 bytes");
+        const size_t stage_bytes = size_t(BLOCK_M) * plan->block_k * 2 + (plan->b_resident ? 0 : b_tile);
+        size_t fixed = 1024 /*align slack*/ + size_t(npad) * 8 + (2 * kMaxStages + 6) * 8 + 16 + (plan->b_resident ? b_tile : 0);
+        size_t budget = kSmemBudget;
+        if (plan->v2) {
+            const int nboxes = ceil_div(plan->block_n, 64);
+            plan->linear_out = (plan->n_tiles == 1 && d.ldc == d.N) ? 1 : 0;
+            plan->pitch = d.N * 2 + (((d.N / 8) % 2 == 0) ? 16 : 0);
+            plan->cbuf_bytes = plan->linear_out ? ((BLOCK_M * plan->pitch + 1023) / 1024) * 1024 : nboxes * BLOCK_M * 128;
+            plan->stage_bufs = (plan->cbuf_bytes <= 16 * 1024) ? 2 : 1;
+            fixed += size_t(plan->stage_bufs) * plan->cbuf_bytes + size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8;
+            budget = 110 * 1024;
+        }
+        int stages = budget > fixed ? int((budget - fixed) / stage_bytes) : 0;
+        stages = std::max(2, std::min(stages, kMaxStages));
+        plan->stages = stages;
+        plan->smem_bytes = fixed + stages * stage_bytes;
+        if (plan->smem_bytes <= 227 * 1024 || block_k == 16 || !plan->v2) break;
     }
-    int stages = budget > fixed ? int((budget - fixed) / stage_bytes) : 0;
-    stages = std::max(2, std::min(stages, kMaxStages));
-    plan->stages = stages;
-    plan->smem_bytes = fixed + stages * stage_bytes;
     AMS_REQUIRE(plan->smem_bytes <= 227 * 1024, "GEMM shared memory overflow");
     const int tiles = plan->m_tiles * plan->n_tiles;
     plan->grid = std::min(tiles, (plan->v2 && plan->smem_bytes <= 113 * 1024) ? 2 * num_sms : num_sms);
     if (encode_2d_bf16(&plan->tmA, d.A, d.K, d.M, size_t(d.lda) * 2, plan->block_k, BLOCK_M, plan->block_k * 2)) return -1;
     if (encode_2d_bf16(&plan->tmB, d.B, d.K, d.N, size_t(d.ldb) * 2, plan->block_k, plan->block_n, plan->block_k * 2)) return -1;
+    if (encode_2d_bf16(&plan->tmB2, d.B_lo ? d.B_lo : d.B, d.K, d.N, size_t(d.ldb) * 2, plan->block_k, plan->block_n, plan->block_k * 2)) return -1;
     if (plan->v2 && encode_2d_bf16(&plan->tmC, d.out, d.N, d.M, size_t(d.ldc) * 2, 64, BLOCK_M)) return -1;
     static bool attr_set = false;
     if (!attr_set) {
@@ -804,6 +856,8 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
 #define AMS_G2A(FL) AMS_CUDA_CHECK(cudaFuncSetAttribute(gemm_kmajor_v2_kernel<FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         AMS_G2A(0) AMS_G2A(1) AMS_G2A(2) AMS_G2A(3) AMS_G2A(4) AMS_G2A(5) AMS_G2A(6) AMS_G2A(7)
         AMS_G2A(8) AMS_G2A(9) AMS_G2A(10) AMS_G2A(11) AMS_G2A(12) AMS_G2A(13) AMS_G2A(14) AMS_G2A(15)
+        AMS_G2A(16) AMS_G2A(17) AMS_G2A(18) AMS_G2A(19) AMS_G2A(20) AMS_G2A(21) AMS_G2A(22) AMS_G2A(23)
+        AMS_G2A(24) AMS_G2A(25) AMS_G2A(26) AMS_G2A(27) AMS_G2A(28) AMS_G2A(29) AMS_G2A(30) AMS_G2A(31)
 #undef AMS_G2A
         attr_set = true;
     }
@@ -818,17 +872,21 @@ int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
         p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;
         p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.n_alloc = pl.n_tiles * pl.block_n;
         p.stage_bufs = pl.stage_bufs; p.nboxes = ceil_div(pl.block_n, 64); p.acc_stages = pl.acc_stages; p.block_k = pl.block_k; p.b_resident = pl.b_resident;
+        p.b_split = d.B_lo ? 1 : 0;
         p.linear_out = pl.linear_out; p.pitch = pl.pitch; p.cbuf_bytes = pl.cbuf_bytes;
-        p.out = static_cast<__nv_bfloat16*>(d.out); p.ldc = d.ldc;
+        p.out = static_cast<uint16_t*>(d.out); p.ldc = d.ldc;
+        p.a_bf16 = d.a_fp16 ? 0 : 1; p.b_bf16 = d.b_fp16 ? 0 : 1;
         p.tmem_cols = pl.tmem_cols;
         p.scale = d.scale; p.shift = d.shift; p.rowbias = d.rowbias; p.rows_per_image = d.rows_per_image;
-        p.residual = d.residual; p.ldr = d.ldr; p.act = d.act; p.stats_partial = d.stats_partial;
+        p.residual = static_cast<const uint16_t*>(d.residual); p.ldr = d.ldr; p.act = d.act; p.stats_partial = d.stats_partial;
         const int flags = ((d.scale || d.shift || d.act) ? kEpiAffine : 0) | (d.residual ? kEpiResidual : 0) |
-                          (d.rowbias ? kEpiRowBias : 0) | (d.stats_partial ? kEpiStats : 0);
+                          (d.rowbias ? kEpiRowBias : 0) | (d.stats_partial ? kEpiStats : 0) | (d.out_fp16 ? kEpiOutF16 : 0);
         switch (flags) {
-#define AMS_G2(FL) case FL: AMS_LAUNCH((gemm_kmajor_v2_kernel<FL>), pl.grid, kGemm2Threads, pl.smem_bytes, stream, pl.tmA, pl.tmB, pl.tmC, p); break;
+#define AMS_G2(FL) case FL: AMS_LAUNCH((gemm_kmajor_v2_kernel<FL>), pl.grid, kGemm2Threads, pl.smem_bytes, stream, pl.tmA, pl.tmB, pl.tmB2, pl.tmC, p); break;
             AMS_G2(0) AMS_G2(1) AMS_G2(2) AMS_G2(3) AMS_G2(4) AMS_G2(5) AMS_G2(6) AMS_G2(7)
             AMS_G2(8) AMS_G2(9) AMS_G2(10) AMS_G2(11) AMS_G2(12) AMS_G2(13) AMS_G2(14) AMS_G2(15)
+            AMS_G2(16) AMS_G2(17) AMS_G2(18) AMS_G2(19) AMS_G2(20) AMS_G2(21) AMS_G2(22) AMS_G2(23)
+            AMS_G2(24) AMS_G2(25) AMS_G2(26) AMS_G2(27) AMS_G2(28) AMS_G2(29) AMS_G2(30) AMS_G2(31)
 #undef AMS_G2
         }
         return 0;
@@ -837,11 +895,12 @@ int gemm_launch(const GemmPlan& pl, cudaStream_t stream) {
     p.M = d.M; p.N = d.N; p.K = d.K;
     p.block_n = pl.block_n; p.n_tiles = pl.n_tiles; p.num_tiles = pl.m_tiles * pl.n_tiles;
     p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.n_alloc = pl.n_tiles * pl.block_n;
-    p.tmem_cols = pl.tmem_cols;
-    p.out = d.out; p.ldc = d.ldc; p.out_fp32 = d.out_fp32;
+    p.tmem_cols = pl.tmem_cols; p.b_split = d.B_lo ? 1 : 0;
+    p.out = d.out; p.ldc = d.ldc; p.out_fp32 = d.out_fp32; p.out_fp16 = d.out_fp16;
+    p.a_bf16 = d.a_fp16 ? 0 : 1; p.b_bf16 = d.b_fp16 ? 0 : 1;
     p.scale = d.scale; p.shift = d.shift; p.rowbias = d.rowbias; p.rows_per_image = d.rows_per_image;
     p.residual = d.residual; p.ldr = d.ldr; p.act = d.act;
-    AMS_LAUNCH((gemm_kmajor_kernel), pl.grid, kGemmThreads, pl.smem_bytes, stream, pl.tmA, pl.tmB, p);
+    AMS_LAUNCH((gemm_kmajor_kernel), pl.grid, kGemmThreads, pl.smem_bytes, stream, pl.tmA, pl.tmB, pl.tmB2, p);
     return 0;
 }
 
@@ -880,7 +939,8 @@ int wgrad_plan(const WgradDesc& d, int num_sms, WgradPlan* plan) {
                 "wgrad workspace too small");
     plan->tmem_cols = tmem_cols_for(plan->block_n);
     const size_t stage_bytes = size_t(2 + plan->boxes_b) * kWgradBoxBytes;
-    const size_t fixed = 1024 + (2 * kMaxStages + 2) * 8 + 16;
+    AMS_REQUIRE(!d.z_fp16, "the filter-gradient GEMM takes bf16 gradients");
+    const size_t fixed = 1024 + (3 * kMaxStages + 2) * 8 + 16;
     // below the full 227 KB: the filter gradients run on a side stream and must leave room for the chain CTAs on the same SM
     static const size_t wg_budget = [] { const char* e = getenv("AMS_WGRAD_SMEM_KB"); return e ? size_t(atoi(e)) * 1024 : kWgradSmemBudget; }();
     int stages = int((wg_budget - fixed) / stage_bytes);
@@ -902,6 +962,7 @@ int wgrad_launch(const WgradPlan& pl, cudaStream_t stream) {
     p.Cin = d.Cin; p.Cout = d.Cout; p.block_n = pl.block_n; p.boxes_b = pl.boxes_b;
     p.co_tiles = pl.co_tiles; p.ci_tiles = pl.ci_tiles; p.splits = pl.splits; p.kb_per_split = pl.kb_per_split;
     p.k_blocks = pl.k_blocks; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.convert_x = d.x_fp16 ? 1 : 0;
     if (pl.splits == 1) { p.out = d.dW; p.ld_out = d.lddw; p.split_stride = 0; }
     else { p.out = d.workspace; p.ld_out = d.Cout; p.split_stride = static_cast<long long>(d.Cin) * d.Cout; }
     const int grid = pl.ci_tiles * pl.co_tiles * pl.splits;

@@ -1,11 +1,13 @@
 // Launch interfaces of the non-GEMM kernels (HBM-bound byte/elementwise/reduction work).
-// All tensors NHWC; activations bf16, statistics / parameters / gradients fp32, counters int64.
+// All tensors NHWC; forward activations fp16 (act_t), activation gradients bf16, statistics / parameters / parameter
+// gradients fp32, counters int64.
 #pragma once
 #include "common.cuh"
 
 namespace ams {
 
-typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat16 bf16;     // activation GRADIENTS (range matters)
+typedef __half act_t;           // forward ACTIVATIONS and 1x1 weight operands (precision matters: DESIGN.md 3)
 
 struct Conv2dGeom {          // one image-plane geometry; TF 'SAME' pads resolved on the host
     int N, H, W, C;          // input
@@ -16,10 +18,10 @@ struct Conv2dGeom {          // one image-plane geometry; TF 'SAME' pads resolve
 
 // ---- stem: pad(127.5) + (x*2/255-1) + 3x3 s2 conv 3->32, fused (SURVEY K1+K2)
 // in: u8 or f32 [N,H,W,3] un-padded frame; the graph's 1-px bottom/right mean-pixel pad is virtual.
-// out bf16 [N,Ho,Wo,32]; scale/shift != null => y = relu6(acc*scale+shift) (frozen BN fold), else raw z.
+// out fp16 [N,Ho,Wo,32]; scale/shift != null => y = relu6(acc*scale+shift) (frozen BN fold), else raw z.
 int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
                   int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w /*[3,3,3,32]*/,
-                  const float* scale, const float* shift, bf16* out, cudaStream_t s);
+                  const float* scale, const float* shift, act_t* out, cudaStream_t s);
 // dW[3,3,3,32] = sum_pixels patch(in) (x) dz ; partials [chunks][864] then fixed-order reduce.
 int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo,
                          int pad_top, int pad_left, float pad_value, float norm_scale, float norm_shift,
@@ -27,10 +29,10 @@ int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int 
 size_t stem_bwd_workspace_floats(int N, int Ho, int Wo);
 
 // ---- depthwise 3x3
-int dw_conv_fwd(const bf16* in, const float* w /*[3,3,C]*/, const Conv2dGeom& g, const float* scale,
-                const float* shift, int act, bf16* out, cudaStream_t s);
+int dw_conv_fwd(const act_t* in, const float* w /*[3,3,C]*/, const Conv2dGeom& g, const float* scale,
+                const float* shift, int act, act_t* out, cudaStream_t s);
 int dw_conv_bwd_data(const bf16* dz, const float* w, const Conv2dGeom& g, bf16* dx, cudaStream_t s);
-int dw_conv_bwd_filter(const bf16* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
+int dw_conv_bwd_filter(const act_t* x, const bf16* dz, const Conv2dGeom& g, float* dw, float* workspace,
                        size_t workspace_floats, cudaStream_t s);
 size_t dw_bwd_workspace_floats(const Conv2dGeom& g);
 // shared-memory tiled forward (dw_tiled.cu): optional BN+act of the PRODUCER applied while staging the input
@@ -38,8 +40,8 @@ size_t dw_bwd_workspace_floats(const Conv2dGeom& g);
 // stats[tile][2][C] (sum, sum of squares of the stored bf16 values) for bn_finalize_partials.
 bool dw_tiled_supported(const Conv2dGeom& g);
 long long dw_tiled_stats_rows(const Conv2dGeom& g);
-int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const float* in_scale, const float* in_shift,
-                      int in_act, const float* out_scale, const float* out_shift, int out_act, bf16* out, double* stats,
+int dw_conv_fwd_tiled(const act_t* in, const float* w, const Conv2dGeom& g, const float* in_scale, const float* in_shift,
+                      int in_act, const float* out_scale, const float* out_shift, int out_act, act_t* out, double* stats,
                       int* stats_rows, cudaStream_t s);
 
 // fused backward (dw_tiled.cu): BN backward of the depthwise layer applied while (g, z) is staged, data gradient +
@@ -47,8 +49,8 @@ int dw_conv_fwd_tiled(const bf16* in, const float* w, const Conv2dGeom& g, const
 // mask applied to the stored gradient, column sums for the producer's BN backward.  coef = [3][C] (A, B, Cc) of
 // bn_backward_reduce.  in_scale == null: `zin` is the (materialised) input activation and bn_partial is not written.
 struct DwBwdFused {
-    const bf16* g; const bf16* z; const float* scale; const float* shift; int act; const float* coef;
-    const bf16* zin; const float* in_scale; const float* in_shift; int in_act;
+    const bf16* g; const act_t* z; const float* scale; const float* shift; int act; const float* coef;
+    const act_t* zin; const float* in_scale; const float* in_shift; int in_act;
     const float* w;
     bf16* gout; float* dw;                  // [N,H,W,C] gradient wrt the producer's BN output (masked); dW [9][C]
     float* dw_partial; size_t dw_partial_floats;    // >= dw_bwd_fused_rows * 9 * C
@@ -87,35 +89,35 @@ struct BnLayer {            // device pointers into the parameter / state arenas
     float* scale; float* shift;                // y = z*scale + shift
 };
 size_t bn_workspace_doubles(long long M, int C);
-// batch statistics of z (bf16 [M,C]) -> scale/shift/mean/rstd (+ moving-average update)
-int bn_forward_stats(const bf16* z, const BnLayer& L, int update_moving, double* workspace, cudaStream_t s);
+// batch statistics of z (fp16 [M,C]) -> scale/shift/mean/rstd (+ moving-average update)
+int bn_forward_stats(const act_t* z, const BnLayer& L, int update_moving, double* workspace, cudaStream_t s);
 // same, from per-chunk partial sums a producer kernel already wrote: partial[chunk][0][C] = sum, [chunk][1][C] = sum sq
 int bn_finalize_partials(const double* partial, int chunks, const BnLayer& L, int update_moving, cudaStream_t s);
 // y = act(z*scale+shift) (+ residual)
-int bn_apply(const bf16* z, const float* scale, const float* shift, int act, const bf16* residual, bf16* y,
+int bn_apply(const act_t* z, const float* scale, const float* shift, int act, const act_t* residual, act_t* y,
              long long M, int C, cudaStream_t s);
 // frozen fold: scale = gamma*rsqrt(mv_var+eps), shift = beta - mv_mean*scale
 int bn_fold_frozen(const float* gamma, const float* beta, const float* mv_mean, const float* mv_var, float eps,
                    float* scale, float* shift, int C, cudaStream_t s);
 // backward: given dy (grad wrt act(BN(z))) and z; writes dz (dz_out may alias dy), d_gamma, d_beta.
 // If dy2 != null the incoming gradient is dy + dy2 (two consumers).
-int bn_backward(const bf16* dy, const bf16* dy2, const bf16* z, const BnLayer& L, int act, bf16* dz_out,
+int bn_backward(const bf16* dy, const bf16* dy2, const act_t* z, const BnLayer& L, int act, bf16* dz_out,
                 float* d_gamma, float* d_beta, double* workspace, cudaStream_t s);
 
 // the three pieces of bn_backward, for callers that fuse the apply pass (or the reduce pass) into another kernel:
 // column sums of (dy masked, dy masked * z) -> coef [3][C] (dz = A*g + B*z + Cc), d_gamma, d_beta
-int bn_backward_reduce(const bf16* dy, const bf16* z, const BnLayer& L, int act, float* coef, float* d_gamma, float* d_beta,
+int bn_backward_reduce(const bf16* dy, const act_t* z, const BnLayer& L, int act, float* coef, float* d_gamma, float* d_beta,
                        double* workspace, cudaStream_t s);
 // same from per-tile partial sums [rows][2][C] a producer kernel wrote (dy already masked)
 int bn_backward_finalize_partials(const double* partial, int rows, const BnLayer& L, float* coef, float* d_gamma,
                                   float* d_beta, cudaStream_t s);
 // dz = A*dy + B*z + Cc for an already-masked dy (dz_out may alias dy)
-int bn_backward_apply(const bf16* dy_masked, const bf16* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s);
+int bn_backward_apply(const bf16* dy_masked, const act_t* z, const BnLayer& L, const float* coef, bf16* dz_out, cudaStream_t s);
 
 // ---- ASPP image-pooling branch folded into a per-image bias
 struct ImgPoolFwd {
     int N, HW, Cin /*320*/, Cmid /*256*/, Cout /*256*/;
-    const bf16* feat;            // [N,HW,Cin]
+    const act_t* feat;           // [N,HW,Cin]
     const float* w_pool;         // [Cin][Cmid]
     const float* w_proj_top;     // concat_projection rows 0..Cmid-1: [Cmid][Cout]
     BnLayer bn;                  // image_pooling BN (M = N)
@@ -180,7 +182,8 @@ int resize_u8(const uint8_t* src, int n, int sh, int sw, int cn, uint8_t* dst, i
 
 // ---- generic reductions
 // colsum[g][c] = sum over rows of group g (rows_per_group consecutive rows) of x[row][c]   (deterministic)
-int colsum_groups(const float* x_f32, const bf16* x_bf16, int ld, long long rows_per_group, int groups, int C,
+// exactly one of x_f32 / x_bf16 / x_fp16 is non-null
+int colsum_groups(const float* x_f32, const bf16* x_bf16, const act_t* x_fp16, int ld, long long rows_per_group, int groups, int C,
                   float scale, float* out, double* workspace, cudaStream_t s);
 size_t colsum_workspace_doubles(int groups, int C);
 
@@ -211,8 +214,10 @@ int unpack_delta_mask(const uint8_t* bits, const VarSeg* segs_dev, int nseg, lon
 int unpack_delta_values(float* params, const uint8_t* mask, long long n, const unsigned int* block_offsets, int nblocks,
                         const __half* vals, cudaStream_t s);
 
-// fp32 HWIO 1x1 weights -> bf16 [Cout][Cin] (forward B operand) and bf16 [Cin][ldb] (dgrad B operand)
-struct WeightCast { const float* w; bf16* w_fwd; bf16* w_bwd; int Cin, Cout, ld_fwd, ld_bwd; int row0, rows; };
+// fp32 HWIO 1x1 weights -> fp16 [Cout][Cin] (forward B operand, multiplies fp16 activations) and bf16 [Cin][ldb] (dgrad B
+// operand, multiplies bf16 gradients)
+// w_lo != null: the forward operand is split, w_fwd = fp16(w), w_lo = fp16(w - w_fwd)
+struct WeightCast { const float* w; act_t* w_fwd; act_t* w_lo; bf16* w_bwd; int Cin, Cout, ld_fwd, ld_bwd; int row0, rows; };
 int cast_weights(const WeightCast* table_dev, int n_layers, int max_elems, cudaStream_t s);
 
 }  // namespace ams

@@ -175,6 +175,10 @@ int net_build_topology(Net* net) {
             w16_off = (w16_off + 63) & ~63LL;
             d.wbwd_off = w16_off; w16_off += static_cast<long long>(d.k_rows) * d.ld_bwd;
             w16_off = (w16_off + 63) & ~63LL;
+            if (d.cout <= kSplitWeightMaxCout) {
+                d.wlo_off = w16_off; w16_off += static_cast<long long>(d.cout) * d.ld_fwd;
+                w16_off = (w16_off + 63) & ~63LL;
+            }
         }
     }
     net->n_bf16 = w16_off;
@@ -276,6 +280,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             GemmDesc g;
             g.A = p->buf[d.input].y; g.lda = L[d.input].cout;
             g.B = net->wpool + d.wfwd_off; g.ldb = d.ld_fwd;
+            if (d.wlo_off >= 0) g.B_lo = net->wpool + d.wlo_off;
             g.M = static_cast<int>(M); g.N = d.cout; g.K = d.k_rows;
             if (d.name == "concat_projection") { g.rowbias = p->bias_img; g.rows_per_image = d.out_h * d.out_w; }
             if (d.kind == kLogits) {
@@ -341,6 +346,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             GemmDesc g;
             if (d.kind == kLogits) { g.A = p->dlogits_bf16; g.lda = 32; g.K = 32; }
             else { g.A = p->buf[i].gz; g.lda = d.cout; g.K = d.cout; }
+            g.a_fp16 = 0; g.b_fp16 = 0; g.out_fp16 = 0;      // bf16 gradient x bf16 transposed weights -> bf16 gradient
             g.B = net->wpool + d.wbwd_off; g.ldb = d.ld_bwd;
             g.M = static_cast<int>(M); g.N = d.k_rows;
             g.out = p->buf[d.input].g; g.ldc = L[d.input].cout;
@@ -358,6 +364,11 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
 }
 
 // ---------------------------------------------------------------------------------------------- weights
+// Frozen (client) graph: trim_graph_frozen(kill_norms=True) replaces every FusedBatchNormV3 by the `_patch` op that
+// tf.layers.batch_normalization(training=False) created (reference utils/graph_utils.py:362-369, :52-76), whose epsilon
+// is the layer default 1e-3 for all 54 layers -- including image_pooling / aspp0 / concat_projection, which TRAIN with
+// epsilon 1.001e-5.
+constexpr float kFrozenBnEps = 1e-3f;
 int net_prepare_weights(Net* net, bool frozen) {
     if (net->weights_dirty) {
         if (cast_weights(net->cast_table, net->cast_layers, net->cast_max, net->stream)) return -1;
@@ -367,7 +378,7 @@ int net_prepare_weights(Net* net, bool frozen) {
         for (const LayerDef& d : net->layers) {
             if (!d.has_bn || d.kind == kImagePool) continue;
             if (bn_fold_frozen(net->params + d.gamma_off, net->params + d.beta_off, net->moving + d.mm_off,
-                               net->moving + d.mv_off, d.eps, fscale(net, d), fshift(net, d), d.cout, net->stream)) return -1;
+                               net->moving + d.mv_off, kFrozenBnEps, fscale(net, d), fshift(net, d), d.cout, net->stream)) return -1;
         }
         net->fold_dirty = false;
     }
@@ -386,6 +397,7 @@ static ImgPoolFwd imgpool_desc(Net* net, Plan* p, bool frozen, bool update_movin
     a.w_proj_top = net->params + cp.w_off;
     a.bn = bn_layer(net, d, p->N);
     a.frozen = frozen; a.update_moving = update_moving;
+    if (frozen) a.bn.eps = kFrozenBnEps;
     a.pooled = p->pooled; a.z = p->ip_z; a.act = p->ip_act; a.bias_img = p->bias_img; a.ws = p->small_ws;
     return a;
 }
@@ -424,7 +436,7 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
             PROF("gemm_logits", 2.0 * M * d.cin + 4.0 * M * 32, gemm_launch(p->fwd_frozen[i], s));
             continue;
         }
-        bf16* conv_out = frozen ? b.y : b.z;
+        act_t* conv_out = frozen ? b.y : b.z;
         int dw_rows = 0;
         const float* sc = frozen ? fscale(net, d) : nullptr;
         const float* sh = frozen ? fshift(net, d) : nullptr;
@@ -493,9 +505,9 @@ int net_backward(Net* net, Plan* p, bool normalize) {
         AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
         AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
         forked = true;
-        if (colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, net->side_stream)) return -1;
+        if (colsum_groups(p->dlogits_f32, nullptr, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, net->side_stream)) return -1;
     } else {
-        PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
+        PROF("bias_grad", 4.0 * M16 * 32, colsum_groups(p->dlogits_f32, nullptr, nullptr, 32, M16, 1, lg.cout, 1.f, net->grads + lg.bias_off, p->small_ws, s));
     }
     if (side) { if (wgrad_on_side(p->wgrad[nl - 1])) return -1; }
     else PROF("gemm_wgrad", 2.0 * M16 * (lg.cin + 32), wgrad_launch(p->wgrad[nl - 1], s));

@@ -17,6 +17,11 @@
 namespace ams {
 
 enum LayerKind { kStem = 0, kConv1x1 = 1, kDepthwise = 2, kImagePool = 3, kLogits = 4 };
+// Forward 1x1 convs with at most this many output channels (one N tile: every project conv, the head, the early expand
+// convs) run on split fp16 weights W = hi + lo (two MMAs per k-step against the same A tile).  Rounding the PROJECT
+// weights to plain fp16 was the largest single term of the end-to-end logit error (oracle ablation); for
+// the wide expand convs the second plane buys nothing measurable and would cost their 2-CTAs-per-SM shared-memory budget.
+constexpr int kSplitWeightMaxCout = 256;
 
 struct VarInfo {
     std::string name;
@@ -40,12 +45,13 @@ struct LayerDef {
     long long bn_off = -1;     // offset into the per-layer BN vector pool (units of floats, 6 vectors of cout)
     // bf16 weight copies (elements into the bf16 pool), 1x1 layers only
     long long wfwd_off = -1, wbwd_off = -1;
+    long long wlo_off = -1;    // low plane of the split forward weights (layers with cout <= kSplitWeightMaxCout), else -1
     int ld_fwd = 0, ld_bwd = 0, k_rows0 = 0, k_rows = 0;   // HWIO row window used by the GEMM (concat_projection: 256..511)
     // geometry at the configured frame size (per image)
     int in_h = 0, in_w = 0, out_h = 0, out_w = 0, pad_top = 0, pad_left = 0;
 };
 
-struct LayerBuf { bf16* z = nullptr; bf16* y = nullptr; bf16* g = nullptr; bf16* gz = nullptr; };
+struct LayerBuf { act_t* z = nullptr; act_t* y = nullptr; bf16* g = nullptr; bf16* gz = nullptr; };   // forward fp16, gradients bf16
 
 struct Plan {
     int N = 0;
@@ -120,7 +126,7 @@ struct Net {
     uint8_t* mask = nullptr; bool mask_all_ones = true;
     float beta1_power = 0.9f, beta2_power = 0.999f;
     float* bnpool = nullptr;                // per layer: scale, shift, mean, rstd (training) + fscale, fshift (frozen)
-    bf16* wpool = nullptr;
+    uint16_t* wpool = nullptr;              // 16-bit GEMM operand copies of the 1x1 weights: fp16 [Cout][Cin] (forward), bf16 [Cin][Cout] (dgrad)
     WeightCast* cast_table = nullptr; int cast_layers = 0, cast_max = 0;
     VarSeg* segs_dev = nullptr; long long mask_bytes = 0;
     SelectScratch* select_sc = nullptr;

@@ -207,7 +207,7 @@ pack_scatter_kernel(const float* __restrict__ params, const uint8_t* __restrict_
     }
 }
 
-// fp32 HWIO [Cin][Cout] -> bf16 [Cout][ld_fwd] (transposed) and bf16 [Cin][ld_bwd]
+// fp32 HWIO [Cin][Cout] -> fp16 [Cout][ld_fwd] (transposed) and bf16 [Cin][ld_bwd]
 __global__ void __launch_bounds__(256)
 cast_weights_kernel(const WeightCast* __restrict__ table) {
     pdl_entry();
@@ -216,9 +216,10 @@ cast_weights_kernel(const WeightCast* __restrict__ table) {
     if (i >= t.rows * t.Cout) return;
     const int ci = i / t.Cout, co = i % t.Cout;              // ci relative to row0
     const float w = t.w[static_cast<long long>(t.row0 + ci) * t.Cout + co];
-    const bf16 b = __float2bfloat16_rn(w);
-    if (t.w_fwd) t.w_fwd[static_cast<long long>(co) * t.ld_fwd + ci] = b;
-    if (t.w_bwd) t.w_bwd[static_cast<long long>(ci) * t.ld_bwd + co] = b;
+    const act_t hi = __float2half_rn(w);                                                          // |w| << 65504
+    if (t.w_fwd) t.w_fwd[static_cast<long long>(co) * t.ld_fwd + ci] = hi;
+    if (t.w_lo) t.w_lo[static_cast<long long>(co) * t.ld_fwd + ci] = __float2half_rn(__fsub_rn(w, __half2float(hi)));
+    if (t.w_bwd) t.w_bwd[static_cast<long long>(ci) * t.ld_bwd + co] = __float2bfloat16_rn(w);
 }
 
 }  // namespace

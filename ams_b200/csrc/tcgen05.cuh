@@ -131,10 +131,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
-// Instruction descriptor (32 bit), kind::f16: c_format=F32 [4,6)=1, a/b_format=BF16 [7,10),[10,13)=1,
+// Instruction descriptor (32 bit), kind::f16: c_format=F32 [4,6)=1, a/b_format [7,10),[10,13): 0 = F16, 1 = BF16,
 // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29).
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// a_bf16 / b_bf16: element format of each operand, 1 = BF16, 0 = F16 (they may differ).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_major, int b_mn_major, int a_bf16, int b_bf16) {
+    return (1u << 4) | (static_cast<uint32_t>(a_bf16) << 7) | (static_cast<uint32_t>(b_bf16) << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
            (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }

@@ -12,8 +12,10 @@ Differences, all at the edges of the hot path:
     generator for tests and benchmarks); nothing else in the loop knows where frames come from;
   * the delta file is written from `SemanticNetwork.delta_bytes()` (packed on the device, byte-identical to the host
     writer of run.py:316-328); the client can apply it in place (`apply_delta`) or reload the exported model;
-  * H.264 up-link emulation (`compress_uplink`) needs /usr/bin/ffmpeg exactly like the reference and is refused with
-    a clear message when it is absent; the PNG accounting path is the default; plotting is out of scope.
+  * H.264 up-link emulation (`compress_uplink`: two-pass ffmpeg encode + re-decode of the sampled frames, reference
+    run.py:196-260) is NOT built -- it is outside the hot path (out of scope) -- and the flag is refused with
+    NotImplementedError rather than silently falling back; the PNG accounting path (the reference's default) is what
+    runs, and frame_memory only ever holds RGB frames at the network size; plotting is out of scope.
 """
 import argparse
 import os
@@ -157,10 +159,8 @@ def get_save_dir(flags, prepend):
 def _resize_pair(flags, frame, label):
     import cv2
     size = (flags.height * 2, flags.height)
-    if flags.compress_uplink:
-        frame = cv2.resize(frame, (size[0] * 2, size[1] * 2))
-    else:
-        frame = cv2.cvtColor(cv2.resize(frame, size), cv2.COLOR_BGR2RGB)
+    # reference run.py:181-183 (PNG path): network-size RGB frame, nearest-neighbour label map
+    frame = cv2.cvtColor(cv2.resize(frame, size), cv2.COLOR_BGR2RGB)
     return frame, cv2.resize(label, size, interpolation=cv2.INTER_NEAREST)
 
 
@@ -189,8 +189,9 @@ def train_model(flags, source, train_start, train_end, sampling_period, gpu_id, 
                 sample_send_period, log=print):
     """Server side (run.py:78-361).  Returns a dict of the per-period logs it also writes to `<run_label>_results_*`."""
     assert train_end - train_start != 0, 'There should be at least one set of data points'
-    if flags.compress_uplink and not os.path.exists('/usr/bin/ffmpeg'):
-        raise RuntimeError('compress_uplink needs /usr/bin/ffmpeg (H.264 up-link emulation is outside the B200 hot path)')
+    if flags.compress_uplink:
+        raise NotImplementedError('compress_uplink (two-pass H.264 encode / re-decode of the up-link through ffmpeg, reference '
+                                  'run.py:196-260) is outside the B200 hot path and not built: run without it (PNG accounting)')
     fps = source.fps
     train_end_frame = train_end * fps
     i = train_start * fps

@@ -162,6 +162,9 @@ class Student:
     def queue_size(self):
         return self._L.ams_queue_size(self._h)
 
+    def queue_clear(self):
+        return self._L.ams_queue_clear(self._h)
+
     # ------------------------------------------------------------------ inference
     def _label_buffer(self, n):
         """Fresh int32 [n,H,W] array in page-locked host memory (torch's caching host allocator recycles the blocks):
@@ -325,4 +328,5 @@ class Student:
     def get_activation(self, index, shape, which=0):
         a = np.empty(shape, dtype=np.uint16)
         nat.check(self._L.ams_get_activation(self._h, index, which, _ptr(a), a.size), 'get_activation')
-        return (a.astype(np.uint32) << 16).view(np.float32)
+        # forward tensors are IEEE fp16, gradients (which == 2) bf16
+        return a.view(np.float16).astype(np.float32) if which != 2 else (a.astype(np.uint32) << 16).view(np.float32)

@@ -82,6 +82,9 @@ int ams_enqueue(ams_net* net, const void* frames, int frames_dtype, const uint8_
 int ams_enqueue_raw(ams_net* net, const uint8_t* frames, int src_h, int src_w, int bgr_to_rgb, const uint8_t* labels,
                     int lab_h, int lab_w, int n);
 int ams_queue_size(ams_net* net);
+/* drops every staged batch (returns how many): what a caller does after a failed training phase so that stale training
+ * batches are not dequeued by the next predict_input (the reference would leave them in its FIFOQueue) */
+int ams_queue_clear(ams_net* net);
 
 /* ---- inference on the oldest queued batch.
  * sess.run(predictions) -- SemanticNetwork.py:173 (frozen), :179 (batch statistics).  out_labels int32 [n,H,W] */
@@ -160,8 +163,9 @@ int ams_get_gradients(ams_net* net, float* host);                     /* trainab
 int ams_num_layers(const ams_net* net);
 int ams_layer_info(const ams_net* net, int index, char* name, int name_capacity, int* kind, int* cin, int* cout,
                    int* stride, int* dilation, int* act, float* bn_eps, float* bn_one_minus_decay, int* residual_from);
-/* activation of conv layer `index` from the last run: which = 0 post-BN/act output, 1 raw conv output (training) */
-int ams_get_activation(ams_net* net, int index, int which, uint16_t* host_bf16, long long count);
+/* tensor of conv layer `index` from the last run as raw 16-bit words: which = 0 post-BN/act output (IEEE fp16),
+ * 1 raw conv output (training; fp16), 2 gradient wrt the layer output (bf16) */
+int ams_get_activation(ams_net* net, int index, int which, uint16_t* host_bits16, long long count);
 
 /* ---- per-kernel-group device timing (CUDA events on the launching stream), for bench.py's roofline line.
  * report: one line per group "<tag> <launches> <total_ms> <algorithmic_bytes>"; returns the text length */
@@ -183,37 +187,41 @@ int ams_layout_layer_info(int num_classes, int graph_variant, int index, char* n
 int ams_debug_dw_tile(int n, int h, int w, int c, int ho, int wo, int stride, int dilation, int* out8);
 int ams_debug_dw_bwd_tile(int n, int h, int w, int c, int ho, int wo, int stride, int dilation, int* out8);
 
-/* ---- op-level entry points on raw DEVICE pointers (kernel unit tests; see tests/test_ops_gpu.py) */
-int ams_op_conv1x1(const void* a_bf16, const void* w_bf16 /*[N][K]*/, int M, int N, int K, const float* scale,
-                   const float* shift, const float* rowbias, int rows_per_image, const void* residual_bf16, int act,
-                   void* out, int out_fp32, int ldc, void* stream);
-int ams_op_wgrad(const void* x_bf16, int cin, const void* dz_bf16, int cout, long long M, float* dw, void* stream);
-int ams_op_depthwise(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
-                     const float* scale, const float* shift, int act, void* out_bf16, void* stream);
+/* ---- op-level entry points on raw DEVICE pointers (kernel unit tests; see tests/test_ops_gpu.py).
+ * Storage types: forward activations and the 1x1 weight operands are IEEE fp16 (`_f16`), activation gradients bf16
+ * (`_bf16`); accumulation, statistics, parameters and parameter gradients are fp32. */
+/* grad_types == 0: forward conv (a, w fp16; out / residual fp16); != 0: data gradient (a, w bf16; out / residual bf16).
+ * w_lo_16 != NULL: split weights, out = a*w^T + a*w_lo^T in one fp32 accumulator (w = fp16(W), w_lo = fp16(W - w)) */
+int ams_op_conv1x1(const void* a_16, const void* w_16 /*[N][K]*/, int M, int N, int K, const float* scale,
+                   const float* shift, const float* rowbias, int rows_per_image, const void* residual_16, int act,
+                   void* out, int out_fp32, int ldc, int grad_types, const void* w_lo_16, void* stream);
+int ams_op_wgrad(const void* x_f16, int cin, const void* dz_bf16, int cout, long long M, float* dw, void* stream);
+int ams_op_depthwise(const void* in_f16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
+                     const float* scale, const float* shift, int act, void* out_f16, void* stream);
 /* cv2.resize on DEVICE buffers: [n,src_h,src_w,channels] u8 -> [n,dst_h,dst_w,channels]; nearest != 0: INTER_NEAREST
  * (1 channel), else INTER_LINEAR (1 or 3 channels; swap_rb exchanges channels 0 and 2 on the way out) */
 int ams_op_resize_u8(const void* src, int n, int src_h, int src_w, int channels, void* dst, int dst_h, int dst_w, int nearest,
                      int swap_rb, void* stream);
 /* tiled depthwise with the producer's BN+act applied while staging the input (in_scale/in_shift may be NULL) and the
  * batch statistics of the stored output: stats_out[2][c] fp64 DEVICE = column sums (sum, sum of squares) */
-int ams_op_depthwise_fused(const void* in_bf16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
-                           const float* in_scale, const float* in_shift, int in_act, void* out_bf16, double* stats_out,
+int ams_op_depthwise_fused(const void* in_f16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
+                           const float* in_scale, const float* in_shift, int in_act, void* out_f16, double* stats_out,
                            void* stream);
 /* fused depthwise backward (see ams_b200/csrc/dw_tiled.cu): coef = [3][c] BN-backward coefficients of the depthwise
  * layer; zin = raw output of the producer whose BN (in_scale/in_shift) + activation is recomputed; bn_sums [2][c] fp64
  * DEVICE = column sums (masked gradient, masked gradient * zin) for the producer's BN backward */
-int ams_op_depthwise_bwd_fused(const void* g_bf16, const void* z_bf16, const float* scale, const float* shift, int act,
-                               const float* coef, const void* zin_bf16, const float* in_scale, const float* in_shift,
+int ams_op_depthwise_bwd_fused(const void* g_bf16, const void* z_f16, const float* scale, const float* shift, int act,
+                               const float* coef, const void* zin_f16, const float* in_scale, const float* in_shift,
                                int in_act, const float* w, int n, int h, int w_, int c, int stride, int dilation,
                                void* gout_bf16, float* dw, double* bn_sums, void* stream);
-int ams_op_depthwise_bwd(const void* x_bf16, const void* dz_bf16, const float* w, int n, int h, int w_, int c, int stride,
+int ams_op_depthwise_bwd(const void* x_f16, const void* dz_bf16, const float* w, int n, int h, int w_, int c, int stride,
                          int dilation, void* dx_bf16, float* dw, void* stream);
 int ams_op_stem(const void* frames, int frames_dtype, int n, int h, int w_, const float* w, const float* scale,
-                const float* shift, void* out_bf16, void* stream);
+                const float* shift, void* out_f16, void* stream);
 int ams_op_stem_bwd(const void* frames, int frames_dtype, int n, int h, int w_, const void* dz_bf16, float* dw, void* stream);
-int ams_op_bn_train(const void* z_bf16, long long M, int C, const float* gamma, const float* beta, float eps, int act,
-                    const void* residual_bf16, void* y_bf16, float* mean, float* rstd, void* stream);
-int ams_op_bn_backward(const void* dy_bf16, const void* z_bf16, long long M, int C, const float* gamma, const float* beta,
+int ams_op_bn_train(const void* z_f16, long long M, int C, const float* gamma, const float* beta, float eps, int act,
+                    const void* residual_f16, void* y_f16, float* mean, float* rstd, void* stream);
+int ams_op_bn_backward(const void* dy_bf16, const void* z_f16, long long M, int C, const float* gamma, const float* beta,
                        float eps, int act, void* dz_bf16, float* dgamma, float* dbeta, void* stream);
 int ams_op_head_infer(const float* logits, int n, int h, int w_, int ldl, int H, int W, int class_count,
                       const int* class_indices, int label_depth, const uint8_t* labels, int32_t* pred, int64_t* confmat,

@@ -234,6 +234,10 @@ class MetaGraphInterpreter:
                 x, gamma, beta = I(0), I(1), I(2)
                 eps = n.attr['epsilon'].f
                 if bn_override == 'moving':
+                    # the frozen client graph swaps EVERY FusedBatchNormV3 for the `_patch` op that
+                    # tf.layers.batch_normalization(training=False) creates (utils/graph_utils.py:362-369, :52-76):
+                    # default epsilon 1e-3, also for the three ASPP layers whose training-graph epsilon is 1.001e-5
+                    eps = 1e-3
                     base = name[:-len('FusedBatchNormV3')]
                     mean = to_float(variables[base + 'moving_mean:0'])
                     var = to_float(variables[base + 'moving_variance:0'])

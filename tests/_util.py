@@ -47,7 +47,13 @@ def call(fn, *args):
 
 
 def bf16_round(t):
+    """storage rounding of activation GRADIENTS"""
     return t.to(torch.bfloat16).to(torch.float32)
+
+
+def ac_round(t):
+    """storage rounding of forward ACTIVATIONS and 1x1 weight operands (IEEE fp16, saturating)"""
+    return t.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)
 
 
 def err_stats(name, got, ref, rtol, atol):

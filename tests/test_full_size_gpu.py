@@ -130,4 +130,4 @@ def test_one_full_size_frame_against_fp32_oracle(world):
     rel = float((logits - sem).norm() / sem.norm())
     agree = float((pred == so.full_res_logits(sem, H, W)[..., CLS].argmax(3).numpy()).mean())     # reduced class space
     log('full size frame: logits rel-L2 vs fp32 oracle %.4f, argmax agreement %.4f' % (rel, agree))
-    assert rel <= 0.08 and agree >= 0.90
+    assert rel <= 0.02 and agree >= 0.99          # random-init stress checkpoint; trained-student bounds: test_parity_e2e_gpu.py

@@ -150,3 +150,20 @@ def test_orchestration_controllers_follow_run_py():
     assert np.array_equal(fa, fb) and np.array_equal(ga, gb) and fa.shape == (64, 128, 3) and ga.dtype == np.uint8
     f = run.parse_flags(['--mode', 'simple', '--height', '64', '--enable_ASR'])
     assert f.mode == 'simple' and f.height == 64 and f.enable_ASR and not f.enable_ATR and f.iter == 200
+
+
+def test_compress_uplink_is_refused_and_sampled_frames_are_rgb_at_network_size():
+    """the H.264 up-link emulation is not built, so the flag must fail loudly (never train on 2x-size BGR
+    frames with PNG sizes reported as H.264), and what enters frame_memory is RGB at the network size."""
+    from ams_b200 import run as ams_run
+    flags = ams_run.default_flags()
+    flags.compress_uplink = True
+    with pytest.raises(NotImplementedError):
+        ams_run.train_model(flags, ams_run.SyntheticSource(16, 32, fps=2), 0, 2, 1, '0', 'x', 12, [0, 1], 1)
+    flags.compress_uplink = False
+    flags.height = 8
+    bgr = np.zeros((16, 32, 3), np.uint8)
+    bgr[..., 0] = 200                                      # blue in BGR
+    frame, label = ams_run._resize_pair(flags, bgr, np.full((16, 32), 3, np.uint8))
+    assert frame.shape == (8, 16, 3) and label.shape == (8, 16)
+    assert frame[..., 2].min() == 200 and frame[..., 0].max() == 0      # converted to RGB

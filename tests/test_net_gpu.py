@@ -2,15 +2,16 @@
 ams_select_topk / ams_pack_delta) against the CPU oracle on the same seeded inputs.
 
 How parity is judged (DESIGN.md "numerics"):
-  * TEACHER-FORCED, per layer: every conv unit of the CUDA path is re-computed by the oracle (precision='bf16',
+  * TEACHER-FORCED, per layer: every conv unit of the CUDA path is re-computed by the oracle (precision='fp16',
     i.e. the reference algorithm with the declared storage precision) from the CUDA path's OWN input tensors;
-    outputs must agree to one bf16 ulp.  This isolates each kernel inside the real end-to-end run.
+    outputs must agree to one fp16 spacing.  This isolates each kernel inside the real end-to-end run.
   * integer results are bit-exact given the same inputs: argmax given the device logits, confusion matrix, mIoU,
     the selection mask given the device deltas, the packed delta bytes, Adam given the device gradients.
-  * END-TO-END against the fp32 reference arithmetic: relative L2 of the logits <= 8 % and argmax agreement >= 90 %
-    on the conditioned synthetic checkpoint -- the calibrated cost of bf16 storage through 53 layers
-    (oracle/calibrate_tolerance.py: 3-4 % / 94-96 %); a random BN/ReLU stack amplifies rounding noise ~30x, so a
-    tighter end-to-end bound would not be honest.
+  * END-TO-END against the fp32 reference arithmetic on the seeded RANDOM-INIT checkpoint used here (a stress case: a
+    random BN/ReLU stack amplifies rounding noise ~30x, no trained network does): relative L2 of the logits <= 2 % and
+    argmax agreement >= 97 % (measured 0.5-0.9 % / 98.6-99.0 %; bf16 storage gave 3-4 % / 91-97 %).  The end-to-end
+    assertions at north_star's tolerance, un-forced, on a TRAINED student and at BASELINE's sizes are in
+    tests/test_parity_e2e_gpu.py.
 """
 import os
 
@@ -24,7 +25,7 @@ from ams_b200 import _native as nat
 from ams_b200.student import Student
 
 pytestmark = pytest.mark.gpu
-ULP = 2.0 ** -7
+ULP = 2.0 ** -10          # one fp16 spacing (both sides round: a value on a rounding boundary may flip)
 H, W, N = 64, 128, 2
 
 
@@ -59,7 +60,7 @@ def layer_inputs(spec, st, i, acts, frames, params, n, mode):
     elif c['name'] == 'concat_projection':
         feat = dev('MobilenetV2/expanded_conv_16/project').mean(dim=(1, 2), keepdim=True)
         ip = spec['convs'][idx['image_pooling']]
-        pooled = so.layer_forward(ip, params, feat, None, None, mode, 'bf16')['y']
+        pooled = so.layer_forward(ip, params, feat, None, None, mode, so.DEVICE_PRECISION)['y']
         src = dev('aspp0')
     elif c['input'] == 'input':
         src = so.preprocess(spec, frames.astype(np.float32))
@@ -77,7 +78,7 @@ def run_layerwise(mode, bn_mode):
     pred = st.infer(N, bn_mode)
     keep = {}
     with torch.no_grad():
-        sem_ref, _ = so.forward(spec, params, fr.astype(np.float32), bn_mode=mode, precision='bf16', keep=keep)
+        sem_ref, _ = so.forward(spec, params, fr.astype(np.float32), bn_mode=mode, precision=so.DEVICE_PRECISION, keep=keep)
         sem_f32, _ = so.forward(spec, params, fr.astype(np.float32), bn_mode=mode, precision='fp32')
     acts, zs = {}, {}
     for i, c in enumerate(spec['convs']):
@@ -93,7 +94,7 @@ def run_layerwise(mode, bn_mode):
             if c['name'] == 'image_pooling':
                 continue
             c, src, res, pooled = layer_inputs(spec, st, i, acts, fr, params, N, mode)
-            r = so.layer_forward(c, params, src, res, pooled, mode, 'bf16')
+            r = so.layer_forward(c, params, src, res, pooled, mode, so.DEVICE_PRECISION)
             if c['name'] == 'logits/semantic':
                 got = torch.from_numpy(st.get_logits(N))
                 ok, _ = err_stats('[%s] %-44s logits' % (mode, c['name']), got, r['y'], 1e-4, 2e-4)
@@ -101,15 +102,15 @@ def run_layerwise(mode, bn_mode):
                 logits_dev = got
                 continue
             if mode == 'batch':
-                ok, _ = err_stats('[%s] %-44s z' % (mode, c['name']), zs[i], r['z'], ULP, 4e-3)
+                ok, _ = err_stats('[%s] %-44s z' % (mode, c['name']), zs[i], r['z'], ULP, 5e-4)
                 all_ok &= ok
                 bn = c['bn']
                 y, _, _ = so.batch_norm(zs[i], params[bn['gamma']], params[bn['beta']], np.float32(bn['eps']).item(), 'batch')
                 y = {None: y, 'relu': y.clamp_min(0), 'relu6': y.clamp(0, 6)}[c['act']]
-                ref = so._bf16_ste(y + res) if res is not None else so._bf16_ste(y)
+                ref = so._fp16_ste(y + res) if res is not None else so._fp16_ste(y)
             else:
                 ref = r['out']
-            ok, _ = err_stats('[%s] %-44s y' % (mode, c['name']), acts[i], ref, ULP, 4e-3)
+            ok, _ = err_stats('[%s] %-44s y' % (mode, c['name']), acts[i], ref, ULP, 5e-4)
             all_ok &= ok
     # integer parity: argmax of the device logits
     full = so.full_res_logits(logits_dev, H, W)
@@ -119,12 +120,12 @@ def run_layerwise(mode, bn_mode):
     rel32 = float((logits_dev - sem_f32).norm() / sem_f32.norm())
     relbf = float((logits_dev - sem_ref).norm() / sem_ref.norm())
     agree32 = float((pred == so.full_res_logits(sem_f32, H, W).argmax(3).numpy()).mean())
-    log('[%s] argmax(device logits) exact %.6f | e2e logits rel-L2 vs fp32 oracle %.4f (max %.3f), vs bf16 oracle %.4f | '
+    log('[%s] argmax(device logits) exact %.6f | e2e logits rel-L2 vs fp32 oracle %.4f (max %.3f), vs fp16-storage oracle %.4f | '
         'argmax agreement vs fp32 oracle %.4f' % (mode, exact, rel32, float((logits_dev - sem_f32).abs().max()), relbf, agree32))
     st.close()
     assert all_ok
     assert exact == 1.0
-    assert rel32 <= 0.08 and agree32 >= 0.90
+    assert rel32 <= 0.02 and agree32 >= 0.97
 
 
 def test_frozen_inference_layerwise():
@@ -191,11 +192,11 @@ def test_train_step_against_oracle(tag, n, h, w, cls):
     st.enqueue(fr, labels)
     loss = st.train_step(1e-3, masked=False)
     g_dev = st.split_trainable(st.get_gradients())
-    ts = so.TrainState(spec, V, precision='bf16')
+    ts = so.TrainState(spec, V, precision=so.DEVICE_PRECISION)
     keep = {}
     with torch.no_grad():
         so.forward(spec, {k: torch.tensor(v) for k, v in V.items()}, fr.astype(np.float32), bn_mode='batch',
-                   precision='bf16', keep=keep)
+                   precision=so.DEVICE_PRECISION, keep=keep)
     forced = {}
     for i, c in enumerate(spec['convs']):
         if c['name'] in ('image_pooling', 'logits/semantic'):
@@ -205,7 +206,7 @@ def test_train_step_against_oracle(tag, n, h, w, cls):
         forced[c['name']] = torch.from_numpy(st.get_activation(i, shape, 0))
     loss_free, g_free, stats, _ = ts.loss_and_grads(fr.astype(np.float32), labels, np.array(cls))
     loss_ref, g_ref, _, _ = ts.loss_and_grads(fr.astype(np.float32), labels, np.array(cls), forced=forced)
-    log('train step loss: device %.6f  oracle(bf16, teacher-forced) %.6f  oracle(bf16, free) %.6f' % (loss, loss_ref, loss_free))
+    log('train step loss: device %.6f  oracle(fp16 storage, teacher-forced) %.6f  oracle(fp16 storage, free) %.6f' % (loss, loss_ref, loss_free))
     assert abs(loss - loss_ref) < 2e-3 * max(1.0, abs(loss_ref))
     gmax = max(float(np.linalg.norm(v)) for v in g_ref.values())
     worst, worst_free, worst_rel = 1.0, 1.0, 0.0
@@ -334,8 +335,8 @@ def test_voc_graph_runs_and_matches_layout():
     assert logits.shape[-1] == 21
     assert np.array_equal(pred, so.full_res_logits(logits, H, W).argmax(3).numpy())
     with torch.no_grad():
-        sem, _ = so.forward(spec, {k: torch.tensor(v) for k, v in V.items()}, fr.astype(np.float32), precision='bf16')
+        sem, _ = so.forward(spec, {k: torch.tensor(v) for k, v in V.items()}, fr.astype(np.float32), precision=so.DEVICE_PRECISION)
     rel = float((logits - sem).norm() / sem.norm())
-    log('VOC graph e2e rel-L2 vs bf16 oracle %.4f' % rel)
-    assert rel < 0.08
+    log('VOC graph e2e rel-L2 vs fp16-storage oracle %.4f' % rel)
+    assert rel < 0.02
     st.close()

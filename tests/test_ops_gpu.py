@@ -1,7 +1,8 @@
 """Kernel-level parity (GPU box): every CUDA kernel, called through the C ABI's op-level entry points on
 torch-owned device buffers, against the oracle's restatement of the same TF op on the same inputs.
-Tolerances: bf16 outputs are compared at one bf16 ulp (2^-8 relative) plus fp32 accumulation slack; integer
-outputs (argmax given logits, confusion matrix, selection mask, Adam in fp32 IEEE ops) are bit-exact."""
+Storage types: forward activations / 1x1 weight operands fp16 (AC), activation gradients bf16 (BF).
+Tolerances: 16-bit outputs are compared at one ulp of their type (fp16 2^-11, bf16 2^-8 relative) plus fp32
+accumulation slack; integer outputs (argmax given logits, confusion matrix, selection mask, Adam in fp32 IEEE ops) are bit-exact."""
 import ctypes as C
 
 import numpy as np
@@ -9,13 +10,15 @@ import pytest
 import torch
 
 import student_oracle as so
-from _util import P, bf16_round, call, err_stats, log, stream_ptr
+from _util import P, ac_round, bf16_round, call, err_stats, log, stream_ptr
 from ams_b200 import _native as nat
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 BF = torch.bfloat16
-ULP = 2.0 ** -8
+AC = torch.float16
+ULP = 2.0 ** -8           # bf16
+AULP = 2.0 ** -11         # fp16
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -27,13 +30,56 @@ def rnd(*shape, seed=0, scale=1.0):
                                    (2145, 160, 960), (5000, 384, 64), (2145, 320, 256), (129, 576, 160), (640, 64, 384)])
 def test_conv1x1_plain(M, K, N):
     L = nat.lib()
-    a = bf16_round(rnd(M, K, seed=1))
-    w = bf16_round(rnd(N, K, seed=2, scale=(2.0 / K) ** 0.5))
+    a = ac_round(rnd(M, K, seed=1))
+    w = ac_round(rnd(N, K, seed=2, scale=(2.0 / K) ** 0.5))
     ref = a @ w.t()
-    out = torch.full((M, N), float('nan'), dtype=BF, device=DEV)
-    call(L.ams_op_conv1x1, P(a.to(DEV, BF)), P(w.to(DEV, BF)), M, N, K, None, None, None, 1, None, 0, P(out), 0, N, stream_ptr())
+    out = torch.full((M, N), float('nan'), dtype=AC, device=DEV)
+    call(L.ams_op_conv1x1, P(a.to(DEV, AC)), P(w.to(DEV, AC)), M, N, K, None, None, None, 1, None, 0, P(out), 0, N, 0, None, stream_ptr())
     torch.cuda.synchronize()
-    ok, _ = err_stats('conv1x1 plain M%d K%d N%d' % (M, K, N), out, ref, ULP, 1e-3)
+    ok, _ = err_stats('conv1x1 plain M%d K%d N%d' % (M, K, N), out, ref, AULP, 2e-4)
+    assert ok
+
+
+@pytest.mark.parametrize('M,K,N,fp32out', [(2145, 960, 160, False), (1000, 96, 24, False), (4097, 32, 16, False), (2145, 320, 256, False),
+                                           (2145, 256, 19, True), (700, 16, 96, False)])
+def test_conv1x1_split_weights(M, K, N, fp32out):
+    """Forward convs with <= 256 output channels: W = hi + lo, both planes fp16, two MMAs per k-step into one fp32
+    accumulator.  The result must match the product with the (almost) full-precision weight hi + lo -- and differ
+    from the plain-fp16-weight product by far more than the tolerance, or the second plane is not being used."""
+    L = nat.lib()
+    a = ac_round(rnd(M, K, seed=51))
+    w32 = rnd(N, K, seed=52, scale=(2.0 / K) ** 0.5)
+    hi = ac_round(w32)
+    lo = ac_round(w32 - hi)
+    ref = a.double() @ (hi.double() + lo.double()).t()
+    ldc = 32 if fp32out else N
+    out = torch.full((M, ldc), float('nan'), dtype=torch.float32 if fp32out else AC, device=DEV)
+    call(L.ams_op_conv1x1, P(a.to(DEV, AC)), P(hi.to(DEV, AC)), M, N, K, None, None, None, 1, None, 0, P(out), 1 if fp32out else 0, ldc, 0,
+         P(lo.to(DEV, AC)), stream_ptr())
+    torch.cuda.synchronize()
+    got = out[:, :N]
+    ok, _ = err_stats('conv1x1 split weights M%d K%d N%d fp32out%d' % (M, K, N, fp32out), got, ref.float(), 1e-6 if fp32out else AULP,
+                      2e-5 if fp32out else 2e-4)
+    assert ok
+    if fp32out:
+        plain = (a.double() @ hi.double().t()).float()
+        assert float((got.float().cpu() - plain).abs().max()) > 1e-4          # the low plane contributes
+
+
+@pytest.mark.parametrize('M,K,N,res', [(2145, 320, 960, False), (1000, 24, 144, True), (4097, 16, 32, False), (2145, 32, 256, False)])
+def test_conv1x1_data_gradient_types(M, K, N, res):
+    """The data-gradient GEMM: bf16 gradient x bf16 copy of the transposed weights -> bf16 gradient (+ bf16 skip gradient).
+    (tcgen05.mma kind::f16 wants one element format for both operands: the forward GEMM is fp16 x fp16.)"""
+    L = nat.lib()
+    a = bf16_round(rnd(M, K, seed=41, scale=0.01))
+    w = bf16_round(rnd(N, K, seed=42, scale=(2.0 / K) ** 0.5))
+    r = bf16_round(rnd(M, N, seed=43, scale=0.01)) if res else None
+    ref = a @ w.t() + (r if res else 0.0)
+    out = torch.full((M, N), float('nan'), dtype=BF, device=DEV)
+    call(L.ams_op_conv1x1, P(a.to(DEV, BF)), P(w.to(DEV, BF)), M, N, K, None, None, None, 1, P(r.to(DEV, BF)) if res else None, 0,
+         P(out), 0, N, 1, None, stream_ptr())
+    torch.cuda.synchronize()
+    ok, _ = err_stats('conv1x1 dgrad types M%d K%d N%d res%d' % (M, K, N, res), out, ref, ULP, 1e-5)
     assert ok
 
 
@@ -41,11 +87,11 @@ def test_conv1x1_plain(M, K, N):
                                                 (2 * 2145, 256, 256, 1, False, 2145), (777, 192, 32, 0, True, 0)])
 def test_conv1x1_epilogue(M, K, N, act, res, rows):
     L = nat.lib()
-    a = bf16_round(rnd(M, K, seed=3))
-    w = bf16_round(rnd(N, K, seed=4, scale=(2.0 / K) ** 0.5))
+    a = ac_round(rnd(M, K, seed=3))
+    w = ac_round(rnd(N, K, seed=4, scale=(2.0 / K) ** 0.5))
     scale = torch.rand(N) + 0.5
     shift = rnd(N, seed=5)
-    r = bf16_round(rnd(M, N, seed=6)) if res else None
+    r = ac_round(rnd(M, N, seed=6)) if res else None
     rb = rnd(M // rows, N, seed=7) if rows else None
     ref = a @ w.t()
     if rows:
@@ -54,23 +100,23 @@ def test_conv1x1_epilogue(M, K, N, act, res, rows):
     ref = {0: ref, 1: ref.clamp_min(0), 2: ref.clamp(0, 6)}[act]
     if res:
         ref = ref + r
-    out = torch.full((M, N), float('nan'), dtype=BF, device=DEV)
-    call(L.ams_op_conv1x1, P(a.to(DEV, BF)), P(w.to(DEV, BF)), M, N, K, P(scale.to(DEV)), P(shift.to(DEV)),
-         P(rb.to(DEV)) if rows else None, max(rows, 1), P(r.to(DEV, BF)) if res else None, act, P(out), 0, N, stream_ptr())
+    out = torch.full((M, N), float('nan'), dtype=AC, device=DEV)
+    call(L.ams_op_conv1x1, P(a.to(DEV, AC)), P(w.to(DEV, AC)), M, N, K, P(scale.to(DEV)), P(shift.to(DEV)),
+         P(rb.to(DEV)) if rows else None, max(rows, 1), P(r.to(DEV, AC)) if res else None, act, P(out), 0, N, 0, None, stream_ptr())
     torch.cuda.synchronize()
-    ok, _ = err_stats('conv1x1 epilogue M%d K%d N%d act%d res%d rb%d' % (M, K, N, act, res, rows), out, ref, ULP, 2e-3)
+    ok, _ = err_stats('conv1x1 epilogue M%d K%d N%d act%d res%d rb%d' % (M, K, N, act, res, rows), out, ref, AULP, 4e-4)
     assert ok
 
 
 def test_conv1x1_logits_fp32():
     L = nat.lib()
     M, K, N = 2145, 256, 19
-    a = bf16_round(rnd(M, K, seed=8))
-    w = bf16_round(rnd(N, K, seed=9, scale=0.1))
+    a = ac_round(rnd(M, K, seed=8))
+    w = ac_round(rnd(N, K, seed=9, scale=0.1))
     bias = rnd(N, seed=10)
     ref = a @ w.t() + bias
     out = torch.full((M, 32), float('nan'), dtype=torch.float32, device=DEV)
-    call(L.ams_op_conv1x1, P(a.to(DEV, BF)), P(w.to(DEV, BF)), M, N, K, None, P(bias.to(DEV)), None, 1, None, 0, P(out), 1, 32, stream_ptr())
+    call(L.ams_op_conv1x1, P(a.to(DEV, AC)), P(w.to(DEV, AC)), M, N, K, None, P(bias.to(DEV)), None, 1, None, 0, P(out), 1, 32, 0, None, stream_ptr())
     torch.cuda.synchronize()
     ok, _ = err_stats('conv1x1 logits fp32', out[:, :N], ref, 1e-5, 1e-4)
     assert ok
@@ -81,17 +127,17 @@ def test_conv1x1_logits_fp32():
                                         (4290, 160, 960), (8385, 192, 32), (2145, 256, 24), (1000, 320, 256), (100, 32, 16)])
 def test_wgrad(M, Cin, Cout):
     L = nat.lib()
-    x = bf16_round(rnd(M, Cin, seed=11))
-    dz = bf16_round(rnd(M, Cout, seed=12, scale=0.05))
-    ref = (x.double().t() @ dz.double()).float()
+    x = ac_round(rnd(M, Cin, seed=11))                        # activations: fp16 in HBM ...
+    dz = bf16_round(rnd(M, Cout, seed=12, scale=0.05))        # gradients: bf16
+    ref = (bf16_round(x).double().t() @ dz.double()).float()  # ... rewritten as bf16 tile by tile inside the kernel
     dw = torch.full((Cin, Cout), float('nan'), dtype=torch.float32, device=DEV)
-    call(L.ams_op_wgrad, P(x.to(DEV, BF)), Cin, P(dz.to(DEV, BF)), Cout, M, P(dw), stream_ptr())
+    call(L.ams_op_wgrad, P(x.to(DEV, AC)), Cin, P(dz.to(DEV, BF)), Cout, M, P(dw), stream_ptr())
     torch.cuda.synchronize()
     ok, _ = err_stats('wgrad M%d Cin%d Cout%d' % (M, Cin, Cout), dw, ref, 1e-4, 1e-5 * float(ref.abs().max()) + 1e-6)
     assert ok
     # determinism: a second run is bit-identical (fixed-order split-K reduction)
     dw2 = torch.empty_like(dw)
-    call(L.ams_op_wgrad, P(x.to(DEV, BF)), Cin, P(dz.to(DEV, BF)), Cout, M, P(dw2), stream_ptr())
+    call(L.ams_op_wgrad, P(x.to(DEV, AC)), Cin, P(dz.to(DEV, BF)), Cout, M, P(dw2), stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal(dw, dw2)
 
@@ -104,19 +150,19 @@ def _dw_ref(x, w, stride, dil):
                                                 (1, 64, 30, 144, 2, 1), (1, 9, 17, 384, 1, 1), (3, 5, 7, 576, 1, 2)])
 def test_depthwise_fwd(n, h, w, c, stride, dil):
     L = nat.lib()
-    x = bf16_round(rnd(n, h, w, c, seed=13))
+    x = ac_round(rnd(n, h, w, c, seed=13))
     wt = rnd(3, 3, c, seed=14, scale=0.4)
     scale = torch.rand(c) + 0.5
     shift = rnd(c, seed=15, scale=0.5)
     raw = _dw_ref(x, wt, stride, dil)
     ho, wo = raw.shape[1], raw.shape[2]
-    out = torch.full((n, ho, wo, c), float('nan'), dtype=BF, device=DEV)
-    call(L.ams_op_depthwise, P(x.to(DEV, BF)), P(wt.to(DEV)), n, h, w, c, stride, dil, None, None, 0, P(out), stream_ptr())
+    out = torch.full((n, ho, wo, c), float('nan'), dtype=AC, device=DEV)
+    call(L.ams_op_depthwise, P(x.to(DEV, AC)), P(wt.to(DEV)), n, h, w, c, stride, dil, None, None, 0, P(out), stream_ptr())
     torch.cuda.synchronize()
-    ok1, _ = err_stats('depthwise raw %s s%d d%d' % ((n, h, w, c), stride, dil), out, raw, ULP, 1e-3)
-    call(L.ams_op_depthwise, P(x.to(DEV, BF)), P(wt.to(DEV)), n, h, w, c, stride, dil, P(scale.to(DEV)), P(shift.to(DEV)), 2, P(out), stream_ptr())
+    ok1, _ = err_stats('depthwise raw %s s%d d%d' % ((n, h, w, c), stride, dil), out, raw, AULP, 2e-4)
+    call(L.ams_op_depthwise, P(x.to(DEV, AC)), P(wt.to(DEV)), n, h, w, c, stride, dil, P(scale.to(DEV)), P(shift.to(DEV)), 2, P(out), stream_ptr())
     torch.cuda.synchronize()
-    ok2, _ = err_stats('depthwise fold+relu6 %s s%d d%d' % ((n, h, w, c), stride, dil), out, (raw * scale + shift).clamp(0, 6), ULP, 2e-3)
+    ok2, _ = err_stats('depthwise fold+relu6 %s s%d d%d' % ((n, h, w, c), stride, dil), out, (raw * scale + shift).clamp(0, 6), AULP, 4e-4)
     assert ok1 and ok2
 
 
@@ -127,19 +173,18 @@ def test_depthwise_fused_bn_on_load_and_stats(n, h, w, c, stride, dil):
     is never materialised; conv zero padding stays zero AFTER the activation) and the batch statistics of the stored
     bf16 output come out of the same kernel."""
     L = nat.lib()
-    z = bf16_round(rnd(n, h, w, c, seed=23, scale=2.0))
+    z = ac_round(rnd(n, h, w, c, seed=23, scale=2.0))
     wt = rnd(3, 3, c, seed=24, scale=0.4)
     sc = torch.rand(c) + 0.5
     sh = rnd(c, seed=25, scale=0.5)
-    y = bf16_round(torch.addcmul(sh, z, sc).clamp(0, 6))            # fmaf(z, sc, sh): one rounding like the kernel
-    y = bf16_round((z.double() * sc.double() + sh.double()).float().clamp(0, 6))
+    y = ac_round((z.double() * sc.double() + sh.double()).float().clamp(0, 6))   # fmaf(z, sc, sh): one rounding like the kernel
     raw = _dw_ref(y, wt, stride, dil)
-    out = torch.full(raw.shape, float('nan'), dtype=BF, device=DEV)
+    out = torch.full(raw.shape, float('nan'), dtype=AC, device=DEV)
     stats = torch.full((2, c), float('nan'), dtype=torch.float64, device=DEV)
-    call(L.ams_op_depthwise_fused, P(z.to(DEV, BF)), P(wt.to(DEV)), n, h, w, c, stride, dil, P(sc.to(DEV)), P(sh.to(DEV)), 2,
+    call(L.ams_op_depthwise_fused, P(z.to(DEV, AC)), P(wt.to(DEV)), n, h, w, c, stride, dil, P(sc.to(DEV)), P(sh.to(DEV)), 2,
          P(out), P(stats), stream_ptr())
     torch.cuda.synchronize()
-    ok, _ = err_stats('depthwise fused (BN on load) %s s%d d%d' % ((n, h, w, c), stride, dil), out, raw, ULP, 2e-3)
+    ok, _ = err_stats('depthwise fused (BN on load) %s s%d d%d' % ((n, h, w, c), stride, dil), out, raw, AULP, 4e-4)
     assert ok
     o = out.float().cpu().double().reshape(-1, c)
     assert torch.allclose(stats[0].cpu(), o.sum(0), rtol=1e-6, atol=1e-4)
@@ -149,14 +194,14 @@ def test_depthwise_fused_bn_on_load_and_stats(n, h, w, c, stride, dil):
 @pytest.mark.parametrize('n,h,w,c,stride,dil', [(2, 33, 65, 32, 1, 1), (1, 65, 129, 96, 2, 1), (2, 17, 33, 960, 1, 2), (1, 64, 30, 144, 2, 1)])
 def test_depthwise_bwd(n, h, w, c, stride, dil):
     L = nat.lib()
-    x = bf16_round(rnd(n, h, w, c, seed=16)).requires_grad_(True)
+    x = ac_round(rnd(n, h, w, c, seed=16)).requires_grad_(True)
     wt = rnd(3, 3, c, seed=17, scale=0.4).requires_grad_(True)
     y = _dw_ref(x, wt, stride, dil)
     dz = bf16_round(rnd(*y.shape, seed=18, scale=0.1))
     y.backward(dz)
     dx = torch.full((n, h, w, c), float('nan'), dtype=BF, device=DEV)
     dw = torch.full((3, 3, c), float('nan'), dtype=torch.float32, device=DEV)
-    call(L.ams_op_depthwise_bwd, P(x.detach().to(DEV, BF)), P(dz.to(DEV, BF)), P(wt.detach().to(DEV)), n, h, w, c, stride, dil, P(dx), P(dw), stream_ptr())
+    call(L.ams_op_depthwise_bwd, P(x.detach().to(DEV, AC)), P(dz.to(DEV, BF)), P(wt.detach().to(DEV)), n, h, w, c, stride, dil, P(dx), P(dw), stream_ptr())
     torch.cuda.synchronize()
     ok1, _ = err_stats('depthwise dX %s s%d d%d' % ((n, h, w, c), stride, dil), dx, x.grad, ULP, 1e-4)
     ok2, _ = err_stats('depthwise dW %s s%d d%d' % ((n, h, w, c), stride, dil), dw, wt.grad, 1e-4, 1e-5 * float(wt.grad.abs().max()))
@@ -174,16 +219,16 @@ def _fma32(a, b, c):
 def test_depthwise_bwd_fused(n, h, w, c, stride, dil):
     """Fused depthwise backward: BN-backward apply of the depthwise layer while staging (g, z), filter + data gradient,
     the producer's BN + ReLU6 recomputed from its raw output, the activation mask on the stored gradient and the column
-    sums for the producer's BN backward -- against autograd through the same (bf16-stored) tensors."""
+    sums for the producer's BN backward -- against autograd through the same stored tensors (fp16 activations, bf16 gradients)."""
     L = nat.lib()
-    zin = bf16_round(rnd(n, h, w, c, seed=31, scale=2.0))
+    zin = ac_round(rnd(n, h, w, c, seed=31, scale=2.0))
     isc = torch.rand(c, generator=torch.Generator().manual_seed(32)) + 0.5
     ish = rnd(c, seed=33, scale=0.5)
     pre = _fma32(zin, isc, ish)
-    x = bf16_round(pre.clamp(0, 6)).requires_grad_(True)
+    x = ac_round(pre.clamp(0, 6)).requires_grad_(True)
     wt = rnd(3, 3, c, seed=34, scale=0.4).requires_grad_(True)
     y = _dw_ref(x, wt, stride, dil)
-    z = bf16_round(y.detach())
+    z = ac_round(y.detach())
     g = bf16_round(rnd(*y.shape, seed=35, scale=0.1))
     sc2 = torch.rand(c, generator=torch.Generator().manual_seed(36)) + 0.5
     sh2 = rnd(c, seed=37, scale=0.5) + 1.0
@@ -198,8 +243,8 @@ def test_depthwise_bwd_fused(n, h, w, c, stride, dil):
     gout = torch.full((n, h, w, c), float('nan'), dtype=BF, device=DEV)
     dw = torch.full((3, 3, c), float('nan'), dtype=torch.float32, device=DEV)
     sums = torch.full((2, c), float('nan'), dtype=torch.float64, device=DEV)
-    call(L.ams_op_depthwise_bwd_fused, P(g.to(DEV, BF)), P(z.to(DEV, BF)), P(sc2.to(DEV)), P(sh2.to(DEV)), 2, P(coef.to(DEV)),
-         P(zin.to(DEV, BF)), P(isc.to(DEV)), P(ish.to(DEV)), 2, P(wt.detach().to(DEV)), n, h, w, c, stride, dil, P(gout), P(dw),
+    call(L.ams_op_depthwise_bwd_fused, P(g.to(DEV, BF)), P(z.to(DEV, AC)), P(sc2.to(DEV)), P(sh2.to(DEV)), 2, P(coef.to(DEV)),
+         P(zin.to(DEV, AC)), P(isc.to(DEV)), P(ish.to(DEV)), 2, P(wt.detach().to(DEV)), n, h, w, c, stride, dil, P(gout), P(dw),
          P(sums), stream_ptr())
     torch.cuda.synchronize()
     tag = '%s s%d d%d' % ((n, h, w, c), stride, dil)
@@ -224,15 +269,15 @@ def test_stem(n, h, w, u8):
     dz = bf16_round(rnd(*raw.shape, seed=20, scale=0.1))
     raw.backward(dz)
     frames = torch.from_numpy(fr).to(DEV) if u8 else torch.from_numpy(fr.astype(np.float32)).to(DEV)
-    out = torch.full((n, ho, wo, 32), float('nan'), dtype=BF, device=DEV)
+    out = torch.full((n, ho, wo, 32), float('nan'), dtype=AC, device=DEV)
     call(L.ams_op_stem, P(frames), 0 if u8 else 1, n, h, w, P(wt.detach().to(DEV)), None, None, P(out), stream_ptr())
     torch.cuda.synchronize()
-    ok1, _ = err_stats('stem raw %s u8=%d' % ((n, h, w), u8), out, raw, ULP, 1e-3)
+    ok1, _ = err_stats('stem raw %s u8=%d' % ((n, h, w), u8), out, raw, AULP, 2e-4)
     scale = torch.rand(32) + 0.5
     shift = rnd(32, seed=21, scale=0.5)
     call(L.ams_op_stem, P(frames), 0 if u8 else 1, n, h, w, P(wt.detach().to(DEV)), P(scale.to(DEV)), P(shift.to(DEV)), P(out), stream_ptr())
     torch.cuda.synchronize()
-    ok2, _ = err_stats('stem fold+relu6 %s' % ((n, h, w),), out, (raw.detach() * scale + shift).clamp(0, 6), ULP, 2e-3)
+    ok2, _ = err_stats('stem fold+relu6 %s' % ((n, h, w),), out, (raw.detach() * scale + shift).clamp(0, 6), AULP, 4e-4)
     dw = torch.full((3, 3, 3, 32), float('nan'), dtype=torch.float32, device=DEV)
     call(L.ams_op_stem_bwd, P(frames), 0 if u8 else 1, n, h, w, P(dz.to(DEV, BF)), P(dw), stream_ptr())
     torch.cuda.synchronize()
@@ -243,10 +288,10 @@ def test_stem(n, h, w, u8):
 @pytest.mark.parametrize('M,C,act,res', [(2 * 33 * 65, 64, 2, False), (4 * 129 * 257, 16, 0, True), (2145, 960, 2, False), (1000, 144, 1, False)])
 def test_bn_train_and_backward(M, C, act, res):
     L = nat.lib()
-    z = bf16_round(rnd(M, C, seed=22) * (torch.rand(C) + 0.5) + rnd(C, seed=23)).requires_grad_(True)
+    z = ac_round(rnd(M, C, seed=22) * (torch.rand(C) + 0.5) + rnd(C, seed=23)).requires_grad_(True)
     gamma = (torch.rand(C) + 0.5).requires_grad_(True)
     beta = rnd(C, seed=24, scale=0.5).requires_grad_(True)
-    r = bf16_round(rnd(M, C, seed=25)) if res else None
+    r = ac_round(rnd(M, C, seed=25)) if res else None
     eps = 1e-3
     y, mean, _ = so.batch_norm(z.view(1, 1, M, C), gamma, beta, eps, 'batch')
     y = y.view(M, C)
@@ -255,14 +300,14 @@ def test_bn_train_and_backward(M, C, act, res):
     yo = y + r if res else y
     dy = bf16_round(rnd(M, C, seed=26, scale=0.01))
     yo.backward(dy)
-    out = torch.full((M, C), float('nan'), dtype=BF, device=DEV)
+    out = torch.full((M, C), float('nan'), dtype=AC, device=DEV)
     mean_d = torch.empty(C, device=DEV)
     rstd_d = torch.empty(C, device=DEV)
-    zd = z.detach().to(DEV, BF)
+    zd = z.detach().to(DEV, AC)
     call(L.ams_op_bn_train, P(zd), M, C, P(gamma.detach().to(DEV)), P(beta.detach().to(DEV)), eps, act,
-         P(r.to(DEV, BF)) if res else None, P(out), P(mean_d), P(rstd_d), stream_ptr())
+         P(r.to(DEV, AC)) if res else None, P(out), P(mean_d), P(rstd_d), stream_ptr())
     torch.cuda.synchronize()
-    ok1, _ = err_stats('bn_train y M%d C%d act%d res%d' % (M, C, act, res), out, yo.detach(), ULP, 2e-3)
+    ok1, _ = err_stats('bn_train y M%d C%d act%d res%d' % (M, C, act, res), out, yo.detach(), AULP, 4e-4)
     ok2, _ = err_stats('bn_train mean', mean_d, mean.detach(), 1e-5, 1e-5)
     dz = torch.full((M, C), float('nan'), dtype=BF, device=DEV)
     dg = torch.empty(C, device=DEV)

@@ -162,15 +162,36 @@ def test_pack_delta_wire_format():
     assert list(vals[:5]) == [0.0, 7.0, 8.0, 9.0, 1.5] and np.isinf(vals[5])
 
 
+def test_frozen_graph_uses_patch_bn_epsilon_for_every_layer():
+    """The frozen client graph (trim_graph_frozen(kill_norms=True), reference utils/graph_utils.py:362-369, :52-76)
+    normalises with the `_patch` ops of tf.layers.batch_normalization(training=False): epsilon 1e-3 for ALL 54 layers,
+    also image_pooling / aspp0 / concat_projection, whose training-graph epsilon is 1.001e-5."""
+    spec = so.load_spec('cityscapes')
+    aspp = [c for c in spec['convs'] if c['name'] in ('image_pooling', 'aspp0', 'concat_projection')]
+    assert len(aspp) == 3 and all(abs(c['bn']['eps'] - 1.001e-5) < 1e-9 for c in aspp)
+    x = torch.tensor([[[[2.0, -1.0]]]])
+    gamma, beta = torch.tensor([1.5, 0.5]), torch.tensor([0.1, -0.2])
+    mm, mv = torch.tensor([0.5, 0.25]), torch.tensor([1e-4, 4.0])          # a tiny moving variance makes epsilon visible
+    y, _, _ = so.batch_norm(x, gamma, beta, 1.001e-5, 'moving', mm, mv)
+    want = (x - mm) / torch.sqrt(mv + 1e-3) * gamma + beta
+    assert torch.allclose(y, want, rtol=1e-6, atol=0)
+    wrong = (x - mm) / torch.sqrt(mv + 1.001e-5) * gamma + beta
+    assert abs(float(y[0, 0, 0, 0]) - float(wrong[0, 0, 0, 0])) > 1.0
+    # batch mode keeps the node's own epsilon
+    xb = torch.tensor([[[[1.0]], [[3.0]]]])
+    yb, _, _ = so.batch_norm(xb, torch.ones(1), torch.zeros(1), 1.001e-5, 'batch')
+    assert abs(float(yb[0, 1, 0, 0]) - 1.0 / np.sqrt(1.0 + 1.001e-5)) < 1e-6
+
+
 def test_teacher_forcing_is_value_neutral():
     spec = so.load_spec('cityscapes')
     V = so.synthetic_variables(spec, 3)
     fr = so.synthetic_frames(1, 32, 48, 1).astype(np.float32)
     lab = so.synthetic_labels(1, 32, 48, 1, block=8)
-    ts = so.TrainState(spec, V, precision='bf16')
+    ts = so.TrainState(spec, V, precision=so.DEVICE_PRECISION)
     keep = {}
     with torch.no_grad():
-        so.forward(spec, {k: torch.tensor(v) for k, v in V.items()}, fr, bn_mode='batch', precision='bf16', keep=keep)
+        so.forward(spec, {k: torch.tensor(v) for k, v in V.items()}, fr, bn_mode='batch', precision=so.DEVICE_PRECISION, keep=keep)
     forced = {}
     for c in spec['convs']:
         if c['name'] in ('image_pooling', 'logits/semantic'):

@@ -14,7 +14,7 @@ for (m, k, n) in cases:
     w = torch.randn(n, k, device='cuda').to(torch.bfloat16)
     out = torch.empty(m, n, device='cuda', dtype=torch.bfloat16)
     def run():
-        rc = L.ams_op_conv1x1(P(a), P(w), m, n, k, None, None, None, 1, None, 0, P(out), 0, n, sp)
+        rc = L.ams_op_conv1x1(P(a), P(w), m, n, k, None, None, None, 1, None, 0, P(out), 0, n, 0, None, sp)
         assert rc == 0, nat.last_error()
     for _ in range(3): run()
     torch.cuda.synchronize()
