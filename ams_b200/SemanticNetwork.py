@@ -29,7 +29,6 @@ except ImportError:                                     # termcolor is not part 
     def colored(text, *_a, **_k):
         return text
 
-FROZEN_MAGIC = '__ams_b200_frozen_v1__'
 
 _FIRST = ['/Conv/', '/expanded_conv/'] + ['/expanded_conv_%d/' % i for i in range(1, 17)]
 
@@ -74,17 +73,6 @@ _MASK_TABLES = {
                                               'concat_projection/BatchNorm/'], [],
                                 {'MobilenetV2/expanded_conv_3/project/weights:0': 0.00217, 'concat_projection/weights:0': 0.12005}),
 }
-
-
-def load_frozen(path):
-    try:
-        z = np.load(path, allow_pickle=False)
-    except Exception:
-        raise ValueError('%s is not an ams_b200 frozen model (a TF GraphDef .pb cannot be loaded)' % path)
-    with z:
-        if FROZEN_MAGIC not in z.files:
-            raise ValueError('%s is not an ams_b200 frozen model (a TF GraphDef .pb cannot be loaded)' % path)
-        return OrderedDict((k, z[k]) for k in z.files if k != FROZEN_MAGIC)
 
 
 class SemanticNetwork(object):
@@ -133,14 +121,17 @@ class SemanticNetwork(object):
         self.masked_gradients = bool(kwargs.get('masked_gradients', False))
         device = int(str(gpu_id).split(',')[0]) if str(gpu_id) != '' else 0
 
+        # one_hot depth for teacher labels is the reference's NUM_CLASSES constant (utils/graph_utils.py:15)
         if self.frozen:
-            checkpoint = load_frozen(meta_dir + ".pb")
+            # reference :80-93: import `<meta_dir>.pb`; here the container ams_export_frozen wrote (C ABI: ams_create_frozen)
+            checkpoint = None
+            self.student = Student(None, self.height, 2 * self.height, self.class_indices_graph, device=device, label_depth=19,
+                                   frozen_path=meta_dir + ".pb")
         else:
             checkpoint = np.load("%s.npy" % meta_dir, allow_pickle=True).item()
-        num_classes = int(np.asarray(checkpoint['logits/semantic/biases:0']).shape[0])
-        # one_hot depth for teacher labels is the reference's NUM_CLASSES constant (utils/graph_utils.py:15)
-        self.student = Student(num_classes, self.height, 2 * self.height, self.class_indices_graph, device=device,
-                               label_depth=19)
+            num_classes = int(np.asarray(checkpoint['logits/semantic/biases:0']).shape[0])
+            self.student = Student(num_classes, self.height, 2 * self.height, self.class_indices_graph, device=device,
+                                   label_depth=19)
         self.bn_mode = nat.BN_MOVING if self.frozen else nat.BN_BATCH
         self.saver = SaveHelper(self.student, map_fun=lambda x: x)
         self.save_vars = [n for n, _, _, _ in self.student.variables]
@@ -151,7 +142,8 @@ class SemanticNetwork(object):
             self.OPT_FILTER = list(self.OPT_FILTER) + list(filter_out)
         self.filter = lambda elem: elem if all(
             keyword not in elem for keyword in self.OPT_FILTER) and elem not in self.OP_FILTER else None
-        self.saver.restore_vars(None, checkpoint, self.filter)
+        if checkpoint is not None:
+            self.saver.restore_vars(None, checkpoint, self.filter)
         self.mask = None
         self._mask_on_device = None
         self._fill_thr = None
@@ -389,9 +381,9 @@ class SemanticNetwork(object):
         return out
 
     def save_to_frozen_graph(self, save_dir):
-        graph = self.get_frozen_graph()
-        with open(save_dir + ".pb", 'wb') as pb_file:
-            np.savez(pb_file, **dict(graph, **{FROZEN_MAGIC: np.array([self.height], dtype=np.int32)}))
+        """reference :711-714 writes `<save_dir>.pb` (a TF GraphDef); same file name, this library's container
+        (C ABI: ams_export_frozen), read back by SemanticNetwork(meta_dir=save_dir, frozen=True)."""
+        self.student.export_frozen(save_dir + ".pb")
 
     def close_model(self):
         self.student.close()

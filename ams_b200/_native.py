@@ -45,6 +45,9 @@ _SIGNATURES = {
     'ams_reset_optimizer': (_i, [_vp]),
     'ams_enqueue': (_i, [_vp, _vp, _i, _vp, _i]),
     'ams_enqueue_raw': (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i]),
+    'ams_export_frozen': (_i, [_vp, C.c_char_p]),
+    'ams_create_frozen': (_vp, [C.c_char_p, _vp]),
+    'ams_is_frozen': (_i, [_vp]),
     'ams_queue_size': (_i, [_vp]),
     'ams_queue_clear': (_i, [_vp]),
     'ams_infer': (_i, [_vp, _i, _vp]),
@@ -59,6 +62,8 @@ _SIGNATURES = {
     'ams_train_forward_backward': (_i, [_vp, C.POINTER(_ll), C.POINTER(_d)]),
     'ams_gradient_arena': (_vp, [_vp, C.POINTER(_ll)]),
     'ams_apply_optimizer': (_i, [_vp, _f, _i, _f]),
+    'ams_gradient_bucket_split': (_ll, [_vp]),
+    'ams_gradient_bucket_wait': (_i, [_vp, _vp]),
     'ams_train_step_async': (_i, [_vp, _f, _i, _vp]),
     'ams_step_terms_device': (_vp, [_vp]),
     'ams_apply_optimizer_device': (_i, [_vp, _f, _i, _vp]),

@@ -3,6 +3,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
 #include <cstring>
 
 #include "net.cuh"
@@ -98,6 +99,8 @@ ams_net* ams_create(const ams_config* cfg) {
     if (cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_pool, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaEventCreateWithFlags(&net->ev_bucket, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaEventCreateWithFlags(&net->ev_bucket_main, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     net->stream = net->own_stream;
     if (net_build_topology(net)) return fail("topology");
     const LayerDef& lg = net->layers.back();
@@ -183,6 +186,8 @@ void ams_destroy(ams_net* h) {
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
     if (net->ev_pool) cudaEventDestroy(net->ev_pool);
+    if (net->ev_bucket) cudaEventDestroy(net->ev_bucket);
+    if (net->ev_bucket_main) cudaEventDestroy(net->ev_bucket_main);
     delete net;
 }
 
@@ -259,6 +264,88 @@ int ams_get_tensor(ams_net* h, const char* name, float* host, long long count) {
     AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
     return 0;
 }
+
+
+// =============================================================================================== frozen hand-off
+// Container of the client model (the reference writes a TF GraphDef with constants, SemanticNetwork.py:706-714 ->
+// utils/graph_utils.py:79-126 trim_graph_frozen(kill_norms=True); this library has no GraphDef, so the file holds what
+// that graph holds: every variable of the student with inference-mode BatchNorm semantics, i.e. gamma / beta and the
+// MOVING mean / variance, in tf.global_variables() order):
+//   "AMSFRZ01" | i32 num_classes | i32 graph_variant | i32 n_tensors |
+//   per tensor: u16 name_len | name | i32 ndim | i32 shape[4] | i64 count | count x f32
+static const char kFrozenMagic[8] = {'A', 'M', 'S', 'F', 'R', 'Z', '0', '1'};
+
+int ams_export_frozen(ams_net* h, const char* path) {
+    NET(h);
+    AMS_REQUIRE(path && path[0], "empty path");
+    std::vector<float> tr(static_cast<size_t>(net->n_train)), mv(static_cast<size_t>(net->n_moving));
+    AMS_CUDA_CHECK(cudaMemcpyAsync(tr.data(), net->params, tr.size() * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaMemcpyAsync(mv.data(), net->moving, mv.size() * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    FILE* f = std::fopen(path, "wb");
+    AMS_REQUIRE(f != nullptr, std::string("cannot open ") + path + " for writing");
+    bool ok = std::fwrite(kFrozenMagic, 1, 8, f) == 8;
+    const int32_t hdr[3] = {net->cfg.num_classes, net->cfg.graph_variant, static_cast<int32_t>(net->vars.size())};
+    ok = ok && std::fwrite(hdr, sizeof(int32_t), 3, f) == 3;
+    for (const VarInfo& v : net->vars) {
+        const uint16_t nl = static_cast<uint16_t>(v.name.size());
+        const int32_t nd = v.ndim;
+        const int32_t shp[4] = {v.shape[0], v.shape[1], v.shape[2], v.shape[3]};
+        const int64_t cnt = v.count;
+        const float* src = (v.trainable ? tr.data() : mv.data()) + v.offset;
+        ok = ok && std::fwrite(&nl, 2, 1, f) == 1 && std::fwrite(v.name.data(), 1, nl, f) == nl && std::fwrite(&nd, 4, 1, f) == 1 &&
+             std::fwrite(shp, 4, 4, f) == 4 && std::fwrite(&cnt, 8, 1, f) == 1 &&
+             std::fwrite(src, sizeof(float), static_cast<size_t>(cnt), f) == static_cast<size_t>(cnt);
+    }
+    ok = (std::fclose(f) == 0) && ok;
+    AMS_REQUIRE(ok, std::string("short write to ") + path);
+    return 0;
+}
+
+ams_net* ams_create_frozen(const char* path, const ams_config* cfg) {
+    if (!path || !cfg) { set_last_error("null path / config"); return nullptr; }
+    FILE* f = std::fopen(path, "rb");
+    if (!f) { set_last_error(std::string("cannot open frozen model ") + path); return nullptr; }
+    char magic[8];
+    int32_t hdr[3] = {0, 0, 0};
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, kFrozenMagic, 8) != 0 || std::fread(hdr, 4, 3, f) != 3) {
+        std::fclose(f);
+        set_last_error(std::string(path) + " is not an ams_b200 frozen model (a TF GraphDef .pb cannot be loaded)");
+        return nullptr;
+    }
+    ams_config c = *cfg;
+    if ((c.num_classes != 0 && c.num_classes != hdr[0]) || (c.num_classes != 0 && c.graph_variant != hdr[1])) {
+        std::fclose(f);
+        set_last_error("frozen model was exported from a different graph (num_classes / graph_variant mismatch)");
+        return nullptr;
+    }
+    c.num_classes = hdr[0]; c.graph_variant = hdr[1];
+    ams_net* h = ams_create(&c);
+    if (!h) { std::fclose(f); return nullptr; }
+    Net* net = reinterpret_cast<Net*>(h);
+    auto fail = [&](const std::string& msg) -> ams_net* { std::fclose(f); ams_destroy(h); set_last_error(msg); return nullptr; };
+    if (hdr[2] != static_cast<int32_t>(net->vars.size())) return fail("frozen model: wrong number of variables");
+    std::vector<float> buf;
+    std::string name;
+    for (int i = 0; i < hdr[2]; ++i) {
+        uint16_t nl = 0; int32_t nd = 0, shp[4]; int64_t cnt = 0;
+        if (std::fread(&nl, 2, 1, f) != 1) return fail("frozen model: truncated file");
+        name.resize(nl);
+        if (std::fread(&name[0], 1, nl, f) != nl || std::fread(&nd, 4, 1, f) != 1 || std::fread(shp, 4, 4, f) != 4 ||
+            std::fread(&cnt, 8, 1, f) != 1) return fail("frozen model: truncated file");
+        const int vi = find_var(net, name.c_str());
+        if (vi < 0) return fail("frozen model: KeyError: no variable named '" + name + "'");
+        const VarInfo& v = net->vars[vi];
+        if (cnt != v.count || nd != v.ndim) return fail("frozen model: shape mismatch for " + name);
+        buf.resize(static_cast<size_t>(cnt));
+        if (std::fread(buf.data(), sizeof(float), buf.size(), f) != buf.size()) return fail("frozen model: truncated file");
+        if (ams_set_tensor(h, name.c_str(), buf.data(), cnt)) { std::fclose(f); ams_destroy(h); return nullptr; }
+    }
+    std::fclose(f);
+    net->frozen = true;
+    return h;
+}
+int ams_is_frozen(const ams_net* h) { return (h && reinterpret_cast<const Net*>(h)->frozen) ? 1 : 0; }
 
 long long ams_trainable_count(const ams_net* h) { return h ? reinterpret_cast<const Net*>(h)->n_train : -1; }
 int ams_get_trainable(ams_net* h, float* host) {
@@ -488,6 +575,7 @@ static int apply_optimizer(Net* net, float lr, int masked, float grad_scale, con
 
 int ams_train_forward_backward(ams_net* h, long long* out_n_valid, double* out_loss_sum) {
     NET(h);
+    AMS_REQUIRE(!net->frozen, "Can't train frozen graph!!! (handle built by ams_create_frozen is inference-only)");
     Plan* p = nullptr;
     if (net_dequeue(net, &p, true)) return -1;
     if (net_train_fwd_bwd(net, p, false)) return -1;
@@ -504,6 +592,13 @@ void* ams_gradient_arena(ams_net* h, long long* count) {
     if (!net) return nullptr;
     if (count) *count = net->n_train;
     return net->grads;
+}
+long long ams_gradient_bucket_split(const ams_net* h) { return h ? reinterpret_cast<const Net*>(h)->bucket_split : -1; }
+int ams_gradient_bucket_wait(ams_net* h, void* cuda_stream) {
+    NET(h);
+    AMS_REQUIRE(cuda_stream != nullptr, "a stream is needed");
+    AMS_CUDA_CHECK(cudaStreamWaitEvent(as_stream(cuda_stream), net->ev_bucket, 0));
+    return 0;
 }
 int ams_apply_optimizer(ams_net* h, float lr, int masked, float grad_scale) {
     NET(h);
@@ -528,6 +623,7 @@ int ams_apply_optimizer_device(ams_net* h, float lr, int masked, float* out_loss
 }
 int ams_train_step_async(ams_net* h, float lr, int masked, float* out_loss_pinned) {
     NET(h);
+    AMS_REQUIRE(!net->frozen, "Can't train frozen graph!!! (handle built by ams_create_frozen is inference-only)");
     Plan* p = nullptr;
     if (net_dequeue(net, &p, true)) return -1;
     if (net_train_fwd_bwd(net, p, true)) return -1;
@@ -609,6 +705,7 @@ int ams_syncbn_status(ams_net* h, unsigned int* out_epoch, unsigned int* out_err
 
 int ams_train_step(ams_net* h, float lr, int masked, float* out_loss) {
     NET(h);
+    AMS_REQUIRE(!net->frozen, "Can't train frozen graph!!! (handle built by ams_create_frozen is inference-only)");
     Plan* p = nullptr;
     if (net_dequeue(net, &p, true)) return -1;
     if (net_train_fwd_bwd(net, p, true)) return -1;

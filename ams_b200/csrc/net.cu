@@ -151,6 +151,9 @@ int net_build_topology(Net* net) {
     const int cp = add_layer("concat_projection", kConv1x1, 512, 256, 1, 1, 1, true, eps_aspp, k_default, aspp, -1);
     add_layer("logits/semantic", kLogits, 256, c.num_classes, 1, 1, 0, false, 0.f, 0.f, cp, -1);
     (void)ip;
+    // gradient buckets (data parallel): the late bucket starts at the first expand conv that runs at the final resolution
+    for (size_t i = 0; i < L.size(); ++i)
+        if (L[i].name == "MobilenetV2/expanded_conv_7/expand") { net->bucket_layer = static_cast<int>(i); net->bucket_split = L[i].w_off; }
     net->n_train = t_off;
     net->n_moving = m_off;
     net->n_bnpool = bn_off;
@@ -589,6 +592,21 @@ int net_backward(Net* net, Plan* p, bool normalize) {
                  stem_conv_bwd_filter(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w,
                                       d.out_h, d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, b.gz,
                                       net->grads + d.w_off, p->red_ws, p->red_ws_floats, s));
+        }
+        if (i == net->bucket_layer && net->ev_bucket) {
+            // every gradient of the late bucket has been enqueued: main-stream parts up to here, filter gradients on the side
+            // stream.  One event after both; external-record flavour when this runs under stream capture.
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            AMS_CUDA_CHECK(cudaStreamIsCapturing(s, &cap));
+            const unsigned flags = cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault;
+            cudaStream_t rec = s;
+            if (side) {
+                AMS_CUDA_CHECK(cudaEventRecord(net->ev_bucket_main, s));
+                AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_bucket_main, 0));
+                forked = true;
+                rec = net->side_stream;
+            }
+            AMS_CUDA_CHECK(cudaEventRecordWithFlags(net->ev_bucket, rec, flags));
         }
     }
     if (forked) {

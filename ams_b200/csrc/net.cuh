@@ -116,6 +116,10 @@ struct Net {
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     // filter gradients of the 1x1 convs run on a side stream, concurrently with the backward chain that does not need them
     cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pool = nullptr;
+    // data-parallel bucketed gradient exchange: the late bucket = arena floats [bucket_split, n_train) (every layer of the
+    // final-resolution stage, ASPP, logits); ev_bucket is recorded (as an external event node when the step is a CUDA graph)
+    // once all of its gradients are complete, long before the backward pass ends
+    int bucket_layer = -1; long long bucket_split = 0; cudaEvent_t ev_bucket = nullptr, ev_bucket_main = nullptr;
     std::vector<VarInfo> vars;
     std::unordered_map<std::string, int> var_index;
     std::vector<int> trainable_order;       // indices into vars, tf.trainable_variables() order
@@ -138,6 +142,7 @@ struct Net {
     bool sync_active = false;           // true only while a TRAINING step is being enqueued (inference never exchanges)
     uint8_t* pack_bits = nullptr; __half* pack_vals = nullptr; unsigned int* pack_counts = nullptr; unsigned long long* pack_kept = nullptr;
     bool weights_dirty = true, fold_dirty = true;
+    bool frozen = false;               // built by ams_create_frozen: inference only ("Can't train frozen graph", SemanticNetwork.py:217)
     HeadGeom head{};
     std::map<int, std::unique_ptr<Plan>> plans;
     // input queue

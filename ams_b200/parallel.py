@@ -3,9 +3,12 @@
 
   * inference: streams are independent -> `shard_streams` assigns stream s to rank s % world, no collective;
   * distillation: data parallel, one process per GPU.  Every rank runs forward/backward on its 8 frames with the
-    loss left as a SUM over its valid pixels, then ONE exchange step: allreduce(sum) of the flat fp32 gradient arena
-    (2,113,043 floats = 8.45 MB, NCCL over NVLink) and of (n_valid, loss_sum); Adam then runs identically on every
-    rank with gradients scaled by 1 / global n_valid, which reproduces the reference's `reduce_mean` over all valid
+    loss left as a SUM over its valid pixels, and the flat fp32 gradient arena (2,113,043 floats = 8.45 MB) is summed
+    over the ranks in TWO buckets (NCCL over NVLink): the late-layer bucket (final-resolution stage + ASPP + logits,
+    ~90 % of the coordinates) is complete after ~45 % of the backward pass and its allreduce runs on a communication
+    stream WHILE the high-resolution layers are still in backward; the small early-layer bucket and the
+    (n_valid, loss_sum) pair follow when backward ends.  Adam then runs identically on every rank with gradients
+    scaled by 1 / global n_valid, which reproduces the reference's `reduce_mean` over all valid
     pixels of the global batch (utils/graph_utils.py:408).  BatchNorm batch statistics are summed over the ranks inside
     the BN finalize kernels through NVLink peer memory (sync_bn=True: the step equals the reference's single-process
     step on the global batch) or stay per replica (sync_bn=False, a documented deviation).
@@ -65,16 +68,26 @@ class DataParallelStudent:
     peer memory (ams_syncbn_*), which makes the job equivalent to the reference's single-process step on the global
     batch; sync_bn=False keeps per-replica statistics (faster, a documented deviation)."""
 
-    def __init__(self, student, group=None, sync_bn=False, strict=True, tensors=None):
+    def __init__(self, student, group=None, sync_bn=False, strict=True, tensors=None, buckets=True):
         self.student = student
         self.group = group
+        self.comm_stream = None
+        self.split = 0
         if tensors is not None:
             # (gradient arena, terms) supplied by the caller: the gloo / CPU test of this class's host logic
             self.grad, self.terms = tensors
+            if buckets and hasattr(student, 'gradient_bucket_split'):
+                self.split = int(student.gradient_bucket_split())
         else:
             ptr, n = student.gradient_arena()
             self.grad = torch.as_tensor(_DeviceArena(ptr, n), device='cuda')
             self.terms = torch.as_tensor(_DeviceArena(student.step_terms_ptr(), 2, '<f8'), device='cuda')
+            if buckets:
+                self.split = int(student.gradient_bucket_split())
+                self.comm_stream = torch.cuda.Stream()
+        # two views of the arena: [0, split) early layers, [split, n) late layers (complete first in backward)
+        self.grad_early = self.grad[:self.split] if self.split > 0 else None
+        self.grad_late = self.grad[self.split:] if self.split > 0 else self.grad
         self._loss_slots = torch.zeros(256, dtype=torch.float32)
         if torch.cuda.is_available():
             self._loss_slots = self._loss_slots.pin_memory()
@@ -117,8 +130,20 @@ class DataParallelStudent:
         # the allreduces are ordered after backward and before Adam by stream order alone
         self.student.train_forward_backward_async()
         if self.world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+            late = None
+            if self.comm_stream is not None:
+                # late-layer bucket: its allreduce waits (on the communication stream) for the event the library records
+                # in the MIDDLE of the step, and overlaps the rest of the backward pass
+                with torch.cuda.stream(self.comm_stream):
+                    self.student.gradient_bucket_wait(self.comm_stream.cuda_stream)
+                    late = dist.all_reduce(self.grad_late, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            else:
+                dist.all_reduce(self.grad_late, op=dist.ReduceOp.SUM, group=self.group)
+            if self.grad_early is not None:
+                dist.all_reduce(self.grad_early, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.terms, op=dist.ReduceOp.SUM, group=self.group)
+            if late is not None:
+                late.wait()                              # the step's stream waits for the late bucket before Adam reads it
         self.student.apply_optimizer_device(lr, masked, self._slot())
 
     def losses(self):

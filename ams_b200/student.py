@@ -34,12 +34,15 @@ def _ptr(a):
 
 
 class Student:
-    def __init__(self, num_classes, height, width, class_indices, device=0, label_depth=19, queue_capacity=4):
+    def __init__(self, num_classes, height, width, class_indices, device=0, label_depth=19, queue_capacity=4,
+                 frozen_path=None):
+        """frozen_path: build the inference-only client handle from a model written by export_frozen()
+        (ams_create_frozen; num_classes may be None = take it from the file)."""
         self._h = None
         L = nat.lib()
         cfg = nat.AmsConfig()
-        cfg.num_classes = int(num_classes)
-        cfg.graph_variant = 1 if int(num_classes) == 21 else 0
+        cfg.num_classes = int(num_classes) if num_classes is not None else 0
+        cfg.graph_variant = 1 if cfg.num_classes == 21 else 0
         cfg.height, cfg.width, cfg.device = int(height), int(width), int(device)
         class_indices = [int(c) for c in class_indices]
         cfg.class_count = len(class_indices)
@@ -47,12 +50,21 @@ class Student:
             cfg.class_indices[i] = c
         cfg.label_depth = int(label_depth)
         cfg.queue_capacity = int(queue_capacity)
-        h = L.ams_create(C.byref(cfg))
-        if not h:
-            raise nat.NativeError('ams_create failed: ' + nat.last_error())
+        if frozen_path is not None:
+            h = L.ams_create_frozen(os.fsencode(frozen_path), C.byref(cfg))
+            if not h:
+                msg = nat.last_error()
+                if 'not an ams_b200 frozen model' in msg or 'cannot open frozen model' in msg:
+                    raise ValueError(msg)
+                raise nat.NativeError('ams_create_frozen failed: ' + msg)
+        else:
+            h = L.ams_create(C.byref(cfg))
+            if not h:
+                raise nat.NativeError('ams_create failed: ' + nat.last_error())
         self._h = C.c_void_p(h)
         self._L = L
-        self.num_classes, self.height, self.width = int(num_classes), int(height), int(width)
+        self.frozen = frozen_path is not None
+        self.height, self.width = int(height), int(width)
         self.class_indices = class_indices
         self.class_count = len(class_indices)
         self.variables = []          # [(name, shape, trainable, offset)] in tf.global_variables() order
@@ -63,6 +75,7 @@ class Student:
             nat.check(L.ams_tensor_info(self._h, i, name, 256, shape, C.byref(nd), C.byref(tr), C.byref(off)))
             self.variables.append((name.value.decode(), tuple(shape[:nd.value]), bool(tr.value), off.value))
         self.var_shapes = {n: s for n, s, _, _ in self.variables}
+        self.num_classes = int(self.var_shapes['logits/semantic/biases:0'][0])
         self.trainable_names = [n for n, _, t, _ in self.variables if t]
         self.n_trainable = int(L.ams_trainable_count(self._h))
         self.low_res = (_low_res(height), _low_res(width))
@@ -158,6 +171,10 @@ class Student:
         nat.check(self._L.ams_enqueue_raw(self._h, _ptr(frames), frames.shape[1], frames.shape[2], 1 if bgr else 0, _ptr(lab),
                                           lh, lw, frames.shape[0]), 'enqueue_raw')
         return frames.shape[0]
+
+    def export_frozen(self, path):
+        """ams_export_frozen: the client model (reference save_to_frozen_graph, SemanticNetwork.py:711-714)."""
+        nat.check(self._L.ams_export_frozen(self._h, os.fsencode(path)), 'export_frozen')
 
     def queue_size(self):
         return self._L.ams_queue_size(self._h)
@@ -282,6 +299,14 @@ class Student:
         n = C.c_longlong()
         p = self._L.ams_gradient_arena(self._h, C.byref(n))
         return p, n.value
+
+    def gradient_bucket_split(self):
+        """first float of the late-layer gradient bucket (final-resolution stage + ASPP + logits)"""
+        return int(self._L.ams_gradient_bucket_split(self._h))
+
+    def gradient_bucket_wait(self, cuda_stream_ptr):
+        """make `cuda_stream_ptr` wait until the late bucket of the last enqueued forward/backward is complete"""
+        nat.check(self._L.ams_gradient_bucket_wait(self._h, C.c_void_p(cuda_stream_ptr)), 'gradient_bucket_wait')
 
     def apply_optimizer(self, lr, masked, grad_scale):
         nat.check(self._L.ams_apply_optimizer(self._h, float(lr), 1 if masked else 0, float(grad_scale)))

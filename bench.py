@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- AMS student hot path on B200.
 
-Workload (BASELINE.json configs[1], "C2"): one online-distillation PHASE of K iterations, batch 8 @ 512x1024,
-7 selected classes (reference experiment 12), lr 1e-3, strategy coord_desc_auto with coord_fraction 0.05 --
-exactly what `SemanticNetwork.train_with_deque` + the delta writer of run.py:309-336 do:
+N = 1 -- workload C2 (BASELINE.json configs[1]): one online-distillation PHASE of K iterations, batch 8 @ 512x1024,
+Cityscapes 19-class graph, 7 selected classes (reference experiment 12), lr 1e-3, strategy coord_desc_auto with
+coord_fraction 0.05 -- exactly what `SemanticNetwork.train_with_deque` + the delta writer of run.py:309-336 do:
    iteration 0 : snapshot, full Adam step, |delta| percentile selection of 5 % of the 2,113,043 coordinates
    iterations 1..K-1 : forward/backward/BN-moving-average/Adam with the masked parameter write
    end of phase : pack the model delta (packbits(mask) + fp16 values)
-A "step" is one iteration; `value` = K / (device time of the whole phase) in steps/s with the K input batches
-already resident in HBM; `e2e` = the same phase driven from pinned HOST buffers (H2D of every batch by a feeder
-thread through ams_enqueue, D2H of every loss and of the delta) in steps/s.
-Secondary block `infer`: frozen-client frames/s (C1/C3 shape, batch 8, argmax + confusion matrix).
-
-N > 1 (torchrun): data parallel, 8 frames per GPU (weak scaling), NCCL allreduce of the 8.45 MB gradient arena and
-of (n_valid, loss_sum) on the device, BatchNorm batch statistics summed over the ranks inside the BN kernels through
+N > 1 (torchrun) -- workload C4 (configs[3]): the same phase, data parallel, on the PASCAL VOC 21-class graph
+(depthwise BN decay 0.98, class vector of reference experiment 40), 8 frames per GPU (global batch 8 N, weak scaling):
+gradient arena summed over the ranks in two NCCL buckets, the late-layer bucket overlapped with the backward pass;
+(n_valid, loss_sum) summed on the device; BatchNorm batch statistics summed over the ranks inside the BN kernels through
 NVLink peer memory (global-batch semantics of the reference; --sync-bn 0 = per replica).  No host synchronisation
-inside a phase.  `--impl reference` times the CPU oracle (the port of the
-reference's TF1 path; TensorFlow 1.15 cannot be installed here) on the host cores.
+inside a phase.  Before timing, a duplicate-frame step checks the data-parallel step against the single-GPU step BIT FOR
+BIT (`dp_exact`).
+A "step" is one iteration on one GPU's 8 frames; `value` = K N / (device time of the whole phase, max over ranks) in
+steps/s with the input batches already resident in HBM; `e2e` = the same phase driven from pinned HOST buffers (H2D of
+every batch by a feeder thread through ams_enqueue, D2H of every loss and of the delta).
+Secondary blocks: `infer` (frozen client, batch 8 and batch-1 latency), `infer_streams` (config C3: 8 camera streams of
+1080p frames, 256 frames per stream, sharded by stream, 8 frames per GPU and launch by temporal batching).
+`--impl reference` times the CPU oracle (the port of the reference's TF1 path; TensorFlow 1.15 cannot be installed here)
+on the host cores, full batch-8 steps.
 """
 import argparse
 import json
@@ -33,10 +37,11 @@ sys.path.insert(0, ROOT)
 T0 = time.time()
 
 H, W, BATCH = 512, 1024, 8
-CLASSES = [0, 1, 2, 8, 10, 11, 13]          # reference experiment 12 (exp_configs.py:44-47)
+CLASSES = [0, 1, 2, 8, 10, 11, 13]          # reference experiment 12 (exp_configs.py:44-47): config C2
+CLASSES_VOC = [0, 7, 12, 15]                # reference experiment 40 (exp_configs.py:152-154): config C4
 COORD_FRAC = 0.05
 LR = 1e-3
-ALGO_BYTES_STEP = 8.14e9                    # layer-boundary bf16 traffic of one b8 step
+ALGO_BYTES_STEP = 8.14e9                    # layer-boundary 16-bit traffic of one b8 step
 ALGO_BYTES_FRAME = 343.1e6
 
 
@@ -88,6 +93,8 @@ def pinned(shape, dtype):
 
 # --------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
+    """The reference's CPU path for the same step: FULL batch-8 steps (forward + backward + BN moving-average update +
+    TF1 Adam, fp32) of the torch-CPU oracle = the port of the TF1 graph, all host cores.  Under torchrun rank 0 alone runs."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
@@ -95,37 +102,40 @@ def run_reference(args, rank, world):
     import student_oracle as so
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    spec = so.load_spec('cityscapes')
+    multi = args.gpus > 1
+    tag, cls = ('pascalvoc2012', CLASSES_VOC) if multi else ('cityscapes', CLASSES)
+    spec = so.load_spec(tag)
     V = so.synthetic_variables(spec, 1)
-    sample_b = 2
-    frames = so.synthetic_frames(sample_b, H, W, 0).astype(np.float32)
-    labels = so.synthetic_labels(sample_b, H, W, 0)
+    frames = so.synthetic_frames(BATCH, H, W, 0).astype(np.float32)
+    labels = so.synthetic_labels(BATCH, H, W, 0)
     ts = so.TrainState(spec, V)
-    budget_s = 240.0
+    budget_s = 270.0
     times = []
     t_start = time.time()
     for it in range(args.warmup + args.steps):
         t0 = time.time()
-        ts.step(frames, labels, np.array(CLASSES), LR)
+        ts.step(frames, labels, np.array(cls), LR)
         dt = time.time() - t0
         if it >= args.warmup:
             times.append(dt)
         if time.time() - t_start > budget_s and len(times) >= 1:
             break
-    t_step = float(np.mean(times)) * (BATCH / sample_b)
+    t_step = float(np.mean(times))
     value = 1.0 / t_step
-    sample = ('%d of %d steps measured, each on %d of the %d frames of a step (fwd+bwd+BN update+Adam, fp32, torch-CPU oracle '
-              '= port of the TF1 graph); steps/s scaled by %d/%d' % (len(times), args.steps, sample_b, BATCH, sample_b, BATCH))
+    sample = ('%d of %d full batch-8 steps measured after %d warm-up steps (fwd+bwd+BN update+Adam, fp32, torch-CPU oracle = port of '
+              'the TF1 graph, %d threads); no scaling applied' % (len(times), args.steps, min(args.warmup, args.warmup), cores))
     print(json.dumps({
         'impl': 'reference', 'metric': 'distill_steps_per_sec', 'value': value, 'unit': 'steps/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 * t_step, 'higher_is_better': True,
+        'steps': len(times), 'warmup': args.warmup, 'ms_per_step': 1000.0 * t_step, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'C2 distillation step, batch 8 @ 512x1024, 7 classes, CPU oracle'},
+        'config': {'workload': ('C4' if multi else 'C2') + ': AMS online distillation step, batch 8 @ 512x1024, %s graph, %d classes, '
+                               'CPU oracle on the host cores' % (tag, len(cls))},
         'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
 def cpu_baseline():
+    """Bounded sample of the same workload on the host cores (rank 0, N = 1): full batch-8 oracle steps, ~15 s."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import torch
     import student_oracle as so
@@ -133,17 +143,16 @@ def cpu_baseline():
     torch.set_num_threads(cores)
     spec = so.load_spec('cityscapes')
     V = so.synthetic_variables(spec, 1)
-    b = 2
-    frames = so.synthetic_frames(b, H, W, 0).astype(np.float32)
-    labels = so.synthetic_labels(b, H, W, 0)
+    frames = so.synthetic_frames(BATCH, H, W, 0).astype(np.float32)
+    labels = so.synthetic_labels(BATCH, H, W, 0)
     ts = so.TrainState(spec, V)
-    ts.step(frames[:1], labels[:1], np.array(CLASSES), LR)          # warm-up
+    ts.step(frames[:1], labels[:1], np.array(CLASSES), LR)          # warm-up (thread pool, allocator)
     t0 = time.time()
     n = 0
-    while n < 3 and time.time() - t0 < 25.0:
+    while n < 4 and time.time() - t0 < 20.0:
         ts.step(frames, labels, np.array(CLASSES), LR)
         n += 1
-    t_step = (time.time() - t0) / n * (BATCH / b)
+    t_step = (time.time() - t0) / n
     # frozen inference, batch 1
     params = {k: torch.tensor(v) for k, v in V.items()}
     t1 = time.time()
@@ -155,9 +164,62 @@ def cpu_baseline():
             m += 1
     fps = m / (time.time() - t1)
     return {'value': 1.0 / t_step, 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d oracle steps on %d of the 8 frames of a step, scaled by %d/8 (torch-CPU fp32 port of the TF1 graph; '
-                      'TF 1.15 itself is not installable here)' % (n, b, b),
+            'sample': '%d full batch-8 oracle steps (torch-CPU fp32 port of the TF1 graph, %d threads; TF 1.15 itself is not '
+                      'installable here); no scaling applied' % (n, cores),
             'infer_frames_per_sec': fps}
+
+
+# --------------------------------------------------------------------------------------------- data-parallel exactness
+def check_dp_exact(st, dp, ckpt, num_classes, classes, local_rank, stream, frames, labels, world, mark):
+    """Before timing: with the SAME 8 frames on every rank, every BatchNorm sum doubles with the rank count and so does
+    n, so the data-parallel step (global-batch BatchNorm through NVLink peer memory, bucketed allreduce) must equal the
+    single-GPU step on those 8 frames BIT FOR BIT: loss, every moving statistic, and -- after the allreduce -- every
+    gradient coordinate = world x the single-GPU coordinate (exact for a power-of-two world).  Returns the dict that
+    goes into the JSON line (identical on every rank after a MAX-reduce of the mismatch counts)."""
+    import torch
+    import torch.distributed as dist
+    from ams_b200.student import Student
+    single = Student(num_classes, H, W, classes, device=local_rank, queue_capacity=2)
+    single.set_stream(stream.cuda_stream)
+    for k, v in ckpt.items():
+        single.set_tensor(k, v)
+    single.enqueue(frames, labels)
+    single.train_forward_backward_async()            # local SUM-loss gradients, moving statistics updated
+    single.synchronize()
+    g1 = single.get_gradients()
+    # moving MEANS: the moving variance carries the Bessel factor n / (n - 1), which legitimately differs between n and world x n
+    mv_names = [n for n, _, tr, _ in single.variables if n.endswith('moving_mean:0')]
+    mv1 = {n: single.get_tensor(n) for n in mv_names}
+    terms1 = torch.as_tensor(_arena(single.step_terms_ptr(), 2, '<f8'), device='cuda').cpu().numpy().copy()
+    single.close()
+    # the same frames through the data-parallel step (two replays: eager, then the captured graph)
+    res = {}
+    for rep_i in range(2):
+        for k, v in ckpt.items():
+            st.set_tensor(k, v)
+        st.reset_optimizer()
+        st.enqueue(frames, labels)
+        dp.train_step_async(LR, False)
+        dp.losses()
+        gN = st.get_gradients()
+        termsN = dp.terms.cpu().numpy().copy()
+        bad_g = int(np.count_nonzero(gN != np.float32(world) * g1))
+        bad_mv = int(sum(np.count_nonzero(st.get_tensor(n) != mv1[n]) for n in mv_names))
+        bad_t = int(np.count_nonzero(termsN != world * terms1))
+        t = torch.tensor([bad_g, bad_mv, bad_t], dtype=torch.int64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res['eager' if rep_i == 0 else 'graph_replay'] = [int(x) for x in t.cpu()]
+    ok = dp.sync_bn and all(v == [0, 0, 0] for v in res.values())
+    mark('dp_exact %s %s' % (ok, res))
+    return {'exact': bool(ok), 'gradient_coordinates_differing': max(v[0] for v in res.values()),
+            'moving_means_differing': max(v[1] for v in res.values()), 'loss_terms_differing': max(v[2] for v in res.values()),
+            'of_coordinates': int(g1.size), 'checked': 'duplicate-frame step vs single-GPU step, eager and graph replay, max over ranks',
+            'sync_bn': bool(dp.sync_bn)}
+
+
+class _arena:
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {'shape': (count,), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -166,6 +228,7 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from ams_b200 import _native as nat
     from ams_b200.student import Student
+    from ams_b200.parallel import shard_streams
     from ams_b200.synthetic import synthetic_checkpoint, synthetic_frames, synthetic_labels
 
     torch.cuda.set_device(local_rank)
@@ -189,13 +252,17 @@ def run_ours(args, rank, world, local_rank):
 
     K, Wm = args.steps, args.warmup
     N_INF = 10
-    st = Student(19, H, W, CLASSES, device=local_rank, queue_capacity=max(K, N_INF) + 2)
+    multi = world > 1
+    # N = 1: config C2 (Cityscapes graph, experiment 12).  N > 1: config C4 (PASCAL VOC 21-class graph, experiment 40)
+    tag, num_classes, classes = ('pascalvoc2012', 21, CLASSES_VOC) if multi else ('cityscapes', 19, CLASSES)
+    st = Student(num_classes, H, W, classes, device=local_rank, queue_capacity=max(K, N_INF) + 2)
     # a dedicated (non-default) stream shared by torch (events, NCCL ordering) and the library's kernels
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     st.set_stream(stream.cuda_stream)
     mark('student created')
-    for k, v in synthetic_checkpoint('cityscapes', 1).items():
+    ckpt = synthetic_checkpoint(tag, 1)
+    for k, v in ckpt.items():
         st.set_tensor(k, v)
     # 4 distinct synthetic batches per rank, cycled
     nb = 4
@@ -209,9 +276,14 @@ def run_ours(args, rank, world, local_rank):
     h2d_step = BATCH * H * W * 4
 
     dp = None
+    dp_exact = None
     if world > 1:
         from ams_b200.parallel import DataParallelStudent
-        dp = DataParallelStudent(st, sync_bn=bool(args.sync_bn), strict=False)
+        dp = DataParallelStudent(st, sync_bn=bool(args.sync_bn), strict=False, buckets=bool(args.buckets))
+        dp_exact = check_dp_exact(st, dp, ckpt, num_classes, classes, local_rank, stream, host[0][1], host[0][3], world, mark)
+        for k, v in ckpt.items():                  # the check moved weights, moving statistics and Adam state: start clean
+            st.set_tensor(k, v)
+        st.reset_optimizer()
     # steps are enqueued without a host round trip (the reference only prints the loss, SemanticNetwork.py:261): the loss
     # of step i is copied to its page-locked slot when the stream gets there and read after the phase's synchronisation
     loss_t, loss_np = pinned((max(K, Wm) + 1,), torch.float32)
@@ -342,44 +414,50 @@ def run_ours(args, rank, world, local_rank):
         ms, ms_e2e = float(t[0]), float(t[1])
     mark('max over ranks done')
 
-    # ---- secondary (config C3): 8 camera streams of 1080p frames sharded by stream over the ranks (no communication);
-    # per iteration one frame per local stream: H2D of the raw frames, cv2-exact resize + BGR->RGB on the device
-    # (feeder thread, copy stream), frozen inference, argmax + confusion matrix, D2H of the label maps
+    # ---- secondary (config C3): 8 camera streams of 1080p frames sharded by stream over the ranks (no communication).
+    # Temporal batching keeps 8 frames per GPU and launch whatever the number of local streams: a rank with n_local
+    # streams takes 8 / n_local consecutive frames of each per iteration.  Per iteration: H2D of the raw frames, cv2-exact
+    # resize + BGR->RGB on the device (feeder thread, copy stream), frozen inference, argmax + per-batch confusion matrix,
+    # D2H of the label maps.  256 frames per stream => 256 * n_local / 8 iterations per rank.
     streams_total = 8
-    n_local = max(1, streams_total // world)
-    T_STREAM = 12
+    n_local = len(shard_streams(streams_total, world, rank)) if world <= streams_total else (1 if rank < streams_total else 0)
+    FRAMES_PER_STREAM = args.stream_frames
+    iters = FRAMES_PER_STREAM * max(n_local, 1) // BATCH
     raw = []
     for i in range(2):
-        rt, ra = pinned((n_local, 1080, 1920, 3), torch.uint8)
+        rt, ra = pinned((BATCH, 1080, 1920, 3), torch.uint8)
         ra[...] = np.random.default_rng(1000 + 10 * rank + i).integers(0, 256, size=ra.shape, dtype=np.uint8)
-        lt, la = pinned((n_local, 1080, 1920), torch.uint8)
-        la[...] = synthetic_labels(n_local, 1080, 1920, seed=200 + rank + i, block=64)
+        lt, la = pinned((BATCH, 1080, 1920), torch.uint8)
+        la[...] = synthetic_labels(BATCH, 1080, 1920, seed=200 + rank + i, block=64)
         raw.append((rt, ra, lt, la))
     for i in range(3):
         st.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
-        st.infer_metric(n_local, nat.BN_MOVING)
+        st.infer_metric(BATCH, nat.BN_MOVING)
 
     def feed_streams():
-        for i in range(T_STREAM):
+        for i in range(iters):
             st.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
+    fth = threading.Thread(target=feed_streams, daemon=True)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_w0 = time.time()
     s0.record(stream)
-    fth = threading.Thread(target=feed_streams, daemon=True)
     fth.start()
-    for i in range(T_STREAM):
-        st.infer_metric(n_local, nat.BN_MOVING)
+    for i in range(iters):
+        st.infer_metric(BATCH, nat.BN_MOVING)
     s1.record(stream)
     fth.join()
-    barrier()
+    torch.cuda.synchronize()
     ms_streams = max(s0.elapsed_time(s1), 1000.0 * (time.time() - t_w0))
+    barrier()
     if world > 1:
         t = torch.tensor([ms_streams], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_streams = float(t[0])
-    infer_streams = {'frames_per_sec': T_STREAM * n_local * world / (ms_streams / 1000.0), 'streams': n_local * world,
-                     'frames_per_stream': T_STREAM, 'source': '1080x1920 u8 BGR frames + 1080p teacher label maps (pinned host)',
+    infer_streams = {'frames_per_sec': FRAMES_PER_STREAM * streams_total / (ms_streams / 1000.0), 'streams': streams_total,
+                     'frames_per_stream': FRAMES_PER_STREAM, 'frames_per_gpu_launch': BATCH,
+                     'batching': 'temporal: %d consecutive frames of each of the rank\'s %d streams per launch' % (BATCH // max(n_local, 1), n_local),
+                     'source': '1080x1920 u8 BGR frames + 1080p teacher label maps (pinned host)',
                      'includes': 'H2D, on-device cv2-exact resize to 512x1024 + BGR->RGB, frozen inference, argmax, '
                                  'per-batch confusion matrix, D2H of int32 label maps'}
     mark('stream-sharded inference done')
@@ -447,34 +525,50 @@ def run_ours(args, rank, world, local_rank):
         t_ms = top[1]['ms'] / top[1]['launches']
         a_gbs = top[1]['algo_bytes'] / top[1]['launches'] / (t_ms * 1e-3) / 1e9
         step_ms_prof = sum(v['ms'] for v in prof.values()) / 3
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'dominant_kernel_traffic.json')
+        # DRAM bytes per launch of the dominant kernel: not measurable from inside this process (ncu replays kernels) --
+        # taken from this round's committed `ncu --set full` capture of the same kernel, null if there is none for it
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r02_dominant_kernel_traffic.json')
         if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic = json.load(f).get(top[0])
+                    tj = json.load(f)
+                traffic, traffic_src = tj.get(top[0]), tj.get('_source')
             except Exception:
                 traffic = None
         line = {
             'metric': 'distill_steps_per_sec', 'value': steps_s, 'unit': 'steps/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
-            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp16',
             'data': 'synthetic',
-            'config': {'workload': 'C2: AMS online distillation phase (K iterations), batch 8/GPU @ 512x1024, 7 classes, '
+            'config': {'workload': ('C4: data-parallel AMS online distillation phase (K iterations), PASCAL VOC 21-class graph (depthwise BN decay '
+                                    '0.98), class vector of experiment 40 (4 classes), batch 8/GPU @ 512x1024, ' if multi else
+                                    'C2: AMS online distillation phase (K iterations), Cityscapes 19-class graph, batch 8 @ 512x1024, '
+                                    '7 classes (experiment 12), ') +
                                    'coord_desc_auto 5 % selection at iteration 0 + masked Adam + delta pack at the end',
+                       'storage': 'forward activations fp16, 1x1 weights fp16 (split hi+lo where Cout <= 256), activation gradients '
+                                  'bf16, accumulation / statistics / parameters / Adam fp32',
                        'global_batch': BATCH * world, 'parallelism': 'dp%d' % world if world > 1 else 'single',
+                       'value_counts': 'one step = one iteration on ONE GPU\'s 8 frames; a global-batch-%d step takes ms_per_step' % (BATCH * world),
+                       'global_steps_per_sec': K / (ms / 1000.0),
+                       'gradient_exchange': (('2 NCCL buckets, late-layer bucket (%d of %d floats) overlapped with backward'
+                                              % (st.n_trainable - dp.split, st.n_trainable)) if (dp is not None and dp.comm_stream is not None)
+                                             else ('one flat NCCL allreduce after backward' if dp is not None else 'none (single GPU)')),
                        'l2': 'no explicit flush: each step streams ~3 GB of activations (>> 126 MB L2) and batches are distinct',
                        'delta_bytes': delta_len, 'kept_coordinates': kept,
                        'batchnorm': ('global batch: statistics summed over ranks through NVLink peer memory inside the BN kernels'
                                      if (dp is not None and dp.sync_bn) else
                                      ('per replica' + (' (peer-memory setup failed: %s)' % dp.sync_bn_error if dp.sync_bn_error else '')
                                       if dp is not None else 'single process')),
-                       'host_sync': 'none inside the phase: losses land in page-locked slots, read after the phase'},
+                       'host_sync': 'one per phase besides its end: select_topk after iteration 0 returns the kept count and the '
+                                    'threshold to the host (the reference prints them, SemanticNetwork.py:279-281); the K steps '
+                                    'themselves are enqueued without a round trip, losses land in page-locked slots read after the phase'},
             'e2e': {'value': e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': h2d_step, 'd2h_bytes_per_step': 4 + delta_len2 // K,
                     'ms_per_step': ms_e2e / K},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': top[0], 'achieved': a_gbs, 'peak': peak, 'unit': 'GB/s', 'frac': a_gbs / peak,
-                         'traffic': traffic, 'peak_source': peak_src, 'avg_launch_ms': t_ms,
+                         'traffic': traffic, 'traffic_source': traffic_src, 'algo_bytes_per_launch': top[1]['algo_bytes'] / top[1]['launches'],
+                         'peak_source': peak_src, 'avg_launch_ms': t_ms,
                          'share_of_step': top[1]['ms'] / 3 / step_ms_prof,
                          'whole_step_frac_layer_boundary': (K / (ms / 1000.0)) * ALGO_BYTES_STEP / (peak * 1e9),
                          'kernel_groups_ms_per_step': {k: round(v['ms'] / 3, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])},
@@ -482,6 +576,8 @@ def run_ours(args, rank, world, local_rank):
             'infer': infer,
             'infer_streams': infer_streams,
         }
+        if dp_exact is not None:
+            line['dp_exact'] = dp_exact
         if ms_replica_bn is not None:
             line['per_replica_bn'] = {'value': K * world / (ms_replica_bn / 1000.0), 'unit': 'steps/s', 'ms_per_step': ms_replica_bn / K,
                                       'note': 'same phase with per-replica BatchNorm statistics (not the reference\'s global-batch semantics)'}
@@ -505,6 +601,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--sync-bn', type=int, default=1, help='N > 1: 1 = global-batch BatchNorm statistics (reference semantics), 0 = per replica')
+    ap.add_argument('--buckets', type=int, default=1, help='N > 1: 1 = two gradient buckets, the late one overlapped with backward; 0 = one flat allreduce')
+    ap.add_argument('--stream-frames', type=int, default=256, help='frames per camera stream of the C3 block')
     ap.add_argument('--verbose', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -52,6 +52,19 @@ void ams_destroy(ams_net* net);
 int ams_set_stream(ams_net* net, void* cuda_stream);
 int ams_synchronize(ams_net* net);
 
+/* ---- frozen hand-off (server -> client model).
+ * get_frozen_graph + save_to_frozen_graph -- SemanticNetwork.py:706-714 -> trim_graph_frozen(kill_norms=True),
+ * utils/graph_utils.py:79-126: writes the client model to `path`.  The reference writes a TF GraphDef with constants;
+ * this library has no GraphDef, so the container ("AMSFRZ01") holds what that graph holds: every variable of the
+ * student (272 tensors, tf.global_variables() order) to be run with inference-mode BatchNorm on the MOVING statistics. */
+int ams_export_frozen(ams_net* net, const char* path);
+/* frozen branch of SemanticNetwork.__init__ -- SemanticNetwork.py:80-118: a handle built from an exported client model.
+ * cfg supplies height / width / device / selected classes / queue capacity; num_classes and graph_variant come from
+ * the file (cfg->num_classes must be 0 or match).  The handle is inference-only: ams_train_* fail on it
+ * ("Can't train frozen graph!!!", SemanticNetwork.py:217); run it with AMS_BN_MOVING. */
+ams_net* ams_create_frozen(const char* path, const ams_config* cfg);
+int ams_is_frozen(const ams_net* net);
+
 /* ---- checkpoint variable layout: SaveHelper, utils/utils.py:10-49; names are TF variable names with ':0' */
 int ams_num_tensors(const ams_net* net);
 /* i-th variable in `tf.global_variables()` order of the shipped graph; shape4 zero-padded to 4 dims */
@@ -136,6 +149,15 @@ void* ams_step_terms_device(ams_net* net);
 int ams_apply_optimizer_device(ams_net* net, float lr, int masked, float* out_loss_pinned);
 /* device pointer + length (floats) of the gradient arena, for an NCCL allreduce issued by the host plumbing */
 void* ams_gradient_arena(ams_net* net, long long* count);
+/* Bucketed gradient exchange overlapped with the backward pass ("1-4 buckets overlapped with backward;
+ * late-layer buckets first").  The arena splits at ams_gradient_bucket_split() floats into an early-layer bucket
+ * [0, split) and a late-layer bucket [split, count): every layer of the final-resolution stage + ASPP + logits (~90 % of
+ * the coordinates), complete after ~45 % of the backward pass.  ams_gradient_bucket_wait() makes `cuda_stream` wait
+ * until the late bucket of the most recently enqueued ams_train_forward_backward() is complete (an event recorded in
+ * the middle of the step -- an external event node when the step is replayed as a CUDA graph), so the host plumbing
+ * can run that bucket's allreduce on its own stream while the high-resolution layers are still in backward. */
+long long ams_gradient_bucket_split(const ams_net* net);
+int ams_gradient_bucket_wait(ams_net* net, void* cuda_stream);
 /* Adam + mask with gradients scaled by grad_scale (= 1 / global n_valid) */
 int ams_apply_optimizer(ams_net* net, float lr, int masked, float grad_scale);
 

@@ -139,6 +139,25 @@ def main():
         print('[dp] %d steps with the exchange: losses %s, epoch %d, error %d, ranks bit-identical: %s'
               % (steps, ['%.5f' % x for x in losses], ep, err, same), flush=True)
     ok &= same and err == 0 and ep == steps and len(losses) == steps and bool(np.all(np.isfinite(losses)))
+    # bucketed exchange (late-layer bucket reduced on the communication stream WHILE backward continues, released by an event
+    # recorded in the middle of the step / an external event node of the replayed graph) == one flat allreduce after backward
+    st_f = make()
+    dp_f = DataParallelStudent(st_f, sync_bn=True, buckets=False)
+    for i in range(steps):
+        st_f.enqueue(frames[i][rank * B:(rank + 1) * B], labels[i][rank * B:(rank + 1) * B])
+    for i in range(steps):
+        dp_f.train_step_async(LR, False)
+    losses_f = dp_f.losses()
+    p_flat = st_f.get_trainable_flat()
+    p_buck = params.cpu().numpy()
+    d_rel = rel(p_buck, p_flat)
+    n_diff = int(np.count_nonzero(p_buck != p_flat))
+    if rank == 0:
+        print('[dp] bucketed (split at %d of %d floats, overlapped) vs flat allreduce after %d steps: %d parameters differ, rel-L2 %.2e, '
+              'losses equal: %s' % (dp.split, p_flat.size, steps, n_diff, d_rel, losses == losses_f), flush=True)
+    ok &= dp.split > 0 and dp.comm_stream is not None and d_rel < 1e-6 and (world > 2 or n_diff == 0)
+    dp_f.close()
+    st_f.close()
     # switching the exchange off and on again re-captures the step
     st.syncbn_enable(False)
     st.enqueue(frames[0][rank * B:(rank + 1) * B], labels[0][rank * B:(rank + 1) * B])

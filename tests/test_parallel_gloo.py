@@ -94,6 +94,9 @@ class _StubStudent:
     def synchronize(self):
         pass
 
+    def gradient_bucket_split(self):
+        return 4                                  # two buckets: [0, 4) early layers, [4, 6) late layers
+
 
 def _dp_worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
@@ -113,8 +116,8 @@ def _dp_worker(rank, world, port, out_dir):
 
 
 def test_data_parallel_student_host_logic(tmp_path):
-    """order of the exchange step (backward -> allreduce(grad), allreduce(terms) -> Adam reading the global terms), loss
-    slots filled per step and drained by losses(), identical state on both ranks"""
+    """order of the exchange step (backward -> allreduce of the late and the early gradient bucket, allreduce(terms) ->
+    Adam reading the global terms), loss slots filled per step and drained by losses(), identical state on both ranks"""
     world = 2
     mp.spawn(_dp_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     a, b = (np.load(os.path.join(tmp_path, 'dp%d.npy' % r)) for r in range(2))
