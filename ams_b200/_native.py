@@ -48,6 +48,7 @@ _SIGNATURES = {
     'ams_export_frozen': (_i, [_vp, C.c_char_p]),
     'ams_create_frozen': (_vp, [C.c_char_p, _vp]),
     'ams_is_frozen': (_i, [_vp]),
+    'ams_set_block_fusion': (_i, [_vp, _i]),
     'ams_queue_size': (_i, [_vp]),
     'ams_queue_clear': (_i, [_vp]),
     'ams_infer': (_i, [_vp, _i, _vp]),
@@ -86,6 +87,8 @@ _SIGNATURES = {
     'ams_debug_dw_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
     'ams_debug_dw_bwd_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
     'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
+    'ams_op_fused_block': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'ams_debug_fused_timeline': (_i, [_vp]),
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     'ams_op_resize_u8': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),

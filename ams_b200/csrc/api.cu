@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "net.cuh"
+#include "fused_block.cuh"
 
 namespace ams {
 static thread_local std::string g_last_error;
@@ -150,6 +151,24 @@ ams_net* ams_create(const ams_config* cfg) {
     if (!ok) return fail("device allocation failed");
     cudaMemcpy(net->cast_table, table.data(), table.size() * sizeof(WeightCast), cudaMemcpyHostToDevice);
     cudaMemcpy(net->segs_dev, segs.data(), segs.size() * sizeof(VarSeg), cudaMemcpyHostToDevice);
+    // block-fused frozen inference (fused_block.cu): padded per-channel parameter vectors of every eligible block
+    net->fused_params.assign(net->layers.size(), nullptr);
+    {
+        // OFF by default: bit-identical to the per-layer schedule but measured slower on B200 (the tensor pipe
+        // retires one small-N tcgen05.mma every ~150 cycles whatever its N, and a 64-channel chunk needs 16-24 of them)
+        const char* nf = getenv("AMS_BLOCK_FUSION");
+        net->block_fusion = (nf && nf[0] == '1');
+        for (size_t i = 0; i + 2 < net->layers.size(); ++i) {
+            const LayerDef& e = net->layers[i]; const LayerDef& dw = net->layers[i + 1]; const LayerDef& pr = net->layers[i + 2];
+            if (e.kind != kConv1x1 || dw.kind != kDepthwise || pr.kind != kConv1x1 || dw.input != static_cast<int>(i) ||
+                pr.input != static_cast<int>(i + 1)) continue;
+            FusedBlockDesc f;
+            f.N = 1; f.H = e.out_h; f.W = e.out_w; f.Cin = e.cin; f.Cexp = e.cout; f.Cout = pr.cout; f.stride = dw.stride; f.dil = dw.dil;
+            if (!fused_block_supported(f)) continue;
+            if (cudaMalloc(reinterpret_cast<void**>(&net->fused_params[i]), fused_block_param_floats(f) * sizeof(float)) != cudaSuccess)
+                return fail("device allocation failed");
+        }
+    }
     const int cap = cfg->queue_capacity > 0 ? cfg->queue_capacity : 4;
     net->slots.resize(cap);
     for (int i = 0; i < cap; ++i) {
@@ -180,6 +199,7 @@ void ams_destroy(ams_net* h) {
                     net->bnpool, net->wpool, net->select_sc, net->head_st, net->cast_table, net->segs_dev, net->pack_bits,
                     net->pack_vals, net->pack_counts, net->pack_kept};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (float* p : net->fused_params) if (p) cudaFree(p);
     if (net->own_stream) cudaStreamDestroy(net->own_stream);
     if (net->copy_stream) cudaStreamDestroy(net->copy_stream);
     if (net->side_stream) cudaStreamDestroy(net->side_stream);
@@ -444,6 +464,15 @@ int ams_enqueue_raw(ams_net* h, const uint8_t* frames, int src_h, int src_w, int
         net->filled.push_back(slot);
     }
     net->qcv.notify_all();
+    return 0;
+}
+int ams_set_block_fusion(ams_net* h, int on) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->block_fusion = on != 0;
+    for (auto& kv : net->plans)                      // captured inference graphs contain the old schedule
+        for (int k = 0; k < 2; ++k)
+            if (kv.second->infer_graph[k]) { cudaGraphExecDestroy(kv.second->infer_graph[k]); kv.second->infer_graph[k] = nullptr; }
     return 0;
 }
 int ams_queue_size(ams_net* h) {
@@ -940,6 +969,35 @@ int ams_op_conv1x1(const void* a, const void* w, int M, int N, int K, const floa
     GemmPlan pl;
     if (gemm_plan(d, sms, &pl)) return -1;
     return gemm_launch(pl, as_stream(stream));
+}
+
+static void* g_fused_debug_timeline = nullptr;
+/* diagnostics (tools/micro/fused_block_run.py): device buffer of 3 x 64 x 4 u64 that the next ams_op_fused_block fills with the
+ * timeline (ns) of CTA 0: [MMA issuer | group E | group W][chunk][event] */
+int ams_debug_fused_timeline(void* device_buffer) { g_fused_debug_timeline = device_buffer; return 0; }
+
+int ams_op_fused_block(const void* x, int n, int h, int w_, int cin, int cexp, int cout, int dil, const void* we, const void* we_lo,
+                       const float* s1, const float* t1, const float* wd, const float* s2, const float* t2, const void* wp, const void* wp_lo,
+                       const float* s3, const float* t3, int residual, void* out, void* stream) {
+    int dev = 0; cudaGetDevice(&dev);
+    int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    FusedBlockDesc d;
+    d.N = n; d.H = h; d.W = w_; d.Cin = cin; d.Cexp = cexp; d.Cout = cout; d.stride = 1; d.dil = dil;
+    d.x = x; d.We = we; d.We_lo = we_lo; d.ld_we = cin; d.Wp = wp; d.Wp_lo = wp_lo; d.ld_wp = cexp;
+    d.s3 = s3; d.t3 = t3; d.residual = residual ? x : nullptr; d.out = out;
+    d.debug_timeline = g_fused_debug_timeline;
+    AMS_REQUIRE(fused_block_supported(d), "fused block: unsupported geometry");
+    float* params = nullptr;
+    AMS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&params), fused_block_param_floats(d) * sizeof(float)));
+    d.params = params;
+    FusedBlockPlan pl;
+    int rc = fused_block_fill_params(d, s1, t1, wd, s2, t2, as_stream(stream));
+    if (!rc) rc = fused_block_plan(d, sms, &pl);
+    if (!rc) rc = fused_block_launch(pl, as_stream(stream));
+    const cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+    cudaFree(params);
+    if (!rc && e != cudaSuccess) { set_last_error(std::string("fused block kernel: ") + cudaGetErrorString(e)); rc = -1; }
+    return rc;
 }
 
 int ams_op_wgrad(const void* x, int cin, const void* dz, int cout, long long M, float* dw, void* stream) {

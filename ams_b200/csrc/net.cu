@@ -302,6 +302,23 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             }
             p->has_fwd[i] = 1;
         }
+        // block-fused frozen inference: expand (i) -> depthwise (i+1) -> project (i+2) of every stride-1 block
+        p->fused_plan.resize(L.size()); p->fused.assign(L.size(), 0);
+        for (size_t i = 0; i + 2 < L.size(); ++i) {
+            if (i >= net->fused_params.size() || !net->fused_params[i]) continue;
+            const LayerDef& e = L[i]; const LayerDef& dw = L[i + 1]; const LayerDef& pr = L[i + 2];
+            FusedBlockDesc f;
+            f.N = N; f.H = e.out_h; f.W = e.out_w; f.Cin = e.cin; f.Cexp = e.cout; f.Cout = pr.cout; f.stride = dw.stride; f.dil = dw.dil;
+            f.x = p->buf[e.input].y;
+            f.We = net->wpool + e.wfwd_off; f.We_lo = e.wlo_off >= 0 ? net->wpool + e.wlo_off : nullptr; f.ld_we = e.ld_fwd;
+            f.Wp = net->wpool + pr.wfwd_off; f.Wp_lo = pr.wlo_off >= 0 ? net->wpool + pr.wlo_off : nullptr; f.ld_wp = pr.ld_fwd;
+            f.params = net->fused_params[i];
+            f.s3 = fscale(net, pr); f.t3 = fshift(net, pr);
+            f.residual = pr.residual >= 0 ? p->buf[pr.residual].y : nullptr;
+            f.out = p->buf[i + 2].y;
+            if (fused_block_plan(f, net->num_sms, &p->fused_plan[i])) return -1;
+            p->fused[i] = 1;
+        }
     }
     if (need_backward && !p->have_backward) {
         size_t red_ws = 0, wg_ws = 0;
@@ -383,6 +400,14 @@ int net_prepare_weights(Net* net, bool frozen) {
             if (bn_fold_frozen(net->params + d.gamma_off, net->params + d.beta_off, net->moving + d.mm_off,
                                net->moving + d.mv_off, kFrozenBnEps, fscale(net, d), fshift(net, d), d.cout, net->stream)) return -1;
         }
+        for (size_t i = 0; i + 2 < net->layers.size() && i < net->fused_params.size(); ++i) {
+            if (!net->fused_params[i]) continue;
+            const LayerDef& e = net->layers[i]; const LayerDef& dw = net->layers[i + 1]; const LayerDef& pr = net->layers[i + 2];
+            FusedBlockDesc f;
+            f.Cin = e.cin; f.Cexp = e.cout; f.Cout = pr.cout; f.stride = dw.stride; f.dil = dw.dil; f.params = net->fused_params[i];
+            if (fused_block_fill_params(f, fscale(net, e), fshift(net, e), net->params + dw.w_off, fscale(net, dw), fshift(net, dw),
+                                        net->stream)) return -1;
+        }
         net->fold_dirty = false;
     }
     return 0;
@@ -429,6 +454,15 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
             } else {
                 PROF("imgpool_fwd", 2.0 * p->N * L[d.input].out_h * L[d.input].out_w * d.cin, imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s));
             }
+            continue;
+        }
+        if (frozen && net->block_fusion && p->fused[i]) {
+            // one kernel for expand -> depthwise -> project (+ skip): the 6C-wide tensors stay in TMEM / shared memory
+            const LayerDef& pr = L[i + 2];
+            const double px = static_cast<double>(p->N) * d.out_h * d.out_w;
+            PROF("fused_block", 2.0 * px * (d.cin + pr.cout * (pr.residual >= 0 ? 2 : 1)) + 2.0 * (d.cin * d.cout + d.cout * pr.cout) + 36.0 * d.cout,
+                 fused_block_launch(p->fused_plan[i], s));
+            i += 2;
             continue;
         }
         if (pool_pending && d.name == "concat_projection") {

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/ams_b200.h"
+#include "fused_block.cuh"
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -70,6 +71,9 @@ struct Plan {
     std::vector<GemmPlan> fwd_frozen, fwd_train, dgrad;
     std::vector<WgradPlan> wgrad;
     std::vector<char> has_fwd, has_dgrad, has_wgrad;
+    // frozen inference: fused[i] != 0 for the EXPAND layer i of a block that runs as one kernel (fused_block.cu); the
+    // expand / depthwise outputs of such a block are never materialised
+    std::vector<FusedBlockPlan> fused_plan; std::vector<char> fused;
     // training-mode fusion (dw_tiled.cu): dw_fused[i] = depthwise layer i runs the fused backward and reads its
     // producer's RAW output; lazy_y[j] = layer j's normalised output is never materialised in training mode
     std::vector<char> dw_fused, lazy_y;
@@ -142,6 +146,8 @@ struct Net {
     bool sync_active = false;           // true only while a TRAINING step is being enqueued (inference never exchanges)
     uint8_t* pack_bits = nullptr; __half* pack_vals = nullptr; unsigned int* pack_counts = nullptr; unsigned long long* pack_kept = nullptr;
     bool weights_dirty = true, fold_dirty = true;
+    bool block_fusion = false;         // frozen inference: stride-1 inverted-residual blocks as one kernel each (ams_set_block_fusion)
+    std::vector<float*> fused_params;  // per expand layer: [13][cpad] padded per-channel vectors of the fused kernel (or null)
     bool frozen = false;               // built by ams_create_frozen: inference only ("Can't train frozen graph", SemanticNetwork.py:217)
     HeadGeom head{};
     std::map<int, std::unique_ptr<Plan>> plans;

@@ -176,6 +176,10 @@ class Student:
         """ams_export_frozen: the client model (reference save_to_frozen_graph, SemanticNetwork.py:711-714)."""
         nat.check(self._L.ams_export_frozen(self._h, os.fsencode(path)), 'export_frozen')
 
+    def set_block_fusion(self, on):
+        """frozen inference: one kernel per stride-1 inverted-residual block (default) or one kernel per layer"""
+        nat.check(self._L.ams_set_block_fusion(self._h, 1 if on else 0), 'set_block_fusion')
+
     def queue_size(self):
         return self._L.ams_queue_size(self._h)
 

@@ -280,7 +280,9 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         from ams_b200.parallel import DataParallelStudent
         dp = DataParallelStudent(st, sync_bn=bool(args.sync_bn), strict=False, buckets=bool(args.buckets))
-        dp_exact = check_dp_exact(st, dp, ckpt, num_classes, classes, local_rank, stream, host[0][1], host[0][3], world, mark)
+        # the SAME 8 frames on every rank (the timed batches are rank-specific)
+        dp_exact = check_dp_exact(st, dp, ckpt, num_classes, classes, local_rank, stream, synthetic_frames(BATCH, H, W, seed=4242),
+                                  synthetic_labels(BATCH, H, W, seed=4242), world, mark)
         for k, v in ckpt.items():                  # the check moved weights, moving statistics and Adam state: start clean
             st.set_tensor(k, v)
         st.reset_optimizer()

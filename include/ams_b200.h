@@ -179,6 +179,14 @@ int ams_syncbn_connect(ams_net* net, const void* all_handles, int count);
 int ams_syncbn_enable(ams_net* net, int on);
 int ams_syncbn_status(ams_net* net, unsigned int* out_epoch, unsigned int* out_error);
 
+/* Frozen inference can run every stride-1 inverted-residual block (13 of the 17) as ONE kernel (expand GEMM -> TMEM ->
+ * BN/ReLU6 -> shared-memory halo tile -> depthwise -> shared-memory A operand -> project GEMM): the 6C-wide tensors
+ * never reach HBM and ams_get_activation() has nothing to return for the expand / depthwise layers of those blocks.
+ * Results are bit-identical to the one-kernel-per-layer schedule (tests/test_net_gpu.py).  Default OFF (env
+ * AMS_BLOCK_FUSION=1: on): on B200 the fused kernel measured 2.0-2.3 ms per batch of 8 frames against 1.76 ms for the
+ * per-layer schedule (DESIGN.md 4 has the timeline and the diagnosis). */
+int ams_set_block_fusion(ams_net* net, int on);
+
 /* ---- parity hooks */
 int ams_get_logits(ams_net* net, float* host, long long count);       /* low-res `semantic` [n,h,w,num_classes] of the last run */
 int ams_get_gradients(ams_net* net, float* host);                     /* trainable-arena order, last train step */
@@ -217,6 +225,15 @@ int ams_debug_dw_bwd_tile(int n, int h, int w, int c, int ho, int wo, int stride
 int ams_op_conv1x1(const void* a_16, const void* w_16 /*[N][K]*/, int M, int N, int K, const float* scale,
                    const float* shift, const float* rowbias, int rows_per_image, const void* residual_16, int act,
                    void* out, int out_fp32, int ldc, int grad_types, const void* w_lo_16, void* stream);
+/* one stride-1 inverted-residual block of the FROZEN graph in a single kernel (ams_b200/csrc/fused_block.cu):
+ * out = BN3(project(relu6(BN2(depthwise3x3_dil(relu6(BN1(expand(x)))))))) [+ x]; x [n,h,w,cin] fp16; we [cexp][cin] and
+ * wp [cout][cexp] fp16 (+ optional low planes of the split weights); wd [3,3,cexp] fp32; s1..s3 / t1..t3 folded BN scale / shift */
+int ams_op_fused_block(const void* x_f16, int n, int h, int w_, int cin, int cexp, int cout, int dilation, const void* we_f16,
+                       const void* we_lo_f16, const float* s1, const float* t1, const float* wd, const float* s2, const float* t2,
+                       const void* wp_f16, const void* wp_lo_f16, const float* s3, const float* t3, int residual, void* out_f16,
+                       void* stream);
+/* diagnostics: device buffer (3 x 64 x 4 u64) that the next ams_op_fused_block fills with the timeline (ns) of CTA 0 */
+int ams_debug_fused_timeline(void* device_buffer);
 int ams_op_wgrad(const void* x_f16, int cin, const void* dz_bf16, int cout, long long M, float* dw, void* stream);
 int ams_op_depthwise(const void* in_f16, const float* w, int n, int h, int w_, int c, int stride, int dilation,
                      const float* scale, const float* shift, int act, void* out_f16, void* stream);
