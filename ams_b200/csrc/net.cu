@@ -497,15 +497,19 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
             const double gb = 2.0 * M * d.k_rows + 2.0 * d.k_rows * d.cout + out_bytes + ((frozen && d.residual >= 0) ? out_bytes : 0.0);
             PROF("gemm_fwd", gb, gemm_launch(frozen ? p->fwd_frozen[i] : p->fwd_train[i], s));
         }
+        // TIMING EXPERIMENTS ONLY (results are wrong): upper bound of what removing a launch group would buy
+        static const bool x_skip_fin = [] { const char* e = getenv("AMS_X_SKIP_FWD_FINALIZE"); return e && e[0] == '1'; }();
+        static const bool x_skip_dwapply = [] { const char* e = getenv("AMS_X_SKIP_DW_BN_APPLY"); return e && e[0] == '1'; }();
         if (!frozen) {
             BnLayer bl = bn_layer(net, d, M);
-            if (d.kind == kConv1x1 && p->fwd_train[i].d.stats_partial)
+            if (x_skip_fin && d.kind != kStem) { /* skipped */ }
+            else if (d.kind == kConv1x1 && p->fwd_train[i].d.stats_partial)
                 PROF("bn_finalize", 16.0 * p->fwd_train[i].grid * d.cout, bn_finalize_partials(p->bn_ws, p->fwd_train[i].grid, bl, update_moving ? 1 : 0, s));
             else if (d.kind == kDepthwise)
                 PROF("bn_finalize", 16.0 * dw_rows * d.cout, bn_finalize_partials(p->bn_ws, dw_rows, bl, update_moving ? 1 : 0, s));
             else
                 PROF("bn_stats", out_bytes, bn_forward_stats(b.z, bl, update_moving ? 1 : 0, p->bn_ws, s));
-            if (!p->lazy_y[i])
+            if (!p->lazy_y[i] && !(x_skip_dwapply && d.kind == kDepthwise))
                 PROF("bn_apply", (d.residual >= 0 ? 3.0 : 2.0) * out_bytes,
                      bn_apply(b.z, bl.scale, bl.shift, d.act, d.residual >= 0 ? p->buf[d.residual].y : nullptr, b.y, M, d.cout, s));
         }
@@ -573,8 +577,10 @@ int net_backward(Net* net, Plan* p, bool normalize) {
             PROF("dw_bwd_fused", 2.0 * tb + 2.0 * ib, dw_conv_bwd_fused(f, g, &p->pending_bn_rows, s));
             continue;
         }
+        static const bool x_skip_bfin = [] { const char* e = getenv("AMS_X_SKIP_BWD_FINALIZE"); return e && e[0] == '1'; }();
         if (p->pending_bn_rows > 0) {
             // the fused depthwise backward left the masked gradient in b.g and the column sums in bn_ws
+            if (!x_skip_bfin)
             PROF("bn_bwd_finalize", 16.0 * p->pending_bn_rows * d.cout,
                  bn_backward_finalize_partials(p->bn_ws, p->pending_bn_rows, bl, p->coef[1], net->grads + d.gamma_off, net->grads + d.beta_off, s));
             PROF("bn_bwd_apply", 3.0 * tb, bn_backward_apply(b.g, b.z, bl, p->coef[1], b.gz, s));

@@ -436,29 +436,57 @@ def run_ours(args, rank, world, local_rank):
         st.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
         st.infer_metric(BATCH, nat.BN_MOVING)
 
-    def feed_streams():
-        for i in range(iters):
-            st.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
-    fth = threading.Thread(target=feed_streams, daemon=True)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_w0 = time.time()
-    s0.record(stream)
-    fth.start()
-    for i in range(iters):
-        st.infer_metric(BATCH, nat.BN_MOVING)
-    s1.record(stream)
-    fth.join()
-    torch.cuda.synchronize()
-    ms_streams = max(s0.elapsed_time(s1), 1000.0 * (time.time() - t_w0))
-    barrier()
-    if world > 1:
-        t = torch.tensor([ms_streams], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_streams = float(t[0])
+    # two schedules: (a) one handle; (b) TWO handles of the same model on this GPU, each with its own stream, feeder thread
+    # and half of the rank's batches -- the per-layer kernels of the low-resolution stages are single-wave and latency
+    # bound, so two independent batches in flight fill the machine (what a serving process with several streams does)
+    extra = []
+    for _ in range(2):
+        hx = Student(num_classes, H, W, classes, device=local_rank, queue_capacity=4)
+        for k, v in ckpt.items():
+            hx.set_tensor(k, v)
+        for i in range(3):
+            hx.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
+            hx.infer_metric(BATCH, nat.BN_MOVING)
+        extra.append(hx)
+
+    def run_streams(handles):
+        share = [iters // len(handles) + (1 if h < iters % len(handles) else 0) for h in range(len(handles))]
+
+        def feed(hd, n):
+            for i in range(n):
+                hd.enqueue_raw(raw[i % 2][1], raw[i % 2][3])
+
+        def work(hd, n):
+            for i in range(n):
+                hd.infer_metric(BATCH, nat.BN_MOVING)
+        threads = [threading.Thread(target=feed, args=(hd, n), daemon=True) for hd, n in zip(handles, share)]
+        threads += [threading.Thread(target=work, args=(hd, n), daemon=True) for hd, n in zip(handles[1:], share[1:])]
+        barrier()
+        t_w0 = time.time()
+        for th in threads:
+            th.start()
+        work(handles[0], share[0])
+        for th in threads:
+            th.join()
+        torch.cuda.synchronize()
+        ms_w = 1000.0 * (time.time() - t_w0)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms_w], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_w = float(t[0])
+        return ms_w
+    ms_by_handles = {1: run_streams([st]), 2: run_streams([st, extra[0]]), 3: run_streams([st] + extra)}
+    for hx in extra:
+        hx.close()
+    best_h = min(ms_by_handles, key=ms_by_handles.get)
+    ms_streams = ms_by_handles[best_h]
     infer_streams = {'frames_per_sec': FRAMES_PER_STREAM * streams_total / (ms_streams / 1000.0), 'streams': streams_total,
+                     'handles_per_gpu': best_h,
+                     'frames_per_sec_by_handles': {str(h): FRAMES_PER_STREAM * streams_total / (m / 1000.0) for h, m in ms_by_handles.items()},
                      'frames_per_stream': FRAMES_PER_STREAM, 'frames_per_gpu_launch': BATCH,
                      'batching': 'temporal: %d consecutive frames of each of the rank\'s %d streams per launch' % (BATCH // max(n_local, 1), n_local),
+                     'timing': 'wall clock around the whole run (threads started inside), max over ranks',
                      'source': '1080x1920 u8 BGR frames + 1080p teacher label maps (pinned host)',
                      'includes': 'H2D, on-device cv2-exact resize to 512x1024 + BGR->RGB, frozen inference, argmax, '
                                  'per-batch confusion matrix, D2H of int32 label maps'}
