@@ -73,6 +73,15 @@ _SIGNATURES = {
     'ams_syncbn_enable': (_i, [_vp, _i]),
     'ams_syncbn_status': (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     'ams_apply_delta': (_i, [_vp, _vp, _ll, C.POINTER(_ll)]),
+    'ams_teacher_create': (_vp, [_i, _i]),
+    'ams_teacher_destroy': (None, [_vp]),
+    'ams_teacher_num_tensors': (_i, [_vp]),
+    'ams_teacher_tensor_info': (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i)]),
+    'ams_teacher_set_tensor': (_i, [_vp, C.c_char_p, _vp, _ll]),
+    'ams_teacher_predict': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    'ams_teacher_time_forward': (_i, [_vp, _i, C.POINTER(_f)]),
+    'ams_teacher_layout_num_tensors': (_i, [_i]),
+    'ams_teacher_layout_tensor_info': (_i, [_i, _i, C.c_char_p, _i, C.POINTER(_i), C.POINTER(_i)]),
     'ams_get_logits': (_i, [_vp, _vp, _ll]),
     'ams_get_gradients': (_i, [_vp, _vp]),
     'ams_num_layers': (_i, [_vp]),

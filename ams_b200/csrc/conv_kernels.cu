@@ -36,7 +36,7 @@ __device__ __forceinline__ void stem_pixel(const T* in, const StemGeom& g, int n
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ w, const float* __restrict__ scale,
-                const float* __restrict__ shift, act_t* __restrict__ out) {
+                const float* __restrict__ shift, act_t* __restrict__ out, float act_hi) {
     pdl_entry();
     __shared__ float sw[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
@@ -69,7 +69,7 @@ stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ 
     if (scale) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-            acc[j] = fminf(fmaxf(fmaf(acc[j], scale[half * 16 + j], shift[half * 16 + j]), 0.f), 6.f);
+            acc[j] = fminf(fmaxf(fmaf(acc[j], scale[half * 16 + j], shift[half * 16 + j]), 0.f), act_hi);      // ReLU6 (6) or ReLU (+inf)
     }
     act_t* o = out + pix * 32 + half * 16;
     stg256(o, pack8h(acc), pack8h(acc + 8));
@@ -372,13 +372,14 @@ int dw_strips_per_block(const Conv2dGeom& g) {
 // ============================================================================================ host
 int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
                   int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w, const float* scale,
-                  const float* shift, act_t* out, cudaStream_t s) {
+                  const float* shift, act_t* out, cudaStream_t s, int act) {
     StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
     const long long total = static_cast<long long>(N) * Ho * Wo * 2;
+    const float act_hi = act == 1 ? INFINITY : 6.f;
     if (in_is_u8)
-        AMS_LAUNCH((stem_fwd_kernel<uint8_t>), blocks_for(total, 256), 256, 0, s, static_cast<const uint8_t*>(in), g, w, scale, shift, out);
+        AMS_LAUNCH((stem_fwd_kernel<uint8_t>), blocks_for(total, 256), 256, 0, s, static_cast<const uint8_t*>(in), g, w, scale, shift, out, act_hi);
     else
-        AMS_LAUNCH((stem_fwd_kernel<float>), blocks_for(total, 256), 256, 0, s, static_cast<const float*>(in), g, w, scale, shift, out);
+        AMS_LAUNCH((stem_fwd_kernel<float>), blocks_for(total, 256), 256, 0, s, static_cast<const float*>(in), g, w, scale, shift, out, act_hi);
     return 0;
 }
 

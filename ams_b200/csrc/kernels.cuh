@@ -21,7 +21,7 @@ struct Conv2dGeom {          // one image-plane geometry; TF 'SAME' pads resolve
 // out fp16 [N,Ho,Wo,32]; scale/shift != null => y = relu6(acc*scale+shift) (frozen BN fold), else raw z.
 int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo, int pad_top,
                   int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w /*[3,3,3,32]*/,
-                  const float* scale, const float* shift, act_t* out, cudaStream_t s);
+                  const float* scale, const float* shift, act_t* out, cudaStream_t s, int act = 2 /* with scale/shift: 2 ReLU6, 1 ReLU */);
 // dW[3,3,3,32] = sum_pixels patch(in) (x) dz ; partials [chunks][864] then fixed-order reduce.
 int stem_conv_bwd_filter(const void* in, int in_is_u8, int N, int H, int W, int Hp, int Wp, int Ho, int Wo,
                          int pad_top, int pad_left, float pad_value, float norm_scale, float norm_shift,

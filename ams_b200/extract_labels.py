@@ -9,13 +9,15 @@ the pixel arithmetic, with two fix-forwards: the reference's `teacher_conf` line
 that is never assigned and would raise NameError on the first frame -- dropped; frames come from any iterable, not only
 cv2.VideoCapture.
 
-What is NOT here is the teacher network itself: DeeplabV3-Xception65's graph (`<teacher_checkpoint>.meta`) and weights
-are not part of the reference repository (external download, README.md:51-53; `create_teacher` only names three of its
-tensors, utils/graph_utils.py:148-152), so there is nothing to check an Xception65 restatement against.  The teacher is
-therefore a plug-in: any object with `predict(frame_rgb_uint8[h, w, 3]) -> label ids [h, w]`.  `StudentGraphTeacher`
-runs the DeeplabV3-MobileNetV2 graph of this library (frozen BatchNorm, all 19 / 21 classes) behind that interface, so the
-whole path -- ingest, pad, network, crop, PNG dump -- runs on a B200 today; an Xception65 backend would slot in at the
-same place.
+The teacher is a plug-in: any object with `predict(frame_rgb_uint8[h, w, 3]) -> label ids [h, w]`.
+  * `ams_b200.teacher.XceptionTeacher`: DeepLabv3+ / Xception-65 (config C5) on the device through the C ABI
+    (ams_teacher_*, ams_b200/csrc/teacher.cu).  The teacher's graph (`<teacher_checkpoint>.meta`) and weights are not
+    part of the reference repository (external download, README.md:45-46; `create_teacher` only names three of its
+    tensors, utils/graph_utils.py:148-152), so the topology restates the public model-zoo definition and is checked
+    against an independent torch restatement (oracle/teacher_oracle.py): unpinned and unsourced, and said so.
+  * `StudentGraphTeacher`: the DeeplabV3-MobileNetV2 graph of this library (frozen BatchNorm, all 19 / 21 classes) behind the
+    same interface, for checkpoints in the student layout.
+`main()` picks the backend from the variable names of the checkpoint.
 """
 import argparse
 import os
@@ -152,10 +154,22 @@ def extract_labels(flags, teacher, frames_bgr=None, log=print):
     return index_frame
 
 
+def make_teacher(checkpoint_prefix, gpu=0):
+    """Backend by checkpoint layout: 'xception_65/...' variables -> XceptionTeacher, 'MobilenetV2/...' -> StudentGraphTeacher."""
+    path = checkpoint_prefix if checkpoint_prefix.endswith('.npy') else checkpoint_prefix + '.npy'
+    ckpt = np.load(path, allow_pickle=True)
+    variables = ckpt.item() if ckpt.dtype == object else dict(ckpt)
+    if any('xception_65/' in k for k in variables):
+        from .teacher import XceptionTeacher
+        nc = int(np.asarray(variables[[k for k in variables if k.endswith('logits/semantic/biases:0')][0]]).size)
+        return XceptionTeacher(variables, nc, gpu)
+    return StudentGraphTeacher(checkpoint_prefix, gpu)
+
+
 def main(argv=None):
     flags = parse_flags(argv)
     print('Extracting labels...')
-    teacher = StudentGraphTeacher(flags.teacher_checkpoint, flags.gpu)
+    teacher = make_teacher(flags.teacher_checkpoint, flags.gpu)
     try:
         print('Starting Teacher Inference')
         n = extract_labels(flags, teacher)

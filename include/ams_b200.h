@@ -187,6 +187,27 @@ int ams_syncbn_status(ams_net* net, unsigned int* out_epoch, unsigned int* out_e
  * per-layer schedule (DESIGN.md 4 has the timeline and the diagnosis). */
 int ams_set_block_fusion(ams_net* net, int on);
 
+/* ---- teacher network (config C5): DeepLabv3+ / Xception-65, inference only -- the network behind
+ * `sess.run(teacher['predictions'], feed_dict={teacher['images']: frame})` of extract_labels.py:84 (graph imported by
+ * create_teacher, utils/graph_utils.py:129-152).  The teacher's .meta and weights are not in the reference repository;
+ * the topology restates the public model-zoo definition (ams_b200/csrc/teacher.cu) and variables are addressed by the
+ * TF names of that definition, so a checkpoint dict `{'<name>:0': ndarray}` loads with ams_teacher_set_tensor. */
+typedef struct ams_teacher ams_teacher;
+ams_teacher* ams_teacher_create(int num_classes, int device);
+void ams_teacher_destroy(ams_teacher* t);
+int ams_teacher_num_tensors(const ams_teacher* t);
+int ams_teacher_tensor_info(const ams_teacher* t, int index, char* name, int name_capacity, int shape4[4], int* ndim);
+int ams_teacher_set_tensor(ams_teacher* t, const char* name, const float* host, long long count);
+/* frames [n,height,width,3] u8 RGB (the caller applies the reference's 1-px symmetric top/left pad, extract_labels.py:83);
+ * out_labels int32 [n,height,width] = predictions:0; out_logits (may be NULL) fp32 [n, ceil(h/4), ceil(w/4), num_classes]
+ * = logits/semantic/BiasAdd:0 before the final upsample.  Plans are rebuilt when the frame size changes. */
+int ams_teacher_predict(ams_teacher* t, const uint8_t* frames, int n, int height, int width, int32_t* out_labels, float* out_logits);
+/* host-only (no device): the variable table of the restated teacher graph, for checkpoint tooling and tests */
+int ams_teacher_layout_num_tensors(int num_classes);
+int ams_teacher_layout_tensor_info(int num_classes, int index, char* name, int name_capacity, int shape4[4], int* ndim);
+/* device time (CUDA events on the teacher's stream) of one forward pass at the last predicted size, averaged over reps */
+int ams_teacher_time_forward(ams_teacher* t, int reps, float* out_ms);
+
 /* ---- parity hooks */
 int ams_get_logits(ams_net* net, float* host, long long count);       /* low-res `semantic` [n,h,w,num_classes] of the last run */
 int ams_get_gradients(ams_net* net, float* host);                     /* trainable-arena order, last train step */
