@@ -844,6 +844,14 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
         if (plan->smem_bytes <= 227 * 1024 || block_k == 16 || !plan->v2) break;
     }
     AMS_REQUIRE(plan->smem_bytes <= 227 * 1024, "GEMM shared memory overflow");
+    // a plan that fills more than half of the SM's shared memory runs ONE CTA per SM anyway: give it the whole tensor memory,
+    // i.e. two accumulator stages also for 256-column tiles, so that the epilogue of tile i overlaps the MMAs of tile i+1
+    // (the K = N = 728 .. 2048 pointwise convs of the teacher network: the tensor-bound GEMMs of the repository)
+    if (plan->v2 && plan->acc_stages == 1 && plan->smem_bytes > 113 * 1024) {
+        plan->acc_stages = 2;
+        plan->tmem_cols = tmem_cols_for(2 * plan->block_n);
+        AMS_REQUIRE(plan->tmem_cols <= 512u, "TMEM overflow");
+    }
     const int tiles = plan->m_tiles * plan->n_tiles;
     plan->grid = std::min(tiles, (plan->v2 && plan->smem_bytes <= 113 * 1024) ? 2 * num_sms : num_sms);
     if (encode_2d_bf16(&plan->tmA, d.A, d.K, d.M, size_t(d.lda) * 2, plan->block_k, BLOCK_M, plan->block_k * 2)) return -1;

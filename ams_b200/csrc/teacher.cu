@@ -291,7 +291,7 @@ struct Teacher {
     std::vector<TOp> ops;
     std::vector<int> t_c, t_scale;              // per tensor: channels, cumulative stride (1 = input resolution)
     long long n_params = 0, n_fold = 0, n_w16 = 0;
-    float* params = nullptr; float* fold = nullptr; uint16_t* w16 = nullptr;
+    float* params = nullptr; float* fold = nullptr; uint16_t* w16 = nullptr; float* ones = nullptr; float* zeros = nullptr;
     bool dirty = true;
     // plan
     std::vector<TTensor> tens; std::vector<void*> allocs;
@@ -549,6 +549,14 @@ int forward(Teacher* t) {
             // separable_conv2d_same: stride 1 -> 'SAME' (dil on each side); stride 2 -> explicit padding (k_eff - 1) / 2 = dil in
             // front followed by a 'VALID' conv (== 'SAME' at the odd sizes the teacher sees: 1025 x 2049 and its halvings)
             const int pt = o.dil, pl = o.dil;
+            Conv2dGeom cg{N, a.h, a.w, a.c, y.h, y.w, o.stride, o.dil, pt, pl};
+            if (dw_tiled_supported(cg)) {
+                // the student's shared-memory tiled depthwise kernel (dw_tiled.cu): ReLU-on-load = its producer-activation hook
+                // with an identity affine, folded BN (+ ReLU) on the way out
+                if (dw_conv_fwd_tiled(a.p, t->params + o.w_off, cg, o.pre_relu ? t->ones : nullptr, o.pre_relu ? t->zeros : nullptr, 1,
+                                      t->fold + o.fold_off, t->fold + o.fold_off + o.cout, o.act ? 1 : 0, y.p, nullptr, nullptr, s)) return -1;
+                break;
+            }
             const long long total = static_cast<long long>(N) * y.h * y.w * (a.c / 8);
             AMS_LAUNCH((t_dw_kernel), static_cast<unsigned>(ceil_div_ll(total, 256)), 256, 0, s, a.p, t->params + o.w_off, t->fold + o.fold_off,
                        t->fold + o.fold_off + o.cout, y.p, N, a.h, a.w, a.c, y.h, y.w, o.stride, o.dil, pt, pl, o.pre_relu, o.act);
@@ -617,8 +625,15 @@ ams_teacher* ams_teacher_create(int num_classes, int device) {
     bool ok = cudaMalloc(reinterpret_cast<void**>(&t->params), t->n_params * sizeof(float)) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&t->fold), t->n_fold * sizeof(float)) == cudaSuccess &&
               cudaMalloc(reinterpret_cast<void**>(&t->w16), t->n_w16 * sizeof(uint16_t)) == cudaSuccess &&
-              cudaMalloc(reinterpret_cast<void**>(&t->head_st), sizeof(HeadStats)) == cudaSuccess;
+              cudaMalloc(reinterpret_cast<void**>(&t->head_st), sizeof(HeadStats)) == cudaSuccess &&
+              cudaMalloc(reinterpret_cast<void**>(&t->ones), 2 * 2048 * sizeof(float)) == cudaSuccess;
     if (!ok) return fail("device allocation failed");
+    {
+        std::vector<float> oz(2 * 2048, 0.f);
+        for (int i = 0; i < 2048; ++i) oz[i] = 1.f;
+        cudaMemcpy(t->ones, oz.data(), oz.size() * sizeof(float), cudaMemcpyHostToDevice);
+        t->zeros = t->ones + 2048;
+    }
     cudaMemset(t->params, 0, t->n_params * sizeof(float));
     cudaMemset(t->w16, 0, t->n_w16 * sizeof(uint16_t));
     std::vector<WeightCast> table;
@@ -643,7 +658,7 @@ void ams_teacher_destroy(ams_teacher* h) {
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     free_plan(t);
-    void* ptrs[] = {t->params, t->fold, t->w16, t->head_st, t->cast_table};
+    void* ptrs[] = {t->params, t->fold, t->w16, t->head_st, t->cast_table, t->ones};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
