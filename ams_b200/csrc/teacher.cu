@@ -8,7 +8,7 @@
 // dict loads by name.  Arithmetic is unpinned and unsourced here: parity is against
 // oracle/teacher_oracle.py, a torch restatement of the same public definition.
 //
-// Kernels: the 1x1 convolutions (93 % of the 1.4 TFLOP of a 1025x2049 frame; K and N up to 2048: the only tensor-bound
+// Kernels: the 1x1 convolutions (96 % of the 0.84 TFLOP of a 1025x2049 frame; K and N up to 2048: the only tensor-bound
 // GEMMs of the repository) run on the tcgen05 GEMM of gemm.cu with the folded BN / ReLU / residual epilogue; the second
 // stem conv (3x3, 32 -> 64) is an implicit GEMM on tcgen05 fed by nine shifted 4-D TMA boxes per tile (zero padding = TMA
 // out-of-bounds fill); depthwise 3x3 (stride 1/2, dilation 1..18, optional ReLU on load), stride-2 subsampling for the
