@@ -49,6 +49,7 @@ _SIGNATURES = {
     'ams_create_frozen': (_vp, [C.c_char_p, _vp]),
     'ams_is_frozen': (_i, [_vp]),
     'ams_set_block_fusion': (_i, [_vp, _i]),
+    'ams_set_infer_split': (_i, [_vp, _i]),
     'ams_queue_size': (_i, [_vp]),
     'ams_queue_clear': (_i, [_vp]),
     'ams_infer': (_i, [_vp, _i, _vp]),

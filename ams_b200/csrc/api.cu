@@ -102,6 +102,11 @@ ams_net* ams_create(const ams_config* cfg) {
     if (cudaEventCreateWithFlags(&net->ev_pool, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_bucket, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_bucket_main, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaStreamCreateWithFlags(&net->split_ss.main, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    if (cudaStreamCreateWithFlags(&net->split_ss.side, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+    for (cudaEvent_t* e : {&net->split_ss.fork, &net->split_ss.join, &net->ev_split_fork, &net->ev_split_join})
+        if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    { const char* e = getenv("AMS_NO_INFER_SPLIT"); if (e && e[0] == '1') net->infer_split = false; }
     net->stream = net->own_stream;
     if (net_build_topology(net)) return fail("topology");
     const LayerDef& lg = net->layers.back();
@@ -187,6 +192,7 @@ void ams_destroy(ams_net* h) {
     for (auto& kv : net->plans) {
         for (cudaGraphExec_t g : kv.second->train_graph) if (g) cudaGraphExecDestroy(g);
         for (cudaGraphExec_t g : kv.second->infer_graph) if (g) cudaGraphExecDestroy(g);
+        for (auto& hv : kv.second->half) if (hv) for (void* p : hv->allocations) cudaFree(p);
         for (void* p : kv.second->allocations) cudaFree(p);
     }
     for (auto& q : net->slots) { if (q.frames) cudaFree(q.frames); if (q.labels) cudaFree(q.labels); if (q.consumed) cudaEventDestroy(q.consumed); }
@@ -208,6 +214,9 @@ void ams_destroy(ams_net* h) {
     if (net->ev_pool) cudaEventDestroy(net->ev_pool);
     if (net->ev_bucket) cudaEventDestroy(net->ev_bucket);
     if (net->ev_bucket_main) cudaEventDestroy(net->ev_bucket_main);
+    if (net->split_ss.main) cudaStreamDestroy(net->split_ss.main);
+    if (net->split_ss.side) cudaStreamDestroy(net->split_ss.side);
+    for (cudaEvent_t e : {net->split_ss.fork, net->split_ss.join, net->ev_split_fork, net->ev_split_join}) if (e) cudaEventDestroy(e);
     delete net;
 }
 
@@ -475,6 +484,15 @@ int ams_set_block_fusion(ams_net* h, int on) {
             if (kv.second->infer_graph[k]) { cudaGraphExecDestroy(kv.second->infer_graph[k]); kv.second->infer_graph[k] = nullptr; }
     return 0;
 }
+int ams_set_infer_split(ams_net* h, int on) {
+    NET(h);
+    AMS_CUDA_CHECK(cudaStreamSynchronize(net->stream));
+    net->infer_split = on != 0;
+    for (auto& kv : net->plans)
+        for (int k = 0; k < 2; ++k)
+            if (kv.second->infer_graph[k]) { cudaGraphExecDestroy(kv.second->infer_graph[k]); kv.second->infer_graph[k] = nullptr; }
+    return 0;
+}
 int ams_queue_size(ams_net* h) {
     NET(h);
     std::unique_lock<std::mutex> lk(net->qmu);
@@ -498,17 +516,47 @@ int ams_queue_clear(ams_net* h) {
 static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels, int64_t* out_cm, float* out_loss) {
     Plan* p = nullptr;
     if (net_dequeue(net, &p, false)) return -1;
-    HeadGeom hg = net->head; hg.N = p->N;
     HeadStats hs;
-    auto body = [&]() -> int {
-        if (net_forward(net, p, bn_mode, false)) return -1;
-        if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
-        cudaStream_t s = net->stream;
-        const double px_ = static_cast<double>(p->N) * net->cfg.height * net->cfg.width;
-        net->prof.begin(s, "head_infer", px_ * (metric ? 5.0 : 4.0) + 4.0 * p->N * hg.h * hg.w * 32);
-        const int rc = head_infer(p->logits, hg, metric ? p->in_labels : nullptr, p->pred, net->head_st, s);
+    // Frozen inference of an even batch >= 4 runs as two half batches on two streams (one graph): the layers at 1/16
+    // resolution launch fewer CTAs than the GPU has SMs and every layer ends in a tail wave, so two independent chains
+    // fill each other's gaps.  Frames are independent in moving-statistics mode and the metric accumulators are integer
+    // atomics, so the result is bit-identical to the unsplit run.
+    const bool split = net->infer_split && bn_mode == AMS_BN_MOVING && !net->prof.enabled && p->N >= 4 && (p->N & 1) == 0 &&
+                       !(net->block_fusion);
+    Plan *ha = nullptr, *hb = nullptr;
+    if (split) {
+        if (net_half_plans(net, p, &ha, &hb)) return -1;
+        const size_t el = p->in_dtype == AMS_FRAMES_U8 ? 1 : 4;
+        const size_t half_bytes = static_cast<size_t>(ha->N) * net->cfg.height * net->cfg.width * 3 * el;
+        ha->in_frames = p->in_frames; hb->in_frames = static_cast<char*>(p->in_frames) + half_bytes;
+        ha->in_dtype = hb->in_dtype = p->in_dtype;
+    }
+    auto head = [&](Plan* q, cudaStream_t s) -> int {
+        HeadGeom g = net->head; g.N = q->N;
+        const double px_ = static_cast<double>(q->N) * net->cfg.height * net->cfg.width;
+        net->prof.begin(s, "head_infer", px_ * (metric ? 5.0 : 4.0) + 4.0 * q->N * g.h * g.w * 32);
+        const int rc = head_infer(q->logits, g, metric ? q->in_labels : nullptr, q->pred, net->head_st, s);
         net->prof.end(s);
         return rc ? -1 : 0;
+    };
+    auto body = [&]() -> int {
+        if (!split) {
+            if (net_forward(net, p, bn_mode, false)) return -1;
+            if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
+            return head(p, net->stream);
+        }
+        if (net_prepare_weights(net, true)) return -1;
+        if (metric) { if (head_reset(net->head_st, net->stream)) return -1; }
+        AMS_CUDA_CHECK(cudaEventRecord(net->ev_split_fork, net->stream));
+        AMS_CUDA_CHECK(cudaStreamWaitEvent(net->split_ss.main, net->ev_split_fork, 0));
+        if (net_forward(net, ha, bn_mode, false)) return -1;
+        if (head(ha, net->stream)) return -1;
+        if (net_forward(net, hb, bn_mode, false, &net->split_ss)) return -1;
+        if (head(hb, net->split_ss.main)) return -1;
+        AMS_CUDA_CHECK(cudaEventRecord(net->ev_split_join, net->split_ss.main));
+        AMS_CUDA_CHECK(cudaStreamWaitEvent(net->stream, net->ev_split_join, 0));
+        p->last_was_train = false;
+        return 0;
     };
     // frozen client inference: the ~60 launches of forward + head are captured once per plan and replayed
     static const bool no_graph = [] { const char* e = getenv("AMS_NO_GRAPH"); return e && e[0] == '1'; }();

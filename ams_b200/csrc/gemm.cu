@@ -815,7 +815,7 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     // v2 runs two CTAs per SM (more epilogue warps in flight): each gets <= 256 TMEM columns and <= ~110 KB smem
     plan->acc_stages = (!plan->v2 || 2 * plan->block_n <= 256) ? 2 : 1;
     plan->tmem_cols = tmem_cols_for(plan->acc_stages * plan->block_n);
-    AMS_REQUIRE(plan->tmem_cols <= (plan->v2 ? 256u : 512u), "TMEM overflow");
+    AMS_REQUIRE(plan->tmem_cols <= (plan->v2 ? 256u : 512), "TMEM overflow");
     // small-K layers: a TMA box as wide as the row (32/64-byte swizzle) instead of a mostly out-of-bounds 128-byte box;
     // a narrower k-block is also the way out when two stages of the widest box do not fit (split weights on N = 256)
     int block_k = (plan->v2 && d.K <= 16) ? 16 : ((plan->v2 && d.K <= 32) ? 32 : BLOCK_K);
@@ -850,7 +850,7 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
     if (plan->v2 && plan->acc_stages == 1 && plan->smem_bytes > 113 * 1024) {
         plan->acc_stages = 2;
         plan->tmem_cols = tmem_cols_for(2 * plan->block_n);
-        AMS_REQUIRE(plan->tmem_cols <= 512u, "TMEM overflow");
+        AMS_REQUIRE(plan->tmem_cols <= 512, "TMEM overflow");
     }
     const int tiles = plan->m_tiles * plan->n_tiles;
     plan->grid = std::min(tiles, (plan->v2 && plan->smem_bytes <= 113 * 1024) ? 2 * num_sms : num_sms);

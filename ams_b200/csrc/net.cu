@@ -222,6 +222,19 @@ Plan* net_get_plan(Net* net, int N, bool need_backward) {
     return it->second.get();
 }
 
+int net_half_plans(Net* net, Plan* p, Plan** a, Plan** b) {
+    if (p->N < 2 || (p->N & 1)) { set_last_error("split inference needs an even batch"); return -1; }
+    for (int k = 0; k < 2; ++k) {
+        if (p->half[k]) continue;
+        std::unique_ptr<Plan> h(new Plan());
+        h->N = p->N / 2; h->parent = p; h->part = k;
+        if (build_plan(net, h.get(), false)) return -1;
+        p->half[k] = std::move(h);
+    }
+    *a = p->half[0].get(); *b = p->half[1].get();
+    return 0;
+}
+
 static int build_plan(Net* net, Plan* p, bool need_backward) {
     const auto& L = net->layers;
     const int N = p->N;
@@ -243,9 +256,18 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
         }
         if (dev_alloc(&p->coef[0], 3 * 1024, &p->allocations)) return -1;
         if (dev_alloc(&p->coef[1], 3 * 1024, &p->allocations)) return -1;
-        if (dev_alloc(reinterpret_cast<float**>(&p->in_frames), static_cast<size_t>(N) * c.height * c.width * 3, &p->allocations)) return -1;
-        if (dev_alloc(&p->in_labels, static_cast<size_t>(N) * c.height * c.width, &p->allocations)) return -1;
-        if (dev_alloc(&p->pred, static_cast<size_t>(N) * c.height * c.width, &p->allocations)) return -1;
+        // a half-batch view (p->parent) shares the parent's per-image buffers at image offset part * N
+        const Plan* par = p->parent;
+        const size_t img0 = par ? static_cast<size_t>(p->part) * N : 0;
+        const size_t px_img = static_cast<size_t>(c.height) * c.width;
+        if (par) {
+            p->in_labels = par->in_labels + img0 * px_img;
+            p->pred = par->pred + img0 * px_img;            // in_frames depends on the frame dtype: set per call (infer_common)
+        } else {
+            if (dev_alloc(reinterpret_cast<float**>(&p->in_frames), static_cast<size_t>(N) * px_img * 3, &p->allocations)) return -1;
+            if (dev_alloc(&p->in_labels, static_cast<size_t>(N) * px_img, &p->allocations)) return -1;
+            if (dev_alloc(&p->pred, static_cast<size_t>(N) * px_img, &p->allocations)) return -1;
+        }
         if (dev_alloc(&p->loss_dev, 4, &p->allocations)) return -1;
         size_t bn_ws = 0;
         for (size_t i = 0; i < L.size(); ++i) {
@@ -253,12 +275,18 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             if (d.kind == kImagePool) continue;
             const long long M = static_cast<long long>(N) * d.out_h * d.out_w;
             if (d.kind == kLogits) {
+                if (par) { p->logits = par->logits + static_cast<size_t>(M) * p->part * 32; continue; }
                 if (dev_alloc(&p->logits, static_cast<size_t>(M) * 32, &p->allocations)) return -1;
                 AMS_CUDA_CHECK(cudaMemset(p->logits, 0, static_cast<size_t>(M) * 32 * sizeof(float)));
                 continue;
             }
-            if (dev_alloc(&p->buf[i].y, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
-            if (dev_alloc(&p->buf[i].z, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
+            if (par) {
+                p->buf[i].y = par->buf[i].y + static_cast<size_t>(M) * p->part * d.cout;
+                p->buf[i].z = par->buf[i].z + static_cast<size_t>(M) * p->part * d.cout;
+            } else {
+                if (dev_alloc(&p->buf[i].y, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
+                if (dev_alloc(&p->buf[i].z, static_cast<size_t>(M) * d.cout, &p->allocations)) return -1;
+            }
             bn_ws = std::max(bn_ws, bn_workspace_doubles(M, d.cout));
             if (d.kind == kDepthwise) {
                 Conv2dGeom g{N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
@@ -430,11 +458,13 @@ static ImgPoolFwd imgpool_desc(Net* net, Plan* p, bool frozen, bool update_movin
     return a;
 }
 
-int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
+int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving, const StreamSet* ss) {
     const auto& L = net->layers;
     const ams_config& c = net->cfg;
     const bool frozen = (bn_mode == AMS_BN_MOVING);
-    cudaStream_t s = net->stream;
+    cudaStream_t s = ss ? ss->main : net->stream;
+    cudaStream_t side_stream = ss ? ss->side : net->side_stream;
+    cudaEvent_t ev_fork = ss ? ss->fork : net->ev_fork, ev_join = ss ? ss->join : net->ev_join;
     if (net_prepare_weights(net, frozen)) return -1;
     bool pool_pending = false;
     for (size_t i = 0; i < L.size(); ++i) {
@@ -445,11 +475,11 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
         const double out_bytes = 2.0 * M * d.cout;
         if (d.kind == kImagePool) {
             // six tiny latency-bound kernels: off the chain (side stream) while aspp0 runs; joined before concat_projection
-            if (!net->prof.enabled && net->side_stream) {
-                AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
-                AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
-                if (imgpool_forward(imgpool_desc(net, p, frozen, update_moving), net->side_stream)) return -1;
-                AMS_CUDA_CHECK(cudaEventRecord(net->ev_join, net->side_stream));
+            if (!net->prof.enabled && side_stream) {
+                AMS_CUDA_CHECK(cudaEventRecord(ev_fork, s));
+                AMS_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+                if (imgpool_forward(imgpool_desc(net, p, frozen, update_moving), side_stream)) return -1;
+                AMS_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
                 pool_pending = true;
             } else {
                 PROF("imgpool_fwd", 2.0 * p->N * L[d.input].out_h * L[d.input].out_w * d.cin, imgpool_forward(imgpool_desc(net, p, frozen, update_moving), s));
@@ -466,7 +496,7 @@ int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving) {
             continue;
         }
         if (pool_pending && d.name == "concat_projection") {
-            AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_join, 0));
+            AMS_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
             pool_pending = false;
         }
         if (d.kind == kLogits) {

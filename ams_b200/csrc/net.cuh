@@ -87,7 +87,14 @@ struct Plan {
     long long infer_graph_kernels[2] = {0, 0};                   // > 0: bn_ws holds the fused kernel's column sums for the next layer
     bool have_backward = false;
     bool last_was_train = false;
+    // split frozen inference (net_half_plans): two half-batch VIEWS of this plan -- same activation / logits / prediction
+    // buffers at an image offset, own GEMM tensor maps and small scratch -- run on two streams inside one graph
+    Plan* parent = nullptr; int part = 0;
+    std::unique_ptr<Plan> half[2];
 };
+
+// The streams and events one forward pass is enqueued on (default: the handle's main + side stream).
+struct StreamSet { cudaStream_t main = nullptr, side = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
 
 // Per-launch-group device timing (CUDA events on the launching stream), aggregated by tag.  Off by default.
 struct ProfEntry { std::string tag; double algo_bytes = 0; cudaEvent_t e0 = nullptr, e1 = nullptr; };
@@ -146,6 +153,8 @@ struct Net {
     bool sync_active = false;           // true only while a TRAINING step is being enqueued (inference never exchanges)
     uint8_t* pack_bits = nullptr; __half* pack_vals = nullptr; unsigned int* pack_counts = nullptr; unsigned long long* pack_kept = nullptr;
     bool weights_dirty = true, fold_dirty = true;
+    // frozen inference of a batch >= 4 as two concurrent half batches (ams_set_infer_split): the second half's stream set
+    bool infer_split = true; StreamSet split_ss{}; cudaEvent_t ev_split_fork = nullptr, ev_split_join = nullptr;
     bool block_fusion = false;         // frozen inference: stride-1 inverted-residual blocks as one kernel each (ams_set_block_fusion)
     std::vector<float*> fused_params;  // per expand layer: [13][cpad] padded per-channel vectors of the fused kernel (or null)
     bool frozen = false;               // built by ams_create_frozen: inference only ("Can't train frozen graph", SemanticNetwork.py:217)
@@ -163,7 +172,9 @@ struct Net {
 int net_build_topology(Net* net);
 Plan* net_get_plan(Net* net, int N, bool need_backward);
 int net_prepare_weights(Net* net, bool frozen);
-int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving);
+int net_forward(Net* net, Plan* p, int bn_mode, bool update_moving, const StreamSet* ss = nullptr);
+// the two half-batch views of an even-sized plan (built on first use); null on failure
+int net_half_plans(Net* net, Plan* p, Plan** a, Plan** b);
 int net_backward(Net* net, Plan* p, bool normalize);
 // forward (batch statistics, moving-average update) + backward of one distillation step: eager the first time on a plan,
 // then a CUDA graph replay (~450 launches, two streams) unless profiling or AMS_NO_GRAPH=1

@@ -180,6 +180,10 @@ class Student:
         """frozen inference: one kernel per stride-1 inverted-residual block (default) or one kernel per layer"""
         nat.check(self._L.ams_set_block_fusion(self._h, 1 if on else 0), 'set_block_fusion')
 
+    def set_infer_split(self, on):
+        """frozen inference of an even batch >= 4 as two concurrent half batches (default on; bit-identical results)"""
+        nat.check(self._L.ams_set_infer_split(self._h, 1 if on else 0), 'set_infer_split')
+
     def queue_size(self):
         return self._L.ams_queue_size(self._h)
 

@@ -187,6 +187,13 @@ int ams_syncbn_status(ams_net* net, unsigned int* out_epoch, unsigned int* out_e
  * per-layer schedule (DESIGN.md 4 has the timeline and the diagnosis). */
 int ams_set_block_fusion(ams_net* net, int on);
 
+/* Frozen inference (AMS_BN_MOVING) of an even batch of >= 4 frames runs as two half batches on two streams inside one
+ * CUDA graph: the 1/16-resolution layers launch fewer CTAs than there are SMs and every layer ends in a partial wave,
+ * so two independent chains fill each other's gaps.  The half-batch plans are views of the full plan's buffers, so
+ * ams_get_logits / ams_get_activation see the same data; predictions, confusion matrix and loss are bit-identical to
+ * the unsplit run (tests/test_net_gpu.py).  Default ON (env AMS_NO_INFER_SPLIT=1: off). */
+int ams_set_infer_split(ams_net* net, int on);
+
 /* ---- teacher network (config C5): DeepLabv3+ / Xception-65, inference only -- the network behind
  * `sess.run(teacher['predictions'], feed_dict={teacher['images']: frame})` of extract_labels.py:84 (graph imported by
  * create_teacher, utils/graph_utils.py:129-152).  The teacher's .meta and weights are not in the reference repository;

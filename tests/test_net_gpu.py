@@ -382,6 +382,37 @@ def test_block_fused_frozen_inference_matches_layer_by_layer(tag, n, h, w):
     assert rel < 3e-3 and agree > 0.995 and worst < 2e-2
 
 
+@pytest.mark.parametrize('tag,n,h,w,u8', [('cityscapes', 4, 64, 128, True), ('cityscapes', 8, 96, 192, False), ('pascalvoc2012', 6, 64, 128, True)])
+def test_split_frozen_inference_is_bit_identical_to_unsplit(tag, n, h, w, u8):
+    """Frozen inference of an even batch >= 4 as two half batches on two streams inside one graph (ams_set_infer_split,
+    default on) against the single-chain schedule on the same handle: logits, predictions, confusion matrix and loss are
+    bit-identical, eager run == graph capture == replay, and an odd batch silently takes the single chain."""
+    spec, V, fr = make_checkpoint(tag, 1, n, h, w)
+    st = load_student(spec, V, None, h, w)
+    frames = fr if u8 else fr.astype(np.float32)
+    lab = so.synthetic_labels(n, h, w, seed=2, block=16) % spec['num_classes']
+    outs = {}
+    for split in (False, True, True, True, False):
+        st.set_infer_split(split)
+        st.enqueue(frames, lab)
+        pred, cm, loss = st.infer_metric(n, nat.BN_MOVING)
+        got = (st.get_logits(n).copy(), pred.copy(), cm.copy(), np.float32(loss))
+        key = 'split' if split else 'plain'
+        if key in outs:
+            assert all(np.array_equal(a, b) for a, b in zip(outs[key], got)), key
+        outs[key] = got
+    for a, b in zip(outs['plain'], outs['split']):
+        assert np.array_equal(a, b)
+    st.set_infer_split(True)
+    for _ in range(3):                                # label-free entry point, graph keyed separately
+        st.enqueue(frames, None)
+        assert np.array_equal(st.infer(n, nat.BN_MOVING), outs['plain'][1])
+    st.enqueue(frames[:3], None)                      # odd batch: single chain
+    assert np.array_equal(st.infer(3, nat.BN_MOVING), outs['plain'][1][:3])
+    st.close()
+    log('split (2 x %d frames, two streams, one graph) == unsplit frozen inference, bit for bit [%s %dx%d]' % (n // 2, tag, h, w))
+
+
 def st_hw(st, layer_index, h, w):
     """output size of a layer: stem and the stride-2 depthwise convs halve (ceil) the padded size"""
     hh, ww = h + 1, w + 1
