@@ -447,20 +447,39 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
     const uint32_t w_mine = w_smem + l4 * kCh * 4;
     int r = (pt * p.mg_s) >> 16, s = pt - r * p.nstrips;
     const int step_r = p.cs_r, step_s = p.cs_s;
-    for (; r < p.th; r += step_r, s += step_s) {
-        if (s >= p.nstrips) { s -= p.nstrips; ++r; if (r >= p.th) break; }
+    // The producer's raw output at the strip's 4 pixels comes through a two-deep per-thread cp.async ring: the loads of
+    // strip i+1 are in flight while strip i is computed (no registers held, no exposed global-memory latency).
+    const uint32_t zring = tile_smem + static_cast<uint32_t>(p.oh) * row_bytes + threadIdx.x * 8;     // [2][kStrip][THREADS] x 8 bytes
+    auto strip_ok = [&](int rr, int ss) { return rr < p.th && iy0 + rr < p.H && ss < p.nstrips; };
+    auto prefetch = [&](int rr, int ss, int stage) {
+        const int lx0 = ss * kStrip;
+        const act_t* zrow = p.zin + ((static_cast<long long>(n) * p.H + iy0 + rr) * p.W + ix0 + lx0) * p.C + c0;
+#pragma unroll
+        for (int a = 0; a < kStrip; ++a) {
+            if ((lx0 + a < p.twt) && (ix0 + lx0 + a < p.W))
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(zring + (stage * kStrip + a) * (THREADS * 8)),
+                             "l"(zrow + static_cast<long long>(a) * p.C) : "memory");
+        }
+    };
+    if (strip_ok(r, s)) prefetch(r, s, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int stage = 0; strip_ok(r, s); stage ^= 1) {
+        int rn = r + step_r, sn = s + step_s;
+        if (sn >= p.nstrips) { sn -= p.nstrips; ++rn; }
+        if (strip_ok(rn, sn)) prefetch(rn, sn, stage ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         const int iy = iy0 + r;
-        if (iy >= p.H) continue;
         const int lx0 = s * kStrip;
-        // the producer's output at the strip's 4 pixels -> x (activated, bf16-rounded) and the activation mask
-        const act_t* zrow = p.zin + ((static_cast<long long>(n) * p.H + iy) * p.W + ix0 + lx0) * p.C + c0;
+        const int s_cur = s;
+        r = rn; s = sn;
         uint2 zraw[kStrip];
         bool pvalid[kStrip];
 #pragma unroll
         for (int a = 0; a < kStrip; ++a) {
             pvalid[a] = (lx0 + a < p.twt) && (ix0 + lx0 + a < p.W);
             zraw[a] = make_uint2(0u, 0u);
-            if (pvalid[a]) zraw[a] = *reinterpret_cast<const uint2*>(zrow + static_cast<long long>(a) * p.C);
+            if (pvalid[a]) zraw[a] = lds64(zring + (stage * kStrip + a) * (THREADS * 8));
         }
         float2 x[kStrip][2];
         uint32_t mask = 0;                                  // bit a*4+q: gradient passes at pixel a, channel q
@@ -486,7 +505,7 @@ dw_bwd_fused_kernel(const DwBwdParams p) {
         float2 gx[kStrip][2];
 #pragma unroll
         for (int a = 0; a < kStrip; ++a) gx[a][0] = gx[a][1] = make_float2(0.f, 0.f);
-        const uint32_t strip_base = tile_smem + (s * Cols::STRIP_COLS * CB + l4 * kCh) * 2;
+        const uint32_t strip_base = tile_smem + (s_cur * Cols::STRIP_COLS * CB + l4 * kCh) * 2;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int ay = iy + p.pad_top - ky * D;
@@ -602,7 +621,7 @@ DwBwdTile pick_bwd_tile(const Conv2dGeom& g, size_t smem_cap) {
             const int nstrips = ceil_div(twt, kStrip);
             const int oh = S == 1 ? th + 2 * D : th / 2 + 1;
             const int owp = S == 1 ? nstrips * kStrip + 2 * D : nstrips * 2 + 1;
-            size_t smem = fixed + static_cast<size_t>(oh) * owp * cb * 2;
+            size_t smem = fixed + static_cast<size_t>(oh) * owp * cb * 2 + 2 * kStrip * dw_threads(cb) * 8;      // + the cp.async ring
             if (smem > smem_cap) continue;
             smem = std::max(smem, static_cast<size_t>(npt) * 11 * cb * sizeof(float));
             const int iters = ceil_div(th * nstrips, npt);
@@ -620,7 +639,7 @@ DwBwdTile pick_bwd_tile(const Conv2dGeom& g, size_t smem_cap) {
     return best;
 }
 
-static const size_t kBwdSmemCap = env_kb("AMS_DWB_SMEM_KB", 100);
+static const size_t kBwdSmemCap = env_kb("AMS_DWB_SMEM_KB", 112);
 
 template <int S, int D, int CB, int PADX>
 int launch_bwd(const DwBwdParams& p, const DwBwdTile& t, cudaStream_t s) {

@@ -150,24 +150,20 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 t5::mbar_wait(&full_bar[stage], phase);
                 t5::fence_after_thread_sync();
-                if (lane == 0) {
-                    const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
-                    const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
+                {
+                    // whole converged warp, one elected lane per instruction (see the v2 kernel); K-major SWIZZLE_128B: 8-row
+                    // groups 1024 B apart (SBO); +32 B (+2 in descriptor units) per UMMA_K step
+                    const uint64_t da0 = t5::make_smem_desc_sw128(t5::smem_u32(smA + stage * stage_a), 16, 1024);
+                    const uint64_t db0 = t5::make_smem_desc_sw128(t5::smem_u32(smB + stage * stage_b), 16, 1024);
+                    const uint64_t dl0 = db0 + (tile_b >> 4);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // K-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO); +32 B per UMMA_K step
-                        const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * UMMA_K * 2, 16, 1024);
-                        const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * UMMA_K * 2, 16, 1024);
-                        t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
-                        if (p.b_split) {
-                            const uint64_t dl = t5::make_smem_desc_sw128(b_addr + tile_b + k * UMMA_K * 2, 16, 1024);
-                            t5::mma_bf16_ss(tmem_d, da, dl, idesc, 1u);
-                        }
+                        t5::mma_f16_ss_warp(tmem_d, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                        if (p.b_split) t5::mma_f16_ss_warp(tmem_d, da0 + 2 * k, dl0 + 2 * k, idesc, 1u);
                     }
-                    t5::mma_commit(&empty_bar[stage]);                    // frees the smem slot when MMAs retire
-                    if (kb == p.k_blocks - 1) t5::mma_commit(&tfull_bar[as]);   // accumulator ready
+                    t5::mma_commit_warp(&empty_bar[stage]);                    // frees the smem slot when MMAs retire
+                    if (kb == p.k_blocks - 1) t5::mma_commit_warp(&tfull_bar[as]);   // accumulator ready
                 }
-                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -368,6 +364,9 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else if (warp == 1) {
         const uint32_t idesc = t5::make_idesc_f16(BLOCK_M, p.block_n, 0, 0, p.a_bf16, p.b_bf16);
         int stage = 0; uint32_t phase = 0; int it = 0;
+        // K-major swizzled rows of block_k*2 bytes (128/64/32-byte swizzle): 8-row groups SBO apart
+        const uint64_t desc_fixed = t5::make_smem_desc(0, 16, 16u * p.block_k, p.block_k == 64 ? 2u : (p.block_k == 32 ? 4u : 6u));
+        const int ksteps = p.block_k / UMMA_K;
         if (p.b_resident) t5::mbar_wait_relaxed(bres_bar, 0);
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int as = (p.acc_stages == 2) ? (it & 1) : 0;
@@ -378,25 +377,21 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int kb = 0; kb < p.k_blocks; ++kb) {
                 t5::mbar_wait_relaxed(&full_bar[stage], phase);
                 t5::fence_after_thread_sync();
-                if (lane == 0) {
-                    const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
-                    const uint32_t b_addr = t5::smem_u32(smB + (p.b_resident ? 0 : stage) * stage_b);
-                    // K-major swizzled rows of block_k*2 bytes (128/64/32-byte swizzle): 8-row groups SBO apart
-                    const uint32_t sbo = 16u * p.block_k, ltype = p.block_k == 64 ? 2u : (p.block_k == 32 ? 4u : 6u);
-                    for (int k = 0; k < p.block_k / UMMA_K; ++k) {
-                        const uint64_t da = t5::make_smem_desc(a_addr + k * UMMA_K * 2, 16, sbo, ltype);
-                        const uint64_t db = t5::make_smem_desc(b_addr + k * UMMA_K * 2, 16, sbo, ltype);
-                        t5::mma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0);
-                        if (p.b_split) {
-                            // low weight plane against the same A tile, accumulated into the same TMEM columns
-                            const uint64_t dl = t5::make_smem_desc(b_addr + tile_b + k * UMMA_K * 2, 16, sbo, ltype);
-                            t5::mma_bf16_ss(tmem_d, da, dl, idesc, 1u);
-                        }
+                {
+                    // Issued by the whole converged warp with warp-uniform operands, one elected lane per instruction, and
+                    // descriptors that differ only by an add in the address field (16-byte units: a UMMA_K step of 32 bytes is
+                    // +2).  Under `if (lane == 0)` with the descriptors rebuilt per instruction this warp needed 200-800 cycles
+                    // per tcgen05.mma while the epilogue warps of its scheduler were busy (tools/micro/mma_contention.cu).
+                    const uint64_t da0 = desc_fixed | ((t5::smem_u32(smA + stage * stage_a) & 0x3FFFFu) >> 4);
+                    const uint64_t db0 = desc_fixed | ((t5::smem_u32(smB + (p.b_resident ? 0 : stage) * stage_b) & 0x3FFFFu) >> 4);
+                    const uint64_t dl0 = db0 + (tile_b >> 4);         // low weight plane: same tile shape, tile_b bytes further
+                    for (int k = 0; k < ksteps; ++k) {
+                        t5::mma_f16_ss_warp(tmem_d, da0 + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                        if (p.b_split) t5::mma_f16_ss_warp(tmem_d, da0 + 2 * k, dl0 + 2 * k, idesc, 1u);
                     }
-                    t5::mma_commit(&empty_bar[stage]);
-                    if (kb == p.k_blocks - 1) t5::mma_commit(&tfull_bar[as]);
+                    t5::mma_commit_warp(&empty_bar[stage]);
+                    if (kb == p.k_blocks - 1) t5::mma_commit_warp(&tfull_bar[as]);
                 }
-                __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -667,21 +662,18 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int i = 0; i < nkb; ++i) {
             t5::mbar_wait(p.convert_x ? &conv_bar[stage] : &full_bar[stage], phase);
             t5::fence_after_thread_sync();
-            if (lane == 0) {
-                const uint32_t a_addr = t5::smem_u32(smA + stage * stage_a);
-                const uint32_t b_addr = t5::smem_u32(smB + stage * stage_b);
+            {
+                // whole converged warp, one elected lane per instruction (see gemm_bn_act_kernel_v2).  MN-major SWIZZLE_128B:
+                // 64-channel atoms one TMA box apart (LBO), 8-pixel groups 1024 B apart (SBO); a UMMA_K = 16 step advances two
+                // pixel groups = 2048 B (+128 in the 16-byte units of the descriptor's address field).
+                const uint64_t da0 = t5::make_smem_desc_sw128(t5::smem_u32(smA + stage * stage_a), kWgradBoxBytes, 1024);
+                const uint64_t db0 = t5::make_smem_desc_sw128(t5::smem_u32(smB + stage * stage_b), kWgradBoxBytes, 1024);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    // MN-major SWIZZLE_128B: 64-channel atoms one TMA box apart (LBO), 8-pixel groups
-                    // 1024 B apart (SBO); a UMMA_K=16 step advances two pixel groups = 2048 B.
-                    const uint64_t da = t5::make_smem_desc_sw128(a_addr + k * 2048, kWgradBoxBytes, 1024);
-                    const uint64_t db = t5::make_smem_desc_sw128(b_addr + k * 2048, kWgradBoxBytes, 1024);
-                    t5::mma_bf16_ss(tmem_base, da, db, idesc, (i | k) != 0);
-                }
-                t5::mma_commit(&empty_bar[stage]);
-                if (i == nkb - 1) t5::mma_commit(done_bar);
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                    t5::mma_f16_ss_warp(tmem_base, da0 + 128 * k, db0 + 128 * k, idesc, (i | k) != 0);
+                t5::mma_commit_warp(&empty_bar[stage]);
+                if (i == nkb - 1) t5::mma_commit_warp(done_bar);
             }
-            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else {

@@ -97,6 +97,35 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / tcgen05.commit take their operands from uniform registers:
+// issued under a thread-dependent branch such as `if (lane == 0)` ptxas has to move every descriptor with R2UR and wraps
+// the instruction in a BRA.U.ANY loop (~200 cycles per MMA, measured with tools/micro/mma_rate.cu); issued by the whole
+// warp with warp-uniform operands and only the instruction itself under the elected predicate, it costs a few cycles.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred;
+}
+// whole-warp versions: every lane calls them with the same (warp-uniform) operands
+__device__ __forceinline__ void mma_f16_ss_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one_sync()) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+__device__ __forceinline__ void mma_commit_warp(uint64_t* bar) {
+    if (elect_one_sync()) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                     :: "r"(smem_u32(bar)) : "memory");
+    }
+}
 // Make the mbarrier track completion of all tcgen05 ops issued so far by this thread.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"

@@ -202,18 +202,15 @@ t_conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int tap = 0; tap < 9; ++tap) {
                 t5::mbar_wait_relaxed(&full_bar[stage], phase);
                 t5::fence_after_thread_sync();
-                if (lane == 0) {
-                    const uint32_t a_addr = t5::smem_u32(smA + stage * kATile), b_addr = t5::smem_u32(smB + tap * kBTile);
+                {
+                    // whole converged warp, one elected lane per instruction (see gemm.cu)
+                    const uint64_t da0 = t5::make_smem_desc(t5::smem_u32(smA + stage * kATile), 16, 512, 4);
+                    const uint64_t db0 = t5::make_smem_desc(t5::smem_u32(smB + tap * kBTile), 16, 512, 4);
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const uint64_t da = t5::make_smem_desc(a_addr + k * 32, 16, 512, 4);
-                        const uint64_t db = t5::make_smem_desc(b_addr + k * 32, 16, 512, 4);
-                        t5::mma_bf16_ss(tmem_d, da, db, idesc, (tap | k) != 0);
-                    }
-                    t5::mma_commit(&empty_bar[stage]);
-                    if (tap == 8) t5::mma_commit(&tfull_bar[as]);
+                    for (int k = 0; k < 2; ++k) t5::mma_f16_ss_warp(tmem_d, da0 + 2 * k, db0 + 2 * k, idesc, (tap | k) != 0);
+                    t5::mma_commit_warp(&empty_bar[stage]);
+                    if (tap == 8) t5::mma_commit_warp(&tfull_bar[as]);
                 }
-                __syncwarp();
                 if (++stage == kC3Stages) { stage = 0; phase ^= 1; }
             }
         }

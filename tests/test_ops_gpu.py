@@ -439,8 +439,8 @@ def test_adam_bit_exact():
     (2, 33, 65, 64, 64, 1, True, True),         # blocks 7-9: ragged tiles in both directions
     (1, 33, 65, 64, 96, 1, False, True),        # block 10
     (2, 17, 33, 96, 96, 1, True, True),         # blocks 11-12 (3 k-blocks, 9 chunks)
-    (1, 33, 65, 160, 160, 2, True, True),       # blocks 14-15: dilation 2, 32-channel chunks
-    (1, 20, 40, 160, 320, 2, False, False),     # block 16: two project N tiles, plain fp16 project weights
+    (1, 33, 65, 160, 160, 2, True, True),       # blocks 14-15: dilation 2 (20-wide halo rows, single TMEM stage)
+    (1, 33, 65, 96, 160, 1, False, True),       # block 13: single TMEM stage at dilation 1
     (1, 40, 70, 24, 24, 1, True, True),         # block 2: Cin 24 (zero-filled k-block), Cexp 144 (padded chunk), Cout 24 (N granule)
     (1, 30, 50, 32, 32, 1, True, True),         # blocks 4-5
 ])

@@ -29,12 +29,13 @@ tl = torch.zeros(3 * 64 * 4, dtype=torch.int64, device=dev)
 L.ams_debug_fused_timeline(P(tl)); run(); L.ams_debug_fused_timeline(None)
 t = tl.cpu().numpy().reshape(3, 64, 4)
 t0 = t[t > 0].min()
-nchunks = (cexp + (32 if cin > 96 else 64) - 1) // (32 if cin > 96 else 64)
-print('timeline of CTA 0 (us since its first event); MMA: expand issued, project issued | E: wait D1, start, done | W: wait halo, start, done')
+nchunks = (cexp + 127) // 128
+print('timeline of CTA 0 (us since its first event); MMA: expand first/last issue, project first/last issue | compute: wait D1, D1 ready, A2 free, done')
 for g in range(min(64, 2 * nchunks)):
     f = lambda v: '%7.2f' % ((v - t0) / 1e3) if v > 0 else '    -  '
-    print('chunk %2d  MMA %s %s | E %s %s %s | W %s %s %s' % (g, f(t[0, g, 0]), f(t[0, g, 1]), f(t[1, g, 0]), f(t[1, g, 1]), f(t[1, g, 2]),
-                                                             f(t[2, g, 0]), f(t[2, g, 1]), f(t[2, g, 2])))
+    print('chunk %2d  MMA expand %s %s project %s %s | compute %s %s %s %s | A2 full %s Wp unit1 %s unit3 %s; producer issued Wp %s' % (
+        g, f(t[0, g, 0]), f(t[0, g, 2]), f(t[0, g, 1]), f(t[0, g, 3]), f(t[1, g, 0]), f(t[1, g, 1]), f(t[1, g, 3]), f(t[1, g, 2]),
+        f(t[2, g, 0]), f(t[2, g, 1]), f(t[2, g, 2]), f(t[2, g, 3])))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); e0.record()
 for _ in range(reps):
