@@ -107,7 +107,7 @@ def test_depthwise_tile_planner_invariants(batch):
             assert all(((n * (65536 // dd + 1)) >> 16) == n // dd for n in range(256)), (dd,)
         assert lib.ams_debug_dw_bwd_tile(batch, h, w, c, ho, wo, s, d, out) == 0
         th, tw, ntx, nty, cb, smem, ctas, nstrips = list(out)
-        assert th * nty >= h and tw * ntx >= w and 0 < smem <= 100 * 1024 and c % cb == 0
+        assert th * nty >= h and tw * ntx >= w and 0 < smem <= 112 * 1024 and c % cb == 0      # two CTAs per SM, cp.async ring included
         if s == 2:
             assert th % 2 == 0 and tw % 2 == 0
         owp = nstrips * 4 + 2 * d if s == 1 else nstrips * 2 + 1
