@@ -159,10 +159,9 @@ ams_net* ams_create(const ams_config* cfg) {
     // block-fused frozen inference (fused_block.cu): padded per-channel parameter vectors of every eligible block
     net->fused_params.assign(net->layers.size(), nullptr);
     {
-        // OFF by default: bit-identical to the per-layer schedule but measured slower on B200 (the tensor pipe
-        // retires one small-N tcgen05.mma every ~150 cycles whatever its N, and a 64-channel chunk needs 16-24 of them)
+        // ON by default (env AMS_BLOCK_FUSION=0: one kernel per layer): same fp16 rounding points as the per-layer schedule
         const char* nf = getenv("AMS_BLOCK_FUSION");
-        net->block_fusion = (nf && nf[0] == '1');
+        net->block_fusion = !(nf && nf[0] == '0');
         for (size_t i = 0; i + 2 < net->layers.size(); ++i) {
             const LayerDef& e = net->layers[i]; const LayerDef& dw = net->layers[i + 1]; const LayerDef& pr = net->layers[i + 2];
             if (e.kind != kConv1x1 || dw.kind != kDepthwise || pr.kind != kConv1x1 || dw.input != static_cast<int>(i) ||
@@ -521,8 +520,7 @@ static int infer_common(Net* net, int bn_mode, bool metric, int32_t* out_labels,
     // resolution launch fewer CTAs than the GPU has SMs and every layer ends in a tail wave, so two independent chains
     // fill each other's gaps.  Frames are independent in moving-statistics mode and the metric accumulators are integer
     // atomics, so the result is bit-identical to the unsplit run.
-    const bool split = net->infer_split && bn_mode == AMS_BN_MOVING && !net->prof.enabled && p->N >= 4 && (p->N & 1) == 0 &&
-                       !(net->block_fusion);
+    const bool split = net->infer_split && bn_mode == AMS_BN_MOVING && !net->prof.enabled && p->N >= 4 && (p->N & 1) == 0;
     Plan *ha = nullptr, *hb = nullptr;
     if (split) {
         if (net_half_plans(net, p, &ha, &hb)) return -1;

@@ -40,8 +40,10 @@ namespace {
 constexpr int kTH = 8, kTW = 16;              // output tile: 128 pixels = one UMMA M tile of the project GEMM
 constexpr int kKB = 32;                       // k-block of every operand ring: 32 channels = 64-byte swizzled rows
 constexpr int kChunk = 128;                   // expanded channels per chunk = UMMA M of the expand GEMM = TMEM lanes
-constexpr int kThreads = 320;                 // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..9 compute
-constexpr int kCompute = 256;
+constexpr int kThreads = 512;                 // four warpgroups: {TMA producer, MMA issuer + TMEM owner, 2 spare}, 2 x compute, epilogue
+constexpr int kCompute = 256;                 // warps 4..11: TMEM lane quarter x upper/lower half of the tile rows
+constexpr int kEpilogue = 128;                // warps 12..15: one TMEM lane quarter (32 output pixels) each
+constexpr int kRegsLight = 64, kRegsEpilogue = 80, kRegsCompute = 176;     // setmaxnreg: 128*(64+80) + 256*176 <= 64K registers
 constexpr int kMaxWe = 8, kMaxWp = 8;         // ring slots
 constexpr uint32_t kSpinLimit = 1u << 28;     // a barrier that never completes traps instead of hanging the GPU
 
@@ -86,6 +88,10 @@ __device__ __forceinline__ void wait_bar_relaxed(uint64_t* bar, uint32_t parity)
     uint32_t spins = 0;
     while (!t5::mbar_try_wait(bar, parity)) { __nanosleep(32); if (++spins > (kSpinLimit >> 4)) __trap(); }
 }
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {          // d += a * b (per lane), packed fp32x2
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+}
 __device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -125,8 +131,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (threadIdx.x == 0) {
         t5::tma_prefetch_desc(&tmX); t5::tma_prefetch_desc(&tmWe); t5::tma_prefetch_desc(&tmWp);
         for (int b = 0; b < B_COUNT; ++b) {
-            const bool by_compute = (b >= B_D1EMPTY && b < B_D1EMPTY + 2) || (b >= B_A2FULL && b < B_A2FULL + 2) || b == B_D2EMPTY;
-            t5::mbar_init(&bars[b], by_compute ? kCompute : 1);
+            const bool by_compute = (b >= B_D1EMPTY && b < B_D1EMPTY + 2) || (b >= B_A2FULL && b < B_A2FULL + 2);
+            t5::mbar_init(&bars[b], by_compute ? kCompute : (b == B_D2EMPTY ? kEpilogue : 1));
         }
         t5::fence_barrier_init();
     }
@@ -143,6 +149,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int my_tiles = (p.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
     const int G = my_tiles * p.n_chunks;
 
+    // register budget per warpgroup (setmaxnreg at the top of each role's branch, so that ptxas allocates the branch against
+    // it): the compute threads hold a (2d+1) x (16+2d) fp32 window + 16 accumulators
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsLight));
     if (warp == 0) {
         // ================================================================== TMA producer: loads in the order the MMA issuer consumes them
         if (lane == 0) {
@@ -261,10 +271,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (++a == p.a2_bufs) { a = 0; ++a2_pass; }
             if (++j == p.n_chunks) { j = 0; ++tl; }
         }
-    } else {
+    }
+    } else if (warp < 12) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(kRegsCompute));
         // ================================================================== 256 compute threads: thread = one expanded channel x half of the tile rows
         const int q = warp & 3;                            // TMEM lane quarter of this warp
-        const int hh = (warp - 2) >> 2;                    // 0: output rows 0..3, 1: rows 4..7
+        const int hh = (warp - 4) >> 2;                    // 0: output rows 0..3, 1: rows 4..7
         const int ch = q * 32 + lane;                      // channel within the chunk = TMEM lane = K row of A2
         const uint32_t a2_s = t5::smem_u32(smA2);
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -284,39 +296,48 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 9; ++k) wd[k] = __ldg(pp + (2 + k) * kChunk);
                 const float s2 = __ldg(pp + 11 * kChunk), t2 = __ldg(pp + 12 * kChunk);
-                if (threadIdx.x == 64) dbg_mark(p, 1, g, 0);
+                if (threadIdx.x == 128) dbg_mark(p, 1, g, 0);
                 wait_bar(&bars[B_D1FULL + b], d1_pass & 1);
                 t5::fence_after_thread_sync();
-                if (threadIdx.x == 64) dbg_mark(p, 1, g, 1);
+                if (threadIdx.x == 128) dbg_mark(p, 1, g, 1);
                 if (a2_pass > 0) wait_bar(&bars[B_A2EMPTY + a], (a2_pass - 1) & 1);     // project GEMM of chunk g - a2_bufs retired
-                if (threadIdx.x == 64) dbg_mark(p, 1, g, 3);
+                if (threadIdx.x == 128) dbg_mark(p, 1, g, 3);
                 const uint32_t taddr = tmem_base + lane_addr + b * p.n1 + (hh * ROWS) * HW;
                 // K row `ch` of both 64-pixel atoms; 16-byte chunk index XOR (ch mod 8)
                 const uint32_t a2_row = a2_s + a * (2 * 16384) + ch * 128;
-                float win[WIN][HW];
+                // window rows as aligned fp32 pairs (columns 2i, 2i+1): taps with an even column offset (all of them at
+                // dilation 2; kx = 0, 2 at dilation 1) run as packed fp32x2 FMAs on two adjacent output pixels
+                float2 win[WIN][HW / 2];
                 uint32_t raw[HW];
+                const float2 s1p = make_float2(s1, s1), t1p = make_float2(t1, t1), s2p = make_float2(s2, s2), t2p = make_float2(t2, t2);
+                float2 wp2[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) wp2[k] = make_float2(wd[k], wd[k]);
                 t5::tmem_ld16(taddr, raw);
                 if (D == 1) tmem_ld2(taddr + 16, raw + 16); else tmem_ld4(taddr + 16, raw + 16);
 #pragma unroll
                 for (int hr = 0; hr < HR; ++hr) {
                     t5::tmem_ld_wait();
                     const int gy = y0 - D + hh * ROWS + hr;
-                    const bool row_ok = gy >= 0 && gy < p.H;
-                    float* wr = win[hr % WIN];
+                    float2* wr = win[hr % WIN];
+                    if (gy >= 0 && gy < p.H) {
 #pragma unroll
-                    for (int c = 0; c < HW; c += 2) {
-                        const float v0 = fminf(fmaxf(fmaf(__uint_as_float(raw[c]), s1, t1), 0.f), 6.f);
-                        const float v1 = fminf(fmaxf(fmaf(__uint_as_float(raw[c + 1]), s1, t1), 0.f), 6.f);
-                        const float2 f = h16x2(pack_h16(v0, v1));                      // the value the unfused path stores (fp16)
-                        wr[c] = row_ok ? f.x : 0.f; wr[c + 1] = row_ok ? f.y : 0.f;
-                    }
-                    if (x0 == 0) {
+                        for (int i = 0; i < HW / 2; ++i) {
+                            float2 v = t1p;
+                            ffma2(v, make_float2(__uint_as_float(raw[2 * i]), __uint_as_float(raw[2 * i + 1])), s1p);
+                            v.x = fminf(fmaxf(v.x, 0.f), 6.f); v.y = fminf(fmaxf(v.y, 0.f), 6.f);
+                            wr[i] = h16x2(pack_h16(v.x, v.y));                          // the value the unfused path stores (fp16)
+                        }
+                        if (x0 == 0) {                                                  // columns left of the image
+                            if (D == 1) wr[0].x = 0.f; else wr[0] = make_float2(0.f, 0.f);
+                        }
+                        if (col_hi < HW) {                                              // columns right of the image (last tile column only)
 #pragma unroll
-                        for (int c = 0; c < D; ++c) wr[c] = 0.f;
-                    }
-                    if (col_hi < HW) {
+                            for (int i = 0; i < HW / 2; ++i) { if (2 * i >= col_hi) wr[i].x = 0.f; if (2 * i + 1 >= col_hi) wr[i].y = 0.f; }
+                        }
+                    } else {                                                            // row above / below the image: the depthwise conv's zero padding
 #pragma unroll
-                        for (int c = 0; c < HW; ++c) if (c >= col_hi) wr[c] = 0.f;
+                        for (int i = 0; i < HW / 2; ++i) wr[i] = make_float2(0.f, 0.f);
                     }
                     if (hr + 1 < HR) {                                                  // next halo row: in flight during the FMAs below
                         t5::tmem_ld16(taddr + (hr + 1) * HW, raw);
@@ -327,26 +348,35 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     }
                     if (hr >= 2 * D && (p.x_skip & 1) == 0) {
                         const int orow = hr - 2 * D;                                    // output row within this warp's half
-                        float acc[kTW];
+                        float2 acc[kTW / 2];
 #pragma unroll
-                        for (int c = 0; c < kTW; ++c) acc[c] = 0.f;
+                        for (int i = 0; i < kTW / 2; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int ky = 0; ky < 3; ++ky) {
-                            const float* xr = win[(orow + ky * D) % WIN];
+                            const float2* xr = win[(orow + ky * D) % WIN];
 #pragma unroll
                             for (int kx = 0; kx < 3; ++kx) {
+                                const int o = kx * D;
+                                if ((o & 1) == 0) {
 #pragma unroll
-                                for (int c = 0; c < kTW; ++c) acc[c] = fmaf(xr[c + kx * D], wd[ky * 3 + kx], acc[c]);
+                                    for (int i = 0; i < kTW / 2; ++i) ffma2(acc[i], xr[i + o / 2], wp2[ky * 3 + kx]);
+                                } else {                                                // odd offset: (x[2i+o], x[2i+o+1]) straddles two pairs
+                                    const float w = wd[ky * 3 + kx];
+#pragma unroll
+                                    for (int i = 0; i < kTW / 2; ++i) {
+                                        acc[i].x = fmaf(xr[i + (o - 1) / 2].y, w, acc[i].x);
+                                        acc[i].y = fmaf(xr[i + (o + 1) / 2].x, w, acc[i].y);
+                                    }
+                                }
                             }
-                            // Two of these FFMA-bound warps share a scheduler with the MMA-issuing (or the TMA) warp, and the
-                            // scheduler keeps issuing from a warp that is always ready: measured (tools/micro/mma_contention.cu)
-                            // 219 cycles per tcgen05.mma issue instead of 49.  A zero-length sleep every 48 FMAs hands the
-                            // slot over (87 cycles) for ~2 % more instructions here.
-                            asm volatile("nanosleep.u32 0;");
                         }
                         float o[kTW];
 #pragma unroll
-                        for (int c = 0; c < kTW; ++c) o[c] = fminf(fmaxf(fmaf(acc[c], s2, t2), 0.f), 6.f);
+                        for (int i = 0; i < kTW / 2; ++i) {
+                            float2 v = t2p;
+                            ffma2(v, acc[i], s2p);
+                            o[2 * i] = fminf(fmaxf(v.x, 0.f), 6.f); o[2 * i + 1] = fminf(fmaxf(v.y, 0.f), 6.f);
+                        }
                         // output pixel m = (hh*4 + orow)*16 + c: atom m / 64, 16-byte chunk (m % 64) / 8
                         const int m0 = (hh * ROWS + orow) * kTW;
                         const uint32_t base = a2_row + (m0 >> 6) * 16384;
@@ -357,47 +387,80 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 }
                 t5::fence_proxy_async_smem();                   // generic-proxy writes of A2 -> visible to the tensor core
                 t5::mbar_arrive(&bars[B_A2FULL + a]);
-                if (threadIdx.x == 64) dbg_mark(p, 1, g, 2);
+                if (threadIdx.x == 128) dbg_mark(p, 1, g, 2);
                 if (++b == p.d1_bufs) { b = 0; ++d1_pass; }
                 if (++a == p.a2_bufs) { a = 0; ++a2_pass; }
             }
-            // -------------------------------------------------------------- final epilogue: D2 -> BN3 (+ x) -> fp16 -> HBM
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(kRegsEpilogue));
+        // ================================================================== epilogue warpgroup: D2 -> BN3 (+ x) -> fp16 -> HBM, one tile behind
+        // the compute warps (which go straight on to the next tile: its first expand GEMM has already run)
+        const int q = warp & 3;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int prow = q * 32 + lane;
+        const int ncols = p.Cout;
+        for (int t = blockIdx.x, tl = 0; t < p.num_tiles; t += gridDim.x, ++tl) {
+            int r = t;
+            const int tx = r % p.tiles_x; r /= p.tiles_x;
+            const int ty = r % p.tiles_y;
+            const int n = r / p.tiles_y;
+            const int oy = ty * kTH + prow / kTW, ox = tx * kTW + prow % kTW;
+            const bool ok = oy < p.H && ox < p.W;
+            const long long pix = (static_cast<long long>(n) * p.H + oy) * p.W + ox;
+            // the skip connection's first 32 channels are in flight while the last project GEMM of the tile retires
+            uint4 res[4];
+            if (p.residual && ok) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k * 8 < ncols) res[k] = ldg_stream(p.residual + pix * p.Cout + k * 8);
+            }
             wait_bar(&bars[B_D2FULL], tl & 1);
             t5::fence_after_thread_sync();
-            {
-                const int prow = q * 32 + lane;
-                const int oy = y0 + prow / kTW, ox = x0 + prow % kTW;
-                const bool ok = oy < p.H && ox < p.W;
-                const long long pix = (static_cast<long long>(n) * p.H + oy) * p.W + ox;
-                const int ncols = p.Cout;
-                const uint32_t taddr = tmem_d2 + lane_addr;
-                for (int c0 = hh * 16; c0 < ncols; c0 += 32) {              // the two warps of a quarter interleave 16-column groups
-                    uint32_t rr[16];
-                    t5::tmem_ld16(taddr + c0, rr);
-                    t5::tmem_ld_wait();
-                    if (!ok) continue;
+            const uint32_t taddr = tmem_d2 + lane_addr;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t ra[16], rb[16];
+                t5::tmem_ld16(taddr + c0, ra);
+                if (c0 + 16 < ncols) t5::tmem_ld16(taddr + c0 + 16, rb);
+                if (c0 > 0 && p.residual && ok) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (c0 + k * 8 < ncols) res[k] = ldg_stream(p.residual + pix * p.Cout + c0 + k * 8);
+                }
+                t5::tmem_ld_wait();
+                if (c0 + 32 >= ncols) {                                      // last read of D2: the next tile's project GEMMs may start
+                    t5::fence_before_thread_sync();
+                    t5::mbar_arrive(&bars[B_D2EMPTY]);
+                }
+                if (!ok) continue;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int cb = c0 + h2 * 16;
+                    if (cb >= ncols) break;
+                    const uint32_t* rr = h2 ? rb : ra;
                     float v[16];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = (c0 + k < ncols) ? fmaf(__uint_as_float(rr[k]), __ldg(p.s3 + c0 + k), __ldg(p.t3 + c0 + k)) : 0.f;
+                    for (int k = 0; k < 16; k += 4) {
+                        if (cb + k < ncols) {                                 // Cout is a multiple of 8: groups of 4 are all-in or all-out
+                            const float4 s3 = __ldg(reinterpret_cast<const float4*>(p.s3 + cb + k)), t3 = __ldg(reinterpret_cast<const float4*>(p.t3 + cb + k));
+                            v[k] = fmaf(__uint_as_float(rr[k]), s3.x, t3.x); v[k + 1] = fmaf(__uint_as_float(rr[k + 1]), s3.y, t3.y);
+                            v[k + 2] = fmaf(__uint_as_float(rr[k + 2]), s3.z, t3.z); v[k + 3] = fmaf(__uint_as_float(rr[k + 3]), s3.w, t3.w);
+                        } else { v[k] = v[k + 1] = v[k + 2] = v[k + 3] = 0.f; }
+                    }
                     if (p.residual) {
-                        const __half* rp = p.residual + pix * p.Cout + c0;
                         float f[8];
-                        unpack8h(ldg_stream(rp), f);
+                        unpack8h(res[2 * h2], f);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) v[k] += f[k];
-                        if (c0 + 8 < ncols) {
-                            unpack8h(ldg_stream(rp + 8), f);
+                        if (cb + 8 < ncols) {
+                            unpack8h(res[2 * h2 + 1], f);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) v[8 + k] += f[k];
                         }
                     }
-                    __half* o = p.out + pix * p.Cout + c0;
+                    __half* o = p.out + pix * p.Cout + cb;
                     stg_stream(o, pack8h(v));
-                    if (c0 + 8 < ncols) stg_stream(o + 8, pack8h(v + 8));
+                    if (cb + 8 < ncols) stg_stream(o + 8, pack8h(v + 8));
                 }
             }
-            t5::fence_before_thread_sync();
-            t5::mbar_arrive(&bars[B_D2EMPTY]);
         }
     }
     t5::fence_before_thread_sync();

@@ -155,7 +155,7 @@ struct Net {
     bool weights_dirty = true, fold_dirty = true;
     // frozen inference of a batch >= 4 as two concurrent half batches (ams_set_infer_split): the second half's stream set
     bool infer_split = true; StreamSet split_ss{}; cudaEvent_t ev_split_fork = nullptr, ev_split_join = nullptr;
-    bool block_fusion = false;         // frozen inference: stride-1 inverted-residual blocks as one kernel each (ams_set_block_fusion)
+    bool block_fusion = true;          // frozen inference: stride-1 inverted-residual blocks as one kernel each (ams_set_block_fusion)
     std::vector<float*> fused_params;  // per expand layer: [13][cpad] padded per-channel vectors of the fused kernel (or null)
     bool frozen = false;               // built by ams_create_frozen: inference only ("Can't train frozen graph", SemanticNetwork.py:217)
     HeadGeom head{};

@@ -179,12 +179,13 @@ int ams_syncbn_connect(ams_net* net, const void* all_handles, int count);
 int ams_syncbn_enable(ams_net* net, int on);
 int ams_syncbn_status(ams_net* net, unsigned int* out_epoch, unsigned int* out_error);
 
-/* Frozen inference can run every stride-1 inverted-residual block (13 of the 17) as ONE kernel (expand GEMM -> TMEM ->
- * BN/ReLU6 -> shared-memory halo tile -> depthwise -> shared-memory A operand -> project GEMM): the 6C-wide tensors
- * never reach HBM and ams_get_activation() has nothing to return for the expand / depthwise layers of those blocks.
- * Results are bit-identical to the one-kernel-per-layer schedule (tests/test_net_gpu.py).  Default OFF (env
- * AMS_BLOCK_FUSION=1: on): on B200 the fused kernel measured 2.0-2.3 ms per batch of 8 frames against 1.76 ms for the
- * per-layer schedule (DESIGN.md 4 has the timeline and the diagnosis). */
+/* Frozen inference runs the stride-1 inverted-residual blocks whose project conv has <= 256 output channels (12 of the 17)
+ * as ONE kernel each (expand GEMM with the expanded channels on the TMEM lanes -> BN/ReLU6 and the depthwise 3x3 in
+ * registers, one channel per thread -> MN-major shared-memory A operand -> project GEMM): the 6C-wide tensors never reach
+ * HBM and ams_get_activation() has nothing to return for the expand / depthwise layers of those blocks.  Same fp16
+ * rounding points as the one-kernel-per-layer schedule; the two agree up to the fp32 accumulation order
+ * (tests/test_net_gpu.py: argmax agreement > 99.5 %, logits rel-L2 < 3e-3; measured 1.00000 / 2e-4).  Default ON (env
+ * AMS_BLOCK_FUSION=0: off).  ams_set_block_fusion(net, 0) restores the per-layer schedule, e.g. to inspect activations. */
 int ams_set_block_fusion(ams_net* net, int on);
 
 /* Frozen inference (AMS_BN_MOVING) of an even batch of >= 4 frames runs as two half batches on two streams inside one
