@@ -88,6 +88,12 @@ __device__ __forceinline__ void wait_bar_relaxed(uint64_t* bar, uint32_t parity)
     uint32_t spins = 0;
     while (!t5::mbar_try_wait(bar, parity)) { __nanosleep(32); if (++spins > (kSpinLimit >> 4)) __trap(); }
 }
+// long waits (the epilogue warps wait a whole tile for D2): a spinning warp takes issue slots from the two compute warps of
+// its scheduler -- the spin loop was 15 % of all executed instructions in the first ncu capture of this kernel
+__device__ __forceinline__ void wait_bar_idle(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!t5::mbar_try_wait(bar, parity)) { __nanosleep(256); if (++spins > (kSpinLimit >> 6)) __trap(); }
+}
 __device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {          // d += a * b (per lane), packed fp32x2
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&d))
         : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
@@ -297,10 +303,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 for (int k = 0; k < 9; ++k) wd[k] = __ldg(pp + (2 + k) * kChunk);
                 const float s2 = __ldg(pp + 11 * kChunk), t2 = __ldg(pp + 12 * kChunk);
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 0);
-                wait_bar(&bars[B_D1FULL + b], d1_pass & 1);
+                wait_bar_relaxed(&bars[B_D1FULL + b], d1_pass & 1);
                 t5::fence_after_thread_sync();
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 1);
-                if (a2_pass > 0) wait_bar(&bars[B_A2EMPTY + a], (a2_pass - 1) & 1);     // project GEMM of chunk g - a2_bufs retired
+                if (a2_pass > 0) wait_bar_relaxed(&bars[B_A2EMPTY + a], (a2_pass - 1) & 1);     // project GEMM of chunk g - a2_bufs retired
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 3);
                 const uint32_t taddr = tmem_base + lane_addr + b * p.n1 + (hh * ROWS) * HW;
                 // K row `ch` of both 64-pixel atoms; 16-byte chunk index XOR (ch mod 8)
@@ -414,7 +420,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (k * 8 < ncols) res[k] = ldg_stream(p.residual + pix * p.Cout + k * 8);
             }
-            wait_bar(&bars[B_D2FULL], tl & 1);
+            wait_bar_idle(&bars[B_D2FULL], tl & 1);
             t5::fence_after_thread_sync();
             const uint32_t taddr = tmem_d2 + lane_addr;
             for (int c0 = 0; c0 < ncols; c0 += 32) {
