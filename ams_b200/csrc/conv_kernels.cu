@@ -32,26 +32,26 @@ __device__ __forceinline__ void stem_pixel(const T* in, const StemGeom& g, int n
     for (int c = 0; c < 3; ++c) v3[c] = __fsub_rn(__fmul_rn(g.norm_scale, load_px<T>(p + c)), g.norm_shift);
 }
 
-// one thread = one output pixel x 16 output channels
+// one thread = one output pixel x all 32 output channels.  The kernel is bound by instruction issue, not by its 80 MB of
+// traffic: the 27 input values are fetched and normalised once per pixel, and the 27 x 32 FMAs run as packed fp32x2
+// instructions (two output channels each; every lane is the same IEEE fma, in the same tap order, as a scalar loop).
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ w, const float* __restrict__ scale,
                 const float* __restrict__ shift, act_t* __restrict__ out, float act_hi) {
     pdl_entry();
-    __shared__ float sw[27 * 32];
+    __shared__ __align__(16) float sw[27 * 32];
     for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
     __syncthreads();
-    const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo * 2;
-    if (tid >= total) return;
-    const int half = static_cast<int>(tid & 1);
-    const long long pix = tid >> 1;
+    const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(g.N) * g.Ho * g.Wo;
+    if (pix >= total) return;
     const int ox = static_cast<int>(pix % g.Wo);
     const int oy = static_cast<int>((pix / g.Wo) % g.Ho);
     const int n = static_cast<int>(pix / (static_cast<long long>(g.Wo) * g.Ho));
-    float acc[16];
+    float2 acc2[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 16; ++j) acc2[j] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -60,19 +60,31 @@ stem_fwd_kernel(const T* __restrict__ in, StemGeom g, const float* __restrict__ 
             stem_pixel<T>(in, g, n, oy * 2 - g.pad_top + ky, ox * 2 - g.pad_left + kx, v);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const float* wr = sw + ((ky * 3 + kx) * 3 + c) * 32 + half * 16;
+                const float4* wr = reinterpret_cast<const float4*>(sw + ((ky * 3 + kx) * 3 + c) * 32);
+                const float2 vv = make_float2(v[c], v[c]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = fmaf(v[c], wr[j], acc[j]);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w4 = wr[j];
+                    const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&acc2[2 * j]))
+                        : "l"(*reinterpret_cast<const unsigned long long*>(&vv)), "l"(*reinterpret_cast<const unsigned long long*>(&wa)));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(*reinterpret_cast<unsigned long long*>(&acc2[2 * j + 1]))
+                        : "l"(*reinterpret_cast<const unsigned long long*>(&vv)), "l"(*reinterpret_cast<const unsigned long long*>(&wb)));
+                }
             }
         }
     }
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
     if (scale) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            acc[j] = fminf(fmaxf(fmaf(acc[j], scale[half * 16 + j], shift[half * 16 + j]), 0.f), act_hi);      // ReLU6 (6) or ReLU (+inf)
+        for (int j = 0; j < 32; ++j)
+            acc[j] = fminf(fmaxf(fmaf(acc[j], __ldg(scale + j), __ldg(shift + j)), 0.f), act_hi);      // ReLU6 (6) or ReLU (+inf)
     }
-    act_t* o = out + pix * 32 + half * 16;
+    act_t* o = out + pix * 32;
     stg256(o, pack8h(acc), pack8h(acc + 8));
+    stg256(o + 16, pack8h(acc + 16), pack8h(acc + 24));
 }
 
 // filter gradient: a block owns `rows_per_block` output rows; per segment of 64 output pixels it stages the three
@@ -374,7 +386,7 @@ int stem_conv_fwd(const void* in, int in_is_u8, int N, int H, int W, int Hp, int
                   int pad_left, float pad_value, float norm_scale, float norm_shift, const float* w, const float* scale,
                   const float* shift, act_t* out, cudaStream_t s, int act) {
     StemGeom g{N, H, W, Hp, Wp, Ho, Wo, pad_top, pad_left, pad_value, norm_scale, norm_shift};
-    const long long total = static_cast<long long>(N) * Ho * Wo * 2;
+    const long long total = static_cast<long long>(N) * Ho * Wo;
     const float act_hi = act == 1 ? INFINITY : 6.f;
     if (in_is_u8)
         AMS_LAUNCH((stem_fwd_kernel<uint8_t>), blocks_for(total, 256), 256, 0, s, static_cast<const uint8_t*>(in), g, w, scale, shift, out, act_hi);
