@@ -225,6 +225,7 @@ int pick_cb(int C) {
     if (C % 64 == 0) return 64;
     if (C % 48 == 0) return 48;
     if (C % 32 == 0) return 32;
+    if (C % 56 == 0) return 56;      // 728 = 13 x 56: the Xception middle flow of the teacher (forward kernel only)
     return 0;
 }
 
@@ -289,6 +290,7 @@ template <int S, int D>
 int launch_fwd_cb(const DwFwdParams& p, const DwTile& t, cudaStream_t s) {
     if (t.cb == 64) return launch_fwd<S, D, 64>(p, t, s);
     if (t.cb == 48) return launch_fwd<S, D, 48>(p, t, s);
+    if (t.cb == 56) return launch_fwd<S, D, 56>(p, t, s);
     return launch_fwd<S, D, 32>(p, t, s);
 }
 
@@ -655,6 +657,7 @@ template <int S, int D, int PADX>
 int launch_bwd_cb(const DwBwdParams& p, const DwBwdTile& t, cudaStream_t s) {
     if (t.cb == 64) return launch_bwd<S, D, 64, PADX>(p, t, s);
     if (t.cb == 48) return launch_bwd<S, D, 48, PADX>(p, t, s);
+    AMS_REQUIRE(t.cb == 32, "fused depthwise backward: channel chunk not instantiated");
     return launch_bwd<S, D, 32, PADX>(p, t, s);
 }
 

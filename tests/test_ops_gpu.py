@@ -147,7 +147,8 @@ def _dw_ref(x, w, stride, dil):
 
 
 @pytest.mark.parametrize('n,h,w,c,stride,dil', [(2, 33, 65, 32, 1, 1), (1, 65, 129, 96, 2, 1), (2, 17, 33, 960, 1, 2),
-                                                (1, 64, 30, 144, 2, 1), (1, 9, 17, 384, 1, 1), (3, 5, 7, 576, 1, 2)])
+                                                (1, 64, 30, 144, 2, 1), (1, 9, 17, 384, 1, 1), (3, 5, 7, 576, 1, 2),
+                                                (1, 33, 65, 728, 1, 1), (1, 66, 40, 728, 2, 1), (1, 20, 33, 112, 1, 2)])   # 56-channel chunks (teacher)
 def test_depthwise_fwd(n, h, w, c, stride, dil):
     L = nat.lib()
     x = ac_round(rnd(n, h, w, c, seed=13))
