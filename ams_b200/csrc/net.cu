@@ -559,7 +559,9 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     // they go to a side stream (fork after their dz is ready, one join at the end) and overlap with the chain.
     const bool side = !net->prof.enabled && net->side_stream != nullptr;
     bool forked = false, pool_bwd_pending = false;
+    static const bool x_skip_wgrad = [] { const char* e = getenv("AMS_X_SKIP_WGRAD"); return e && e[0] == '1'; }();   // TIMING EXPERIMENT ONLY
     auto wgrad_on_side = [&](const WgradPlan& wp) -> int {
+        if (x_skip_wgrad) return 0;
         AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
         AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
         forked = true;
