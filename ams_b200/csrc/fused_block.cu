@@ -306,7 +306,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 wait_bar_relaxed(&bars[B_D1FULL + b], d1_pass & 1);
                 t5::fence_after_thread_sync();
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 1);
-                if (a2_pass > 0) wait_bar_relaxed(&bars[B_A2EMPTY + a], (a2_pass - 1) & 1);     // project GEMM of chunk g - a2_bufs retired
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 3);
                 const uint32_t taddr = tmem_base + lane_addr + b * p.n1 + (hh * ROWS) * HW;
                 // K row `ch` of both 64-pixel atoms; 16-byte chunk index XOR (ch mod 8)
@@ -385,6 +384,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         }
                         // output pixel m = (hh*4 + orow)*16 + c: atom m / 64, 16-byte chunk (m % 64) / 8
                         const int m0 = (hh * ROWS + orow) * kTW;
+                        // first store of the chunk: the project GEMM that last read this A2 buffer must have retired (waited for
+                        // HERE, after the BN1 work of 2d+1 halo rows, so that its latency hides behind that work)
+                        if (orow == 0 && a2_pass > 0) wait_bar_relaxed(&bars[B_A2EMPTY + a], (a2_pass - 1) & 1);
                         const uint32_t base = a2_row + (m0 >> 6) * 16384;
                         const int ck = (m0 & 63) >> 3;
                         sts128(base + (((ck) ^ (ch & 7)) << 4), pack8h(o));
@@ -550,12 +552,21 @@ int fused_block_plan(const FusedBlockDesc& d, int num_sms, FusedBlockPlan* plan)
     p.x_slab = p.n1 * 64;
     p.we_plane = kChunk * 64; p.we_unit = p.we_plane * (p.we_split ? 2 : 1);
     p.wp_plane = p.np_mma * 64; p.wp_unit = p.wp_plane * (p.wp_split ? 2 : 1);
-    // rings as deep as shared memory allows: up to two chunks of expand weights and two chunks of project weights in flight
-    const int options[6][3] = {   // {we units, wp units, a2 buffers}
-        {2 * p.k_blocks, 8, 2}, {2 * p.k_blocks, 4, 2}, {p.k_blocks + 1, 4, 2}, {p.k_blocks + 1, 4, 1}, {std::max(2, p.k_blocks - 1), 3, 1}, {2, 2, 1}};
+    // Rings as deep as shared memory allows.  Priorities: (1) the expand ring holds at least one whole chunk (k_blocks units) --
+    // otherwise every expand GEMM stalls on a TMA round trip in its middle; (2) two A2 buffers, so that the project GEMM of a
+    // chunk is off the compute warps' critical path; (3) a whole chunk of project weights (4 units); (4) deeper rings.
     bool fits = false;
-    for (int o = 0; o < 6 && !fits; ++o) {
-        p.we_slots = std::min(std::max(options[o][0], 2), kMaxWe); p.wp_slots = std::min(options[o][1], kMaxWp); p.a2_bufs = options[o][2];
+    int best_score = -1;
+    for (int a2 = 1; a2 <= 2; ++a2)
+        for (int we = 2; we <= kMaxWe; ++we)
+            for (int wp = 2; wp <= kMaxWp; ++wp) {
+                const size_t total = 1024 + size_t(p.k_blocks) * p.x_slab + size_t(we) * p.we_unit + size_t(wp) * p.wp_unit + size_t(a2) * 2 * 16384 +
+                                     4096 /* alignment slack + barriers */;
+                if (total > 227 * 1024) continue;
+                const int score = (we >= p.k_blocks ? 1000 : 0) + (a2 == 2 ? 400 : 0) + (wp >= 4 ? 200 : 0) + std::min(we, 2 * p.k_blocks) * 8 + std::min(wp, 8) * 4;
+                if (score > best_score) { best_score = score; p.we_slots = we; p.wp_slots = wp; p.a2_bufs = a2; fits = true; }
+            }
+    if (fits) {
         uint32_t off = 0;
         auto take = [&](uint32_t bytes) { const uint32_t at = off; off = (off + bytes + 1023u) & ~1023u; return at; };
         p.off_x = take(p.k_blocks * p.x_slab);
