@@ -97,7 +97,7 @@ _SIGNATURES = {
     'ams_debug_dw_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
     'ams_debug_dw_bwd_tile': (_i, [_i] * 8 + [C.POINTER(_i)]),
     'ams_op_conv1x1': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
-    'ams_op_fused_block': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'ams_op_fused_block': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     'ams_debug_fused_timeline': (_i, [_vp]),
     'ams_op_wgrad': (_i, [_vp, _i, _vp, _i, _ll, _vp, _vp]),
     'ams_op_depthwise': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),

@@ -1022,13 +1022,13 @@ static void* g_fused_debug_timeline = nullptr;
  * timeline (ns) of CTA 0: [MMA issuer | group E | group W][chunk][event] */
 int ams_debug_fused_timeline(void* device_buffer) { g_fused_debug_timeline = device_buffer; return 0; }
 
-int ams_op_fused_block(const void* x, int n, int h, int w_, int cin, int cexp, int cout, int dil, const void* we, const void* we_lo,
+int ams_op_fused_block(const void* x, int n, int h, int w_, int cin, int cexp, int cout, int dil, int stride, const void* we, const void* we_lo,
                        const float* s1, const float* t1, const float* wd, const float* s2, const float* t2, const void* wp, const void* wp_lo,
                        const float* s3, const float* t3, int residual, void* out, void* stream) {
     int dev = 0; cudaGetDevice(&dev);
     int sms = kNumSMs; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     FusedBlockDesc d;
-    d.N = n; d.H = h; d.W = w_; d.Cin = cin; d.Cexp = cexp; d.Cout = cout; d.stride = 1; d.dil = dil;
+    d.N = n; d.H = h; d.W = w_; d.Cin = cin; d.Cexp = cexp; d.Cout = cout; d.stride = stride; d.dil = dil;
     d.x = x; d.We = we; d.We_lo = we_lo; d.ld_we = cin; d.Wp = wp; d.Wp_lo = wp_lo; d.ld_wp = cexp;
     d.s3 = s3; d.t3 = t3; d.residual = residual ? x : nullptr; d.out = out;
     d.debug_timeline = g_fused_debug_timeline;

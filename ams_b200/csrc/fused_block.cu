@@ -49,21 +49,23 @@ constexpr uint32_t kSpinLimit = 1u << 28;     // a barrier that never completes 
 
 struct FusedParams {
     int N, H, W, Cin, Cexp, Cout, dil;
+    int Ho, Wo, pad_top, pad_left;    // stride-2 blocks: output size and the depthwise conv's 'SAME' padding (stride 1: Ho = H, Wo = W, pad = dil)
     int k_blocks;                 // ceil(Cin / 32)
     int n_chunks;                 // ceil(Cexp / 128)
     int we_split, wp_split;       // low weight planes present
     int np_mma;                   // Cout rounded up to the UMMA N granule (16)
+    int wp_stack;                 // split project weights as ONE operand of 2*np_mma rows (hi rows, then lo rows): half the MMAs, D2 = two column halves
     int tiles_x, tiles_y, num_tiles;
     int halo_w, halo_h, halo_rows, n1;        // n1 = halo_rows rounded up to 16 = UMMA N of the expand GEMM
-    int d1_bufs, a2_bufs, we_slots, wp_slots;
-    uint32_t tmem_cols, d2_col;
+    int d1_bufs, a2_bufs, we_slots, wp_slots, x_bufs, d2_bufs;
+    int wp_group;                 // 32-channel k-blocks of project weights per ring unit / barrier (4 = a whole chunk, else 1)
+    uint32_t tmem_cols, d2_col, d2_cols;       // first D2 column; columns per D2 buffer
     const float* par;             // [n_chunks][13][128]: s1 t1 wd[9] s2 t2, zero beyond Cexp
     const float* s3; const float* t3;           // [Cout]
     const __half* residual;                      // block input (same geometry) or null
     __half* out;
     uint32_t off_x, off_we, off_wp, off_a2, off_bar;       // shared-memory offsets (bytes, from the 1024-aligned base)
-    uint32_t x_slab, we_unit, we_plane, wp_unit, wp_plane;  // bytes: one k-block of X; one ring unit (all planes); one plane of it
-    int x_skip;                                  // TIMING EXPERIMENTS ONLY (env AMS_X_FUSED_SKIP): 1 = compute warps skip the depthwise FMAs, 2 = skip BN1 too
+    uint32_t x_slab, x_buf, we_unit, we_plane, wp_unit, wp_plane, wp_kb;  // bytes: one k-block of X; one ring unit; one plane of a k-block; wp_kb = all planes of one k-block
     unsigned long long* dbg;                     // optional timeline of CTA 0 (tools/micro/fused_block_run.py): [role][chunk][4] ns
 };
 __device__ __forceinline__ void dbg_mark(const FusedParams& p, int role, long long g, int k) {
@@ -110,19 +112,22 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
 }
 
 // barrier slots inside the shared-memory barrier area
-enum : int { B_XFULL = 0, B_XEMPTY, B_WEFULL, B_WEEMPTY = B_WEFULL + kMaxWe, B_WPFULL = B_WEEMPTY + kMaxWe, B_WPEMPTY = B_WPFULL + kMaxWp,
+enum : int { B_XFULL = 0, B_XEMPTY = 2, B_WEFULL = 4, B_WEEMPTY = B_WEFULL + kMaxWe, B_WPFULL = B_WEEMPTY + kMaxWe, B_WPEMPTY = B_WPFULL + kMaxWp,
              B_D1FULL = B_WPEMPTY + kMaxWp, B_D1EMPTY = B_D1FULL + 2, B_A2FULL = B_D1EMPTY + 2, B_A2EMPTY = B_A2FULL + 2,
-             B_D2FULL = B_A2EMPTY + 2, B_D2EMPTY, B_COUNT };
+             B_D2FULL = B_A2EMPTY + 2, B_D2EMPTY = B_D2FULL + 2, B_COUNT = B_D2EMPTY + 2 };
 
-template <int D>
+// <D, S>: depthwise dilation (1 | 2, stride 1) and stride (1 | 2, dilation 1).  Stride 1: 8x16 output tile, halo (8+2D) x (16+2D).
+// Stride 2: 2x16 output tile (32 of the 128 project-GEMM rows carry pixels), input halo 5 x 33.
+template <int D, int S>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmWe,
                    const __grid_constant__ CUtensorMap tmWeLo, const __grid_constant__ CUtensorMap tmWp,
                    const __grid_constant__ CUtensorMap tmWpLo, const FusedParams p) {
-    constexpr int HW = kTW + 2 * D;            // halo row length = TMEM columns per halo row
+    constexpr int TH = S == 1 ? kTH : 2;       // output tile rows
+    constexpr int HW = S == 1 ? kTW + 2 * D : 2 * kTW + 1;      // halo row length = TMEM columns per halo row
     constexpr int WIN = 2 * D + 1;             // halo rows one output row needs
-    constexpr int ROWS = kTH / 2;              // output rows per compute warp
-    constexpr int HR = ROWS + 2 * D;           // halo rows per compute warp
+    constexpr int ROWS = TH / 2;               // output rows per compute warp
+    constexpr int HR = S == 1 ? ROWS + 2 * D : 3;               // halo rows per compute warp
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smX = smem + p.off_x;        // [k_blocks][n1 rows][64 B]                 K-major, swizzle 64B (row = halo pixel)
@@ -138,7 +143,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         t5::tma_prefetch_desc(&tmX); t5::tma_prefetch_desc(&tmWe); t5::tma_prefetch_desc(&tmWp);
         for (int b = 0; b < B_COUNT; ++b) {
             const bool by_compute = (b >= B_D1EMPTY && b < B_D1EMPTY + 2) || (b >= B_A2FULL && b < B_A2FULL + 2);
-            t5::mbar_init(&bars[b], by_compute ? kCompute : (b == B_D2EMPTY ? kEpilogue : 1));
+            t5::mbar_init(&bars[b], by_compute ? kCompute : ((b >= B_D2EMPTY && b < B_D2EMPTY + 2) ? kEpilogue : 1));
         }
         t5::fence_barrier_init();
     }
@@ -165,16 +170,18 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             // ring bookkeeping without divisions: slot index + number of completed passes over the ring
             int we_s = 0, wp_s = 0; uint32_t we_pass = 0, wp_pass = 0;
             int tl_e = 0, j_e = 0, j_p = 0;             // tile / chunk of the next expand-weight issue; chunk of the next project-weight issue
+            int xb = 0; uint32_t x_pass = 0;            // X buffer of that tile and completed passes over the X buffers
             auto issue_we = [&]() {
                 if (j_e == 0) {
                     int r = static_cast<int>(blockIdx.x) + tl_e * static_cast<int>(gridDim.x);
                     const int tx = r % p.tiles_x; r /= p.tiles_x;
                     const int ty = r % p.tiles_y;
                     const int n = r / p.tiles_y;
-                    if (tl_e > 0) wait_bar_relaxed(&bars[B_XEMPTY], (tl_e - 1) & 1);         // every expand GEMM of the previous tile retired
-                    t5::mbar_arrive_expect_tx(&bars[B_XFULL], static_cast<uint32_t>(p.k_blocks * p.halo_rows * 64));
+                    if (x_pass > 0) wait_bar_relaxed(&bars[B_XEMPTY + xb], (x_pass - 1) & 1);   // every expand GEMM of the tile that used this buffer retired
+                    t5::mbar_arrive_expect_tx(&bars[B_XFULL + xb], static_cast<uint32_t>(p.k_blocks * p.halo_rows * 64));
                     for (int kb = 0; kb < p.k_blocks; ++kb)
-                        tma_load_4d(smX + kb * p.x_slab, &tmX, &bars[B_XFULL], kb * kKB, tx * kTW - D, ty * kTH - D, n);
+                        tma_load_4d(smX + xb * p.x_buf + kb * p.x_slab, &tmX, &bars[B_XFULL + xb], kb * kKB, tx * kTW * S - p.pad_left, ty * TH * S - p.pad_top, n);
+                    if (++xb == p.x_bufs) { xb = 0; ++x_pass; }
                 }
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
                     if (we_pass > 0) wait_bar_relaxed(&bars[B_WEEMPTY + we_s], (we_pass - 1) & 1);
@@ -187,12 +194,16 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 if (++j_e == p.n_chunks) { j_e = 0; ++tl_e; }
             };
             auto issue_wp = [&]() {
-                for (int u = 0; u < kChunk / kKB; ++u) {
+                const int kbs = min(kChunk / kKB, (p.Cexp - j_p * kChunk + kKB - 1) / kKB);      // k-blocks of this chunk that hold channels
+                for (int u0 = 0; u0 < kbs; u0 += p.wp_group) {
+                    const int nkb = min(p.wp_group, kbs - u0);
                     if (wp_pass > 0) wait_bar_relaxed(&bars[B_WPEMPTY + wp_s], (wp_pass - 1) & 1);
                     uint8_t* dst = smWp + wp_s * p.wp_unit;
-                    t5::mbar_arrive_expect_tx(&bars[B_WPFULL + wp_s], p.wp_unit);
-                    t5::tma_load_2d(dst, &tmWp, &bars[B_WPFULL + wp_s], j_p * kChunk + u * kKB, 0);
-                    if (p.wp_split) t5::tma_load_2d(dst + p.wp_plane, &tmWpLo, &bars[B_WPFULL + wp_s], j_p * kChunk + u * kKB, 0);
+                    t5::mbar_arrive_expect_tx(&bars[B_WPFULL + wp_s], nkb * p.wp_kb);
+                    for (int u = 0; u < nkb; ++u) {
+                        t5::tma_load_2d(dst + u * p.wp_kb, &tmWp, &bars[B_WPFULL + wp_s], j_p * kChunk + (u0 + u) * kKB, 0);
+                        if (p.wp_split) t5::tma_load_2d(dst + u * p.wp_kb + p.wp_plane, &tmWpLo, &bars[B_WPFULL + wp_s], j_p * kChunk + (u0 + u) * kKB, 0);
+                    }
                     if (++wp_s == p.wp_slots) { wp_s = 0; ++wp_pass; }
                 }
                 if (++j_p == p.n_chunks) j_p = 0;
@@ -206,12 +217,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     } else if (warp == 1) {
         // ================================================================== MMA issuer (one elected lane issues)
         const uint32_t idesc1 = t5::make_idesc_f16(128, p.n1, 0, 0, 0, 0);            // A = We (K-major), B = X (K-major)
-        const uint32_t idesc2 = t5::make_idesc_f16(128, p.np_mma, 1, 0, 0, 0);        // A = A2 (MN-major: pixels contiguous), B = Wp (K-major)
+        const uint32_t idesc2 = t5::make_idesc_f16(128, p.wp_stack ? 2 * p.np_mma : p.np_mma, 1, 0, 0, 0);   // A = A2 (MN-major: pixels contiguous), B = Wp (K-major)
         int we_s = 0, wp_s = 0; uint32_t we_pass = 0, wp_pass = 0;
         // expand side: tile / chunk / D1 buffer / pass over the D1 buffers of the NEXT expand GEMM
         int tl_e = 0, j_e = 0, b_e = 0; uint32_t d1_pass = 0;
+        int xb = 0; uint32_t x_pass = 0;                // X buffer of the tile being expanded
         auto expand = [&](int g) {
-            if (j_e == 0) wait_bar_relaxed(&bars[B_XFULL], tl_e & 1);
+            if (j_e == 0) wait_bar_relaxed(&bars[B_XFULL + xb], x_pass & 1);
             if (d1_pass > 0) wait_bar_relaxed(&bars[B_D1EMPTY + b_e], (d1_pass - 1) & 1);          // the compute warps have read the previous chunk out of this buffer
             t5::fence_after_thread_sync();
             const uint32_t d = tmem_base + b_e * p.n1;
@@ -225,7 +237,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     // matters because this warp shares its scheduler with two FFMA-bound compute warps.
                     // Descriptors: the start-address field is bits [0,14) in 16-byte units, so a k-step of 32 bytes is +2.
                     const uint64_t da0 = t5::make_smem_desc(t5::smem_u32(smWe) + we_s * p.we_unit, 16, 512, 4);
-                    const uint64_t db0 = t5::make_smem_desc(t5::smem_u32(smX) + kb * p.x_slab, 16, 512, 4);
+                    const uint64_t db0 = t5::make_smem_desc(t5::smem_u32(smX) + xb * p.x_buf + kb * p.x_slab, 16, 512, 4);
                     const uint64_t lo = p.we_plane >> 4;
 #pragma unroll
                     for (int k = 0; k < kKB / 16; ++k) {
@@ -238,44 +250,47 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 if (++we_s == p.we_slots) { we_s = 0; ++we_pass; }
             }
             t5::mma_commit_warp(&bars[B_D1FULL + b_e]);
-            if (j_e == p.n_chunks - 1) t5::mma_commit_warp(&bars[B_XEMPTY]);
+            if (j_e == p.n_chunks - 1) t5::mma_commit_warp(&bars[B_XEMPTY + xb]);
             if (++b_e == p.d1_bufs) { b_e = 0; ++d1_pass; }
-            if (++j_e == p.n_chunks) { j_e = 0; ++tl_e; }
+            if (++j_e == p.n_chunks) { j_e = 0; ++tl_e; if (++xb == p.x_bufs) { xb = 0; ++x_pass; } }
         };
         if (G > 0) expand(0);
         int tl = 0, j = 0, a = 0; uint32_t a2_pass = 0;
+        int db = 0; uint32_t d2_pass = 0;               // D2 buffer of the tile being projected
         for (int g = 0; g < G; ++g) {
             if (g + 1 < G) expand(g + 1);
-            if (j == 0 && tl > 0) wait_bar_relaxed(&bars[B_D2EMPTY], (tl - 1) & 1);          // final epilogue of the previous tile drained D2
+            if (j == 0 && d2_pass > 0) wait_bar_relaxed(&bars[B_D2EMPTY + db], (d2_pass - 1) & 1);   // the epilogue of the tile that used this D2 buffer drained it
+            const uint32_t tmem_d2b = tmem_d2 + db * p.d2_cols;
             wait_bar_relaxed(&bars[B_A2FULL + a], a2_pass & 1);
             t5::fence_after_thread_sync();
-            for (int u = 0; u < kChunk / kKB; ++u) {
+            const int kbs = min(kChunk / kKB, (p.Cexp - j * kChunk + kKB - 1) / kKB);
+            for (int u0 = 0; u0 < kbs; u0 += p.wp_group) {
+                const int nkb = min(p.wp_group, kbs - u0);
                 wait_bar_relaxed(&bars[B_WPFULL + wp_s], wp_pass & 1);
                 t5::fence_after_thread_sync();
-                if (lane == 0 && u == 0) dbg_mark(p, 0, g, 1);
+                if (lane == 0 && u0 == 0) dbg_mark(p, 0, g, 1);
                 {
                     // A2 is MN-major SWIZZLE_128B: 64-pixel atoms 16 KB apart (LBO), 8-channel groups 1024 B apart (SBO); one
                     // UMMA_K = 16 channels = 2048 B (+128 in the 16-byte units of the descriptor's address field)
-                    uint64_t da0 = t5::make_smem_desc_sw128(t5::smem_u32(smA2) + a * (2 * 16384) + u * 4096, 16384, 1024);
+                    const uint64_t da0 = t5::make_smem_desc_sw128(t5::smem_u32(smA2) + a * (2 * 16384) + u0 * 4096, 16384, 1024);
                     const uint64_t db0 = t5::make_smem_desc(t5::smem_u32(smWp) + wp_s * p.wp_unit, 16, 512, 4);
-                    if (p.x_skip & 4) da0 = t5::make_smem_desc(t5::smem_u32(smWe), 16, 512, 4);       // timing experiment: K-major A (wrong results)
-                    const uint64_t lo = p.wp_plane >> 4;
+                    const uint64_t lo = p.wp_plane >> 4, kbstep = p.wp_kb >> 4;
+                    for (int u = 0; u < nkb; ++u) {
 #pragma unroll
-                    for (int k = 0; k < kKB / 16; ++k) {
-                        const uint32_t id2 = (p.x_skip & 4) ? (idesc2 & ~(1u << 15)) : idesc2;
-                        const uint64_t dak = (p.x_skip & 4) ? da0 + 2 * k : da0 + 128 * k;
-                        t5::mma_f16_ss_warp((p.x_skip & 8) ? tmem_base : tmem_d2, dak, db0 + 2 * k, id2, (j | u | k) != 0);
-                        if (p.wp_split && !(p.x_skip & 16)) t5::mma_f16_ss_warp((p.x_skip & 8) ? tmem_base : tmem_d2, dak, db0 + lo + 2 * k, id2, 1u);
+                        for (int k = 0; k < kKB / 16; ++k) {
+                            t5::mma_f16_ss_warp(tmem_d2b, da0 + 256 * u + 128 * k, db0 + kbstep * u + 2 * k, idesc2, (j | (u0 + u) | k) != 0);
+                            if (p.wp_split && !p.wp_stack) t5::mma_f16_ss_warp(tmem_d2b, da0 + 256 * u + 128 * k, db0 + kbstep * u + lo + 2 * k, idesc2, 1u);
+                        }
                     }
                     t5::mma_commit_warp(&bars[B_WPEMPTY + wp_s]);
                 }
-                if (lane == 0 && u == kChunk / kKB - 1) dbg_mark(p, 0, g, 3);
+                if (lane == 0 && u0 + nkb >= kbs) dbg_mark(p, 0, g, 3);
                 if (++wp_s == p.wp_slots) { wp_s = 0; ++wp_pass; }
             }
             t5::mma_commit_warp(&bars[B_A2EMPTY + a]);
-            if (j == p.n_chunks - 1) t5::mma_commit_warp(&bars[B_D2FULL]);
+            if (j == p.n_chunks - 1) t5::mma_commit_warp(&bars[B_D2FULL + db]);
             if (++a == p.a2_bufs) { a = 0; ++a2_pass; }
-            if (++j == p.n_chunks) { j = 0; ++tl; }
+            if (++j == p.n_chunks) { j = 0; ++tl; if (++db == p.d2_bufs) { db = 0; ++d2_pass; } }
         }
     }
     } else if (warp < 12) {
@@ -292,8 +307,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const int tx = r % p.tiles_x; r /= p.tiles_x;
             const int ty = r % p.tiles_y;
             const int n = r / p.tiles_y;
-            const int y0 = ty * kTH, x0 = tx * kTW;
-            const int col_hi = p.W - x0 + D;               // halo columns >= col_hi lie right of the image
+            const int y0 = ty * TH * S - p.pad_top, x0 = tx * kTW * S - p.pad_left;     // image coordinates of halo position (0, 0)
+            const int col_hi = p.W - x0;                    // halo columns >= col_hi lie right of the image
             for (int j = 0; j < p.n_chunks; ++j, ++g) {
                 // per-channel constants of this chunk (coalesced over the lanes; zero beyond Cexp)
                 const float* pp = p.par + static_cast<long long>(j) * 13 * kChunk + ch;
@@ -307,9 +322,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 t5::fence_after_thread_sync();
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 1);
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 3);
-                const uint32_t taddr = tmem_base + lane_addr + b * p.n1 + (hh * ROWS) * HW;
+                const uint32_t taddr = tmem_base + lane_addr + b * p.n1 + (hh * ROWS * S) * HW;
                 // K row `ch` of both 64-pixel atoms; 16-byte chunk index XOR (ch mod 8)
                 const uint32_t a2_row = a2_s + a * (2 * 16384) + ch * 128;
+                if constexpr (S == 1) {
                 // window rows as aligned fp32 pairs (columns 2i, 2i+1): taps with an even column offset (all of them at
                 // dilation 2; kx = 0, 2 at dilation 1) run as packed fp32x2 FMAs on two adjacent output pixels
                 float2 win[WIN][HW / 2];
@@ -323,7 +339,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
                 for (int hr = 0; hr < HR; ++hr) {
                     t5::tmem_ld_wait();
-                    const int gy = y0 - D + hh * ROWS + hr;
+                    const int gy = y0 + hh * ROWS + hr;
                     float2* wr = win[hr % WIN];
                     if (gy >= 0 && gy < p.H) {
 #pragma unroll
@@ -333,7 +349,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                             v.x = fminf(fmaxf(v.x, 0.f), 6.f); v.y = fminf(fmaxf(v.y, 0.f), 6.f);
                             wr[i] = h16x2(pack_h16(v.x, v.y));                          // the value the unfused path stores (fp16)
                         }
-                        if (x0 == 0) {                                                  // columns left of the image
+                        if (x0 < 0) {                                                   // columns left of the image (x0 = -D)
                             if (D == 1) wr[0].x = 0.f; else wr[0] = make_float2(0.f, 0.f);
                         }
                         if (col_hi < HW) {                                              // columns right of the image (last tile column only)
@@ -351,7 +367,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         t5::fence_before_thread_sync();
                         t5::mbar_arrive(&bars[B_D1EMPTY + b]);                         // this thread has read its part of D1
                     }
-                    if (hr >= 2 * D && (p.x_skip & 1) == 0) {
+                    if (hr >= 2 * D) {
                         const int orow = hr - 2 * D;                                    // output row within this warp's half
                         float2 acc[kTW / 2];
 #pragma unroll
@@ -393,6 +409,70 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         sts128(base + (((ck + 1) ^ (ch & 7)) << 4), pack8h(o + 8));
                     }
                 }
+                } else {
+                // stride 2: this warp computes ONE output row (16 pixels) from 3 halo rows x 33 columns held as scalars
+                float win[3][HW];
+                uint32_t raw[HW];
+                auto load_row = [&](int hr) {
+                    t5::tmem_ld16(taddr + hr * HW, raw);
+                    t5::tmem_ld16(taddr + hr * HW + 16, raw + 16);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(raw[32]) : "r"(taddr + hr * HW + 32) : "memory");
+                };
+                load_row(0);
+#pragma unroll
+                for (int hr = 0; hr < HR; ++hr) {
+                    t5::tmem_ld_wait();
+                    const int gy = y0 + hh * ROWS * 2 + hr;
+                    float* wr = win[hr];
+                    if (gy >= 0 && gy < p.H) {
+#pragma unroll
+                        for (int i = 0; i < HW / 2; ++i) {
+                            const float v0 = fminf(fmaxf(fmaf(__uint_as_float(raw[2 * i]), s1, t1), 0.f), 6.f);
+                            const float v1 = fminf(fmaxf(fmaf(__uint_as_float(raw[2 * i + 1]), s1, t1), 0.f), 6.f);
+                            const float2 f = h16x2(pack_h16(v0, v1));                  // the value the unfused path stores (fp16)
+                            wr[2 * i] = f.x; wr[2 * i + 1] = f.y;
+                        }
+                        {
+                            const float v0 = fminf(fmaxf(fmaf(__uint_as_float(raw[HW - 1]), s1, t1), 0.f), 6.f);
+                            wr[HW - 1] = h16x2(pack_h16(v0, 0.f)).x;
+                        }
+                        if (x0 < 0) wr[0] = 0.f;                                        // column left of the image (pad_left = 1)
+                        if (col_hi < HW) {                                              // columns right of the image
+#pragma unroll
+                            for (int c = 0; c < HW; ++c) if (c >= col_hi) wr[c] = 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < HW; ++c) wr[c] = 0.f;
+                    }
+                    if (hr + 1 < HR) {
+                        load_row(hr + 1);
+                    } else {
+                        t5::fence_before_thread_sync();
+                        t5::mbar_arrive(&bars[B_D1EMPTY + b]);                         // this thread has read its part of D1
+                    }
+                }
+                {
+                    float acc[kTW];
+#pragma unroll
+                    for (int c = 0; c < kTW; ++c) acc[c] = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int c = 0; c < kTW; ++c) acc[c] = fmaf(win[ky][2 * c + kx], wd[ky * 3 + kx], acc[c]);
+                    }
+                    float o[kTW];
+#pragma unroll
+                    for (int c = 0; c < kTW; ++c) o[c] = fminf(fmaxf(fmaf(acc[c], s2, t2), 0.f), 6.f);
+                    // output pixel m = hh*16 + c (rows 32..127 of the project GEMM's M tile carry no pixels)
+                    if (a2_pass > 0) wait_bar_relaxed(&bars[B_A2EMPTY + a], (a2_pass - 1) & 1);
+                    const int ck = (hh * kTW) >> 3;
+                    sts128(a2_row + (((ck) ^ (ch & 7)) << 4), pack8h(o));
+                    sts128(a2_row + (((ck + 1) ^ (ch & 7)) << 4), pack8h(o + 8));
+                }
+                }
                 t5::fence_proxy_async_smem();                   // generic-proxy writes of A2 -> visible to the tensor core
                 t5::mbar_arrive(&bars[B_A2FULL + a]);
                 if (threadIdx.x == 128) dbg_mark(p, 1, g, 2);
@@ -408,27 +488,40 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int prow = q * 32 + lane;
         const int ncols = p.Cout;
-        for (int t = blockIdx.x, tl = 0; t < p.num_tiles; t += gridDim.x, ++tl) {
+        int db = 0; uint32_t d2_pass = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             int r = t;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
             const int ty = r % p.tiles_y;
             const int n = r / p.tiles_y;
-            const int oy = ty * kTH + prow / kTW, ox = tx * kTW + prow % kTW;
-            const bool ok = oy < p.H && ox < p.W;
-            const long long pix = (static_cast<long long>(n) * p.H + oy) * p.W + ox;
+            const int oy = ty * TH + prow / kTW, ox = tx * kTW + prow % kTW;
+            const bool ok = prow < TH * kTW && oy < p.Ho && ox < p.Wo;
+            const long long pix = (static_cast<long long>(n) * p.Ho + oy) * p.Wo + ox;
             // the skip connection's first 32 channels are in flight while the last project GEMM of the tile retires
             uint4 res[4];
             if (p.residual && ok) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (k * 8 < ncols) res[k] = ldg_stream(p.residual + pix * p.Cout + k * 8);
             }
-            wait_bar_idle(&bars[B_D2FULL], tl & 1);
+            wait_bar_idle(&bars[B_D2FULL + db], d2_pass & 1);
             t5::fence_after_thread_sync();
-            const uint32_t taddr = tmem_d2 + lane_addr;
+            const uint32_t taddr = tmem_d2 + db * p.d2_cols + lane_addr;
             for (int c0 = 0; c0 < ncols; c0 += 32) {
                 uint32_t ra[16], rb[16];
                 t5::tmem_ld16(taddr + c0, ra);
                 if (c0 + 16 < ncols) t5::tmem_ld16(taddr + c0 + 16, rb);
+                if (p.wp_stack) {
+                    // hi-plane and lo-plane products were accumulated in two column halves of D2: add them here
+                    uint32_t la[16], lb[16];
+                    t5::tmem_ld16(taddr + p.np_mma + c0, la);
+                    if (c0 + 16 < ncols) t5::tmem_ld16(taddr + p.np_mma + c0 + 16, lb);
+                    t5::tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        ra[k] = __float_as_uint(__uint_as_float(ra[k]) + __uint_as_float(la[k]));
+                        if (c0 + 16 < ncols) rb[k] = __float_as_uint(__uint_as_float(rb[k]) + __uint_as_float(lb[k]));
+                    }
+                }
                 if (c0 > 0 && p.residual && ok) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) if (c0 + k * 8 < ncols) res[k] = ldg_stream(p.residual + pix * p.Cout + c0 + k * 8);
@@ -436,7 +529,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 t5::tmem_ld_wait();
                 if (c0 + 32 >= ncols) {                                      // last read of D2: the next tile's project GEMMs may start
                     t5::fence_before_thread_sync();
-                    t5::mbar_arrive(&bars[B_D2EMPTY]);
+                    t5::mbar_arrive(&bars[B_D2EMPTY + db]);
                 }
                 if (!ok) continue;
 #pragma unroll
@@ -469,6 +562,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     if (cb + 8 < ncols) stg_stream(o + 8, pack8h(v + 8));
                 }
             }
+            if (++db == p.d2_bufs) { db = 0; ++d2_pass; }
         }
     }
     t5::fence_before_thread_sync();
@@ -503,23 +597,36 @@ int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, 
 }
 
 // geometry-only part of the plan (shared by fused_block_supported / _param_floats / _plan)
-struct FusedGeom { int halo_w, halo_h, halo_rows, n1, np_mma, k_blocks, n_chunks, d1_bufs; bool ok; };
+struct FusedGeom { int halo_w, halo_h, halo_rows, n1, np_mma, k_blocks, n_chunks, d1_bufs, wp_stack, d2_bufs; bool ok; };
 FusedGeom fused_geom(const FusedBlockDesc& d) {
     FusedGeom g{};
-    g.halo_w = kTW + 2 * d.dil; g.halo_h = kTH + 2 * d.dil; g.halo_rows = g.halo_w * g.halo_h;
+    if (d.stride == 2) { g.halo_w = 2 * kTW + 1; g.halo_h = 5; }                   // 2x16 output tile: input rows 2r..2r+2, columns 2c..2c+2
+    else { g.halo_w = kTW + 2 * d.dil; g.halo_h = kTH + 2 * d.dil; }
+    g.halo_rows = g.halo_w * g.halo_h;
     g.n1 = ceil_div(g.halo_rows, 16) * 16;
     g.np_mma = ceil_div(d.Cout, 16) * 16;
     g.k_blocks = ceil_div(d.Cin, kKB);
     g.n_chunks = ceil_div(d.Cexp, kChunk);
     g.d1_bufs = (2 * g.n1 + g.np_mma <= 512) ? 2 : 1;
     g.ok = g.n1 <= 256 && g.np_mma <= 256 && g.n1 + g.np_mma <= 512;
+    // D2: (a) both planes of the split project weights as one 2*np-row operand (half the project MMAs, D2 = two column halves
+    // added in the epilogue) and (b) two D2 buffers, so that the epilogue of a tile overlaps the project GEMMs of the next one
+    // -- what bounds tiles of one or two chunks.  Whatever fits in the 512 columns next to the D1 stages; (b) first for short tiles.
+    const int room = 512 - g.d1_bufs * g.n1;
+    const bool short_tiles = g.n_chunks <= 2;
+    g.wp_stack = 0; g.d2_bufs = 1;
+    if (2 * g.np_mma <= 256 && 4 * g.np_mma <= room) { g.wp_stack = 1; g.d2_bufs = 2; }
+    else if (short_tiles && 2 * g.np_mma <= room) { g.d2_bufs = 2; }
+    else if (2 * g.np_mma <= 256 && 2 * g.np_mma <= room) { g.wp_stack = 1; }
+    else if (2 * g.np_mma <= room) { g.d2_bufs = 2; }
     return g;
 }
 
 }  // namespace
 
 bool fused_block_supported(const FusedBlockDesc& d) {
-    if (d.stride != 1 || (d.dil != 1 && d.dil != 2)) return false;
+    if (d.stride == 2) { if (d.dil != 1 || d.residual) return false; }
+    else if (d.stride != 1 || (d.dil != 1 && d.dil != 2)) return false;
     if (d.Cin % 8 || d.Cexp % 8 || d.Cout % 8) return false;
     return fused_geom(d).ok;
 }
@@ -539,37 +646,55 @@ int fused_block_plan(const FusedBlockDesc& d, int num_sms, FusedBlockPlan* plan)
     p.k_blocks = g.k_blocks; p.n_chunks = g.n_chunks;
     p.we_split = d.We_lo ? 1 : 0; p.wp_split = d.Wp_lo ? 1 : 0;
     p.np_mma = g.np_mma;
-    p.tiles_x = ceil_div(d.W, kTW); p.tiles_y = ceil_div(d.H, kTH); p.num_tiles = d.N * p.tiles_x * p.tiles_y;
+    p.wp_stack = (g.wp_stack && d.Wp_lo) ? 1 : 0;
+    p.d2_cols = (p.wp_stack ? 2 : 1) * p.np_mma;
+    p.d2_bufs = (g.d2_bufs == 2 || (!p.wp_stack && g.d1_bufs * g.n1 + 2 * g.np_mma <= 512)) ? 2 : 1;
+    if (d.stride == 2) {
+        p.Ho = ceil_div(d.H, 2); p.Wo = ceil_div(d.W, 2);
+        // TensorFlow 'SAME': total padding max((out-1)*2 + 3 - in, 0), the smaller half first
+        p.pad_top = d.pad_top >= 0 ? d.pad_top : std::max((p.Ho - 1) * 2 + 3 - d.H, 0) / 2;
+        p.pad_left = d.pad_left >= 0 ? d.pad_left : std::max((p.Wo - 1) * 2 + 3 - d.W, 0) / 2;
+    } else { p.Ho = d.H; p.Wo = d.W; p.pad_top = p.pad_left = d.dil; }
+    p.tiles_x = ceil_div(p.Wo, kTW); p.tiles_y = ceil_div(p.Ho, d.stride == 2 ? 2 : kTH); p.num_tiles = d.N * p.tiles_x * p.tiles_y;
     p.halo_w = g.halo_w; p.halo_h = g.halo_h; p.halo_rows = g.halo_rows; p.n1 = g.n1;
     p.s3 = d.s3; p.t3 = d.t3;
     p.residual = static_cast<const __half*>(d.residual); p.out = static_cast<__half*>(d.out);
     p.dbg = static_cast<unsigned long long*>(d.debug_timeline);
     p.par = d.params;
-    { const char* e = getenv("AMS_X_FUSED_SKIP"); p.x_skip = e ? atoi(e) : 0; }
     p.d1_bufs = g.d1_bufs;
     p.d2_col = p.d1_bufs * p.n1;
     p.tmem_cols = 512;
     p.x_slab = p.n1 * 64;
     p.we_plane = kChunk * 64; p.we_unit = p.we_plane * (p.we_split ? 2 : 1);
-    p.wp_plane = p.np_mma * 64; p.wp_unit = p.wp_plane * (p.wp_split ? 2 : 1);
+    p.wp_plane = p.np_mma * 64; p.wp_kb = p.wp_plane * (p.wp_split ? 2 : 1);
     // Rings as deep as shared memory allows.  Priorities: (1) the expand ring holds at least one whole chunk (k_blocks units) --
     // otherwise every expand GEMM stalls on a TMA round trip in its middle; (2) two A2 buffers, so that the project GEMM of a
-    // chunk is off the compute warps' critical path; (3) a whole chunk of project weights (4 units); (4) deeper rings.
+    // chunk is off the compute warps' critical path; (3) a whole chunk of project weights in flight; (4) deeper rings.
+    // Project weights come as whole chunks (4 k-blocks behind ONE barrier) where two such units fit: the MMA-issuing warp
+    // shares its scheduler with two compute warps and every wait / commit / descriptor build costs it ~0.1 us.
     bool fits = false;
     int best_score = -1;
+    p.x_buf = (p.k_blocks * p.x_slab + 1023u) & ~1023u;
+    static const int grp_hi = [] { const char* e = getenv("AMS_FUSED_WP_GROUP"); return (e && e[0] == '4') ? 4 : 1; }();
+    for (int grp = grp_hi; grp >= 1; grp -= 3)
+    for (int xbf = 1; xbf <= 2; ++xbf)
     for (int a2 = 1; a2 <= 2; ++a2)
         for (int we = 2; we <= kMaxWe; ++we)
             for (int wp = 2; wp <= kMaxWp; ++wp) {
-                const size_t total = 1024 + size_t(p.k_blocks) * p.x_slab + size_t(we) * p.we_unit + size_t(wp) * p.wp_unit + size_t(a2) * 2 * 16384 +
+                if (grp == 4 && wp > 3) continue;
+                const size_t total = 1024 + size_t(xbf) * p.x_buf + size_t(we) * p.we_unit + size_t(wp) * grp * p.wp_kb + size_t(a2) * 2 * 16384 +
                                      4096 /* alignment slack + barriers */;
                 if (total > 227 * 1024) continue;
-                const int score = (we >= p.k_blocks ? 1000 : 0) + (a2 == 2 ? 400 : 0) + (wp >= 4 ? 200 : 0) + std::min(we, 2 * p.k_blocks) * 8 + std::min(wp, 8) * 4;
-                if (score > best_score) { best_score = score; p.we_slots = we; p.wp_slots = wp; p.a2_bufs = a2; fits = true; }
+                // a second X buffer (the next tile's input lands while this tile computes) matters when a tile has few chunks
+                const int score = (we >= p.k_blocks ? 1000 : 0) + (a2 == 2 ? 400 : 0) + (wp * grp >= 4 ? 200 : 0) + (xbf == 2 ? (p.n_chunks <= 2 ? 300 : 100) : 0) +
+                                  (grp == 4 ? 150 : 0) + std::min(we, 2 * p.k_blocks) * 8 + std::min(wp * grp, 8) * 4;
+                if (score > best_score) { best_score = score; p.we_slots = we; p.wp_slots = wp; p.a2_bufs = a2; p.x_bufs = xbf; p.wp_group = grp; fits = true; }
             }
+    p.wp_unit = p.wp_group * p.wp_kb;
     if (fits) {
         uint32_t off = 0;
         auto take = [&](uint32_t bytes) { const uint32_t at = off; off = (off + bytes + 1023u) & ~1023u; return at; };
-        p.off_x = take(p.k_blocks * p.x_slab);
+        p.off_x = take(p.x_bufs * p.x_buf);
         p.off_we = take(p.we_unit * p.we_slots);
         p.off_wp = take(p.wp_unit * p.wp_slots);
         p.off_a2 = take(p.a2_bufs * 2 * 16384);
@@ -604,8 +729,9 @@ int fused_block_plan(const FusedBlockDesc& d, int num_sms, FusedBlockPlan* plan)
     }
     static bool attr = false;
     if (!attr) {
-        AMS_CUDA_CHECK(cudaFuncSetAttribute((fused_block_kernel<1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        AMS_CUDA_CHECK(cudaFuncSetAttribute((fused_block_kernel<2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute((fused_block_kernel<1, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute((fused_block_kernel<2, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        AMS_CUDA_CHECK(cudaFuncSetAttribute((fused_block_kernel<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
     return 0;
@@ -613,10 +739,12 @@ int fused_block_plan(const FusedBlockDesc& d, int num_sms, FusedBlockPlan* plan)
 
 int fused_block_launch(const FusedBlockPlan& plan, cudaStream_t s) {
     const FusedParams& p = *reinterpret_cast<const FusedParams*>(plan.params);
-    if (p.dil == 1)
-        AMS_LAUNCH((fused_block_kernel<1>), plan.grid, kThreads, plan.smem_bytes, s, plan.tmX, plan.tmWe, plan.tmWeLo, plan.tmWp, plan.tmWpLo, p);
+    if (plan.d.stride == 2)
+        AMS_LAUNCH((fused_block_kernel<1, 2>), plan.grid, kThreads, plan.smem_bytes, s, plan.tmX, plan.tmWe, plan.tmWeLo, plan.tmWp, plan.tmWpLo, p);
+    else if (p.dil == 1)
+        AMS_LAUNCH((fused_block_kernel<1, 1>), plan.grid, kThreads, plan.smem_bytes, s, plan.tmX, plan.tmWe, plan.tmWeLo, plan.tmWp, plan.tmWpLo, p);
     else
-        AMS_LAUNCH((fused_block_kernel<2>), plan.grid, kThreads, plan.smem_bytes, s, plan.tmX, plan.tmWe, plan.tmWeLo, plan.tmWp, plan.tmWpLo, p);
+        AMS_LAUNCH((fused_block_kernel<2, 1>), plan.grid, kThreads, plan.smem_bytes, s, plan.tmX, plan.tmWe, plan.tmWeLo, plan.tmWp, plan.tmWpLo, p);
     return 0;
 }
 

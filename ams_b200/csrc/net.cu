@@ -337,6 +337,7 @@ static int build_plan(Net* net, Plan* p, bool need_backward) {
             const LayerDef& e = L[i]; const LayerDef& dw = L[i + 1]; const LayerDef& pr = L[i + 2];
             FusedBlockDesc f;
             f.N = N; f.H = e.out_h; f.W = e.out_w; f.Cin = e.cin; f.Cexp = e.cout; f.Cout = pr.cout; f.stride = dw.stride; f.dil = dw.dil;
+            f.pad_top = dw.pad_top; f.pad_left = dw.pad_left;
             f.x = p->buf[e.input].y;
             f.We = net->wpool + e.wfwd_off; f.We_lo = e.wlo_off >= 0 ? net->wpool + e.wlo_off : nullptr; f.ld_we = e.ld_fwd;
             f.Wp = net->wpool + pr.wfwd_off; f.Wp_lo = pr.wlo_off >= 0 ? net->wpool + pr.wlo_off : nullptr; f.ld_wp = pr.ld_fwd;

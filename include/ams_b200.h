@@ -254,10 +254,11 @@ int ams_debug_dw_bwd_tile(int n, int h, int w, int c, int ho, int wo, int stride
 int ams_op_conv1x1(const void* a_16, const void* w_16 /*[N][K]*/, int M, int N, int K, const float* scale,
                    const float* shift, const float* rowbias, int rows_per_image, const void* residual_16, int act,
                    void* out, int out_fp32, int ldc, int grad_types, const void* w_lo_16, void* stream);
-/* one stride-1 inverted-residual block of the FROZEN graph in a single kernel (ams_b200/csrc/fused_block.cu):
+/* one inverted-residual block of the FROZEN graph in a single kernel (ams_b200/csrc/fused_block.cu): stride 1 with
+ * dilation 1 | 2, or stride 2 with dilation 1 (output [n,ceil(h/2),ceil(w/2),cout], TensorFlow 'SAME' padding, no skip):
  * out = BN3(project(relu6(BN2(depthwise3x3_dil(relu6(BN1(expand(x)))))))) [+ x]; x [n,h,w,cin] fp16; we [cexp][cin] and
  * wp [cout][cexp] fp16 (+ optional low planes of the split weights); wd [3,3,cexp] fp32; s1..s3 / t1..t3 folded BN scale / shift */
-int ams_op_fused_block(const void* x_f16, int n, int h, int w_, int cin, int cexp, int cout, int dilation, const void* we_f16,
+int ams_op_fused_block(const void* x_f16, int n, int h, int w_, int cin, int cexp, int cout, int dilation, int stride, const void* we_f16,
                        const void* we_lo_f16, const float* s1, const float* t1, const float* wd, const float* s2, const float* t2,
                        const void* wp_f16, const void* wp_lo_f16, const float* s3, const float* t3, int residual, void* out_f16,
                        void* stream);

@@ -435,17 +435,20 @@ def test_adam_bit_exact():
         assert np.array_equal(p.cpu().numpy(), st.vars['v']), 'params differ at step %d' % it
 
 
-@pytest.mark.parametrize('n,h,w,cin,cout,dil,res,split', [
-    (1, 8, 16, 64, 64, 1, True, True),          # exactly one tile
-    (2, 33, 65, 64, 64, 1, True, True),         # blocks 7-9: ragged tiles in both directions
-    (1, 33, 65, 64, 96, 1, False, True),        # block 10
-    (2, 17, 33, 96, 96, 1, True, True),         # blocks 11-12 (3 k-blocks, 9 chunks)
-    (1, 33, 65, 160, 160, 2, True, True),       # blocks 14-15: dilation 2 (20-wide halo rows, single TMEM stage)
-    (1, 33, 65, 96, 160, 1, False, True),       # block 13: single TMEM stage at dilation 1
-    (1, 40, 70, 24, 24, 1, True, True),         # block 2: Cin 24 (zero-filled k-block), Cexp 144 (padded chunk), Cout 24 (N granule)
-    (1, 30, 50, 32, 32, 1, True, True),         # blocks 4-5
+@pytest.mark.parametrize('n,h,w,cin,cout,dil,res,split,stride', [
+    (1, 8, 16, 64, 64, 1, True, True, 1),          # exactly one tile
+    (2, 33, 65, 64, 64, 1, True, True, 1),         # blocks 7-9: ragged tiles in both directions
+    (1, 33, 65, 64, 96, 1, False, True, 1),        # block 10
+    (2, 17, 33, 96, 96, 1, True, True, 1),         # blocks 11-12 (3 k-blocks, 4.5 chunks)
+    (1, 33, 65, 160, 160, 2, True, True, 1),       # blocks 14-15: dilation 2 (20-wide halo rows, single TMEM stage)
+    (1, 33, 65, 96, 160, 1, False, True, 1),       # block 13: single TMEM stage at dilation 1
+    (1, 40, 70, 24, 24, 1, True, True, 1),         # block 2: Cin 24 (zero-filled k-block), Cexp 144 (padded chunk), Cout 24 (N granule)
+    (1, 30, 50, 32, 32, 1, True, True, 1),         # blocks 4-5
+    (2, 65, 129, 16, 24, 1, False, True, 2),       # block 1: stride 2, odd input size (pad 1 / 1), Cexp 96 (one padded chunk)
+    (1, 64, 96, 24, 32, 1, False, True, 2),        # block 3: stride 2, even input size (pad 0 / 1), two chunks
+    (1, 33, 65, 32, 64, 1, False, True, 2),        # block 6
 ])
-def test_fused_inverted_residual_block(n, h, w, cin, cout, dil, res, split):
+def test_fused_inverted_residual_block(n, h, w, cin, cout, dil, res, split, stride):
     """The block-fused frozen-inference kernel against the same block computed layer by layer with the storage rounding
     of the unfused path (fp16 after the expand conv, after the depthwise conv and at the block output; split fp16 weights
     where the layer has at most 256 output channels)."""
@@ -466,17 +469,18 @@ def test_fused_inverted_residual_block(n, h, w, cin, cout, dil, res, split):
     we_eff = we_hi + (we_lo if we_split else 0.0)
     wp_eff = wp_hi + (wp_lo if split else 0.0)
     y1 = ac_round(((x.reshape(-1, cin).double() @ we_eff.double().t()).float().reshape(n, h, w, cexp) * s1 + t1).clamp(0, 6))
-    y2 = ac_round((_dw_ref(y1, wd, 1, dil) * s2 + t2).clamp(0, 6))
-    y3 = (y2.reshape(-1, cexp).double() @ wp_eff.double().t()).float().reshape(n, h, w, cout) * s3 + t3
+    y2 = ac_round((_dw_ref(y1, wd, stride, dil) * s2 + t2).clamp(0, 6))
+    ho, wo = y2.shape[1], y2.shape[2]
+    y3 = (y2.reshape(-1, cexp).double() @ wp_eff.double().t()).float().reshape(n, ho, wo, cout) * s3 + t3
     ref = y3 + x if res else y3
-    out = torch.full((n, h, w, cout), float('nan'), dtype=AC, device=DEV)
+    out = torch.full((n, ho, wo, cout), float('nan'), dtype=AC, device=DEV)
     dv = lambda t: P(t.to(DEV)) if t is not None else None
     hv = lambda t: P(t.to(DEV, AC)) if t is not None else None
-    call(L.ams_op_fused_block, hv(x), n, h, w, cin, cexp, cout, dil, hv(we_hi), hv(we_lo), dv(s1), dv(t1), dv(wd), dv(s2), dv(t2),
+    call(L.ams_op_fused_block, hv(x), n, h, w, cin, cexp, cout, dil, stride, hv(we_hi), hv(we_lo), dv(s1), dv(t1), dv(wd), dv(s2), dv(t2),
          hv(wp_hi), hv(wp_lo), dv(s3), dv(t3), 1 if res else 0, P(out), stream_ptr())
     torch.cuda.synchronize()
     # an fp16 flip of an intermediate (accumulation order of the tensor core vs the fp64 reference) moves the output by ~1e-3
-    ok, _ = err_stats('fused block n%d %dx%d cin%d cout%d d%d res%d' % (n, h, w, cin, cout, dil, res), out, ref, 4 * AULP, 6e-3)
+    ok, _ = err_stats('fused block n%d %dx%d cin%d cout%d d%d s%d res%d' % (n, h, w, cin, cout, dil, stride, res), out, ref, 4 * AULP, 6e-3)
     assert ok
     rel = float((out.float().cpu() - ref).norm() / ref.norm())
     assert rel < 1e-3
