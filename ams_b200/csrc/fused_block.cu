@@ -19,9 +19,13 @@
 //              ReLU6 -> fp16 -> 16-byte stores into the MN-major (pixel-contiguous) swizzled A operand of the project GEMM.
 //   tcgen05  : D2[128 pixels x Cout] += A2[128 px x 128 ch] * Wp^T (+ Wp_lo^T), accumulated over the channel chunks
 //   epilogue : D2 -> folded BN3 (+ residual x) -> fp16 -> HBM
-// A persistent CTA owns one 8x16-pixel output tile at a time; warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 =
-// 256 compute threads (TMEM lane quarter x upper/lower half of the tile rows).  X tile: 4-D TMA with zero fill outside
-// the image, K-major SWIZZLE_64B (32-channel k-blocks); weights stream through two rings of 32-k units.
+// A persistent CTA (four warpgroups, setmaxnreg per role) owns one output tile at a time: {TMA producer, MMA issuer} | 2 x 4
+// compute warps (TMEM lane quarter x upper/lower half of the tile rows) | 4 epilogue warps, one tile behind.  Stride-1
+// blocks (dilation 1 | 2): 8x16 output pixels, halo (8+2d) x (16+2d).  Stride-2 blocks: 2x16 output pixels from a 5x33
+// input halo (32 of the project GEMM's 128 rows carry pixels; the tensor pipe is idle most of the time anyway).
+// X tile: 4-D TMA with zero fill outside the image, K-major SWIZZLE_64B (32-channel k-blocks), two buffers where they fit;
+// weights stream through two rings of 32-k units; D1 / A2 / D2 are double-buffered where TMEM / shared memory allow; where
+// N <= 256 both planes of the split project weights are ONE stacked operand (D2 = two column halves, added in the epilogue).
 // Every stored value goes through the same fp16 rounding points as the unfused path (expand output, depthwise output,
 // block output), so the two paths agree up to the accumulation order.
 //
