@@ -62,6 +62,7 @@ struct FusedParams {
     int tiles_x, tiles_y, num_tiles;
     int halo_w, halo_h, halo_rows, n1;        // n1 = halo_rows rounded up to 16 = UMMA N of the expand GEMM
     int d1_bufs, a2_bufs, we_slots, wp_slots, x_bufs, d2_bufs;
+    int resident;                 // the whole block's weights stay in the rings (each ring = exactly one tile's units): loaded once per CTA
     int wp_group;                 // 32-channel k-blocks of project weights per ring unit / barrier (4 = a whole chunk, else 1)
     uint32_t tmem_cols, d2_col, d2_cols;       // first D2 column; columns per D2 buffer
     const float* par;             // [n_chunks][13][128]: s1 t1 wd[9] s2 t2, zero beyond Cexp
@@ -188,11 +189,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                     if (++xb == p.x_bufs) { xb = 0; ++x_pass; }
                 }
                 for (int kb = 0; kb < p.k_blocks; ++kb) {
-                    if (we_pass > 0) wait_bar_relaxed(&bars[B_WEEMPTY + we_s], (we_pass - 1) & 1);
-                    uint8_t* dst = smWe + we_s * p.we_unit;
-                    t5::mbar_arrive_expect_tx(&bars[B_WEFULL + we_s], p.we_unit);
-                    t5::tma_load_2d(dst, &tmWe, &bars[B_WEFULL + we_s], kb * kKB, j_e * kChunk);
-                    if (p.we_split) t5::tma_load_2d(dst + p.we_plane, &tmWeLo, &bars[B_WEFULL + we_s], kb * kKB, j_e * kChunk);
+                    if (!(p.resident && we_pass > 0)) {                                  // resident weights: first tile only
+                        if (we_pass > 0) wait_bar_relaxed(&bars[B_WEEMPTY + we_s], (we_pass - 1) & 1);
+                        uint8_t* dst = smWe + we_s * p.we_unit;
+                        t5::mbar_arrive_expect_tx(&bars[B_WEFULL + we_s], p.we_unit);
+                        t5::tma_load_2d(dst, &tmWe, &bars[B_WEFULL + we_s], kb * kKB, j_e * kChunk);
+                        if (p.we_split) t5::tma_load_2d(dst + p.we_plane, &tmWeLo, &bars[B_WEFULL + we_s], kb * kKB, j_e * kChunk);
+                    }
                     if (++we_s == p.we_slots) { we_s = 0; ++we_pass; }
                 }
                 if (++j_e == p.n_chunks) { j_e = 0; ++tl_e; }
@@ -201,12 +204,14 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const int kbs = min(kChunk / kKB, (p.Cexp - j_p * kChunk + kKB - 1) / kKB);      // k-blocks of this chunk that hold channels
                 for (int u0 = 0; u0 < kbs; u0 += p.wp_group) {
                     const int nkb = min(p.wp_group, kbs - u0);
-                    if (wp_pass > 0) wait_bar_relaxed(&bars[B_WPEMPTY + wp_s], (wp_pass - 1) & 1);
-                    uint8_t* dst = smWp + wp_s * p.wp_unit;
-                    t5::mbar_arrive_expect_tx(&bars[B_WPFULL + wp_s], nkb * p.wp_kb);
-                    for (int u = 0; u < nkb; ++u) {
-                        t5::tma_load_2d(dst + u * p.wp_kb, &tmWp, &bars[B_WPFULL + wp_s], j_p * kChunk + (u0 + u) * kKB, 0);
-                        if (p.wp_split) t5::tma_load_2d(dst + u * p.wp_kb + p.wp_plane, &tmWpLo, &bars[B_WPFULL + wp_s], j_p * kChunk + (u0 + u) * kKB, 0);
+                    if (!(p.resident && wp_pass > 0)) {
+                        if (wp_pass > 0) wait_bar_relaxed(&bars[B_WPEMPTY + wp_s], (wp_pass - 1) & 1);
+                        uint8_t* dst = smWp + wp_s * p.wp_unit;
+                        t5::mbar_arrive_expect_tx(&bars[B_WPFULL + wp_s], nkb * p.wp_kb);
+                        for (int u = 0; u < nkb; ++u) {
+                            t5::tma_load_2d(dst + u * p.wp_kb, &tmWp, &bars[B_WPFULL + wp_s], j_p * kChunk + (u0 + u) * kKB, 0);
+                            if (p.wp_split) t5::tma_load_2d(dst + u * p.wp_kb + p.wp_plane, &tmWpLo, &bars[B_WPFULL + wp_s], j_p * kChunk + (u0 + u) * kKB, 0);
+                        }
                     }
                     if (++wp_s == p.wp_slots) { wp_s = 0; ++wp_pass; }
                 }
@@ -232,7 +237,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             t5::fence_after_thread_sync();
             const uint32_t d = tmem_base + b_e * p.n1;
             for (int kb = 0; kb < p.k_blocks; ++kb) {
-                wait_bar_relaxed(&bars[B_WEFULL + we_s], we_pass & 1);
+                if (!(p.resident && we_pass > 0)) wait_bar_relaxed(&bars[B_WEFULL + we_s], we_pass & 1);     // resident weights: arrived during the first tile
                 t5::fence_after_thread_sync();
                 if (lane == 0 && kb == 0) dbg_mark(p, 0, g, 0);
                 {
@@ -248,7 +253,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         t5::mma_f16_ss_warp(d, da0 + 2 * k, db0 + 2 * k, idesc1, (kb | k) != 0);
                         if (p.we_split) t5::mma_f16_ss_warp(d, da0 + lo + 2 * k, db0 + 2 * k, idesc1, 1u);
                     }
-                    t5::mma_commit_warp(&bars[B_WEEMPTY + we_s]);
+                    if (!p.resident) t5::mma_commit_warp(&bars[B_WEEMPTY + we_s]);
                 }
                 if (lane == 0 && kb == p.k_blocks - 1) dbg_mark(p, 0, g, 2);
                 if (++we_s == p.we_slots) { we_s = 0; ++we_pass; }
@@ -270,7 +275,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const int kbs = min(kChunk / kKB, (p.Cexp - j * kChunk + kKB - 1) / kKB);
             for (int u0 = 0; u0 < kbs; u0 += p.wp_group) {
                 const int nkb = min(p.wp_group, kbs - u0);
-                wait_bar_relaxed(&bars[B_WPFULL + wp_s], wp_pass & 1);
+                if (!(p.resident && wp_pass > 0)) wait_bar_relaxed(&bars[B_WPFULL + wp_s], wp_pass & 1);
                 t5::fence_after_thread_sync();
                 if (lane == 0 && u0 == 0) dbg_mark(p, 0, g, 1);
                 {
@@ -286,7 +291,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                             if (p.wp_split && !p.wp_stack) t5::mma_f16_ss_warp(tmem_d2b, da0 + 256 * u + 128 * k, db0 + kbstep * u + lo + 2 * k, idesc2, 1u);
                         }
                     }
-                    t5::mma_commit_warp(&bars[B_WPEMPTY + wp_s]);
+                    if (!p.resident) t5::mma_commit_warp(&bars[B_WPEMPTY + wp_s]);
                 }
                 if (lane == 0 && u0 + nkb >= kbs) dbg_mark(p, 0, g, 3);
                 if (++wp_s == p.wp_slots) { wp_s = 0; ++wp_pass; }
@@ -694,6 +699,21 @@ int fused_block_plan(const FusedBlockDesc& d, int num_sms, FusedBlockPlan* plan)
                                   (grp == 4 ? 150 : 0) + std::min(we, 2 * p.k_blocks) * 8 + std::min(wp * grp, 8) * 4;
                 if (score > best_score) { best_score = score; p.we_slots = we; p.wp_slots = wp; p.a2_bufs = a2; p.x_bufs = xbf; p.wp_group = grp; fits = true; }
             }
+    p.resident = 0;
+    {
+        // short blocks: ALL weights of the block stay resident (each ring = exactly the units of one tile, so the slot of a unit
+        // is the same in every tile): no weight TMA, no FULL polls and no EMPTY commits after the first tile -- the barrier
+        // polls are what the MMA-issuing warp spends most of its time on for tiles of one or two chunks
+        static const bool off = [] { const char* e = getenv("AMS_FUSED_NO_RESIDENT"); return e && e[0] == '1'; }();
+        const int we_all = p.n_chunks * p.k_blocks, wp_all = ceil_div(d.Cexp, kKB);
+        if (!off && p.n_chunks <= 2 && we_all <= kMaxWe && wp_all <= kMaxWp) {
+            for (int xbf = 2; xbf >= 1 && !p.resident; --xbf)
+                for (int a2 = 2; a2 >= 1 && !p.resident; --a2) {
+                    const size_t total = 1024 + size_t(xbf) * p.x_buf + size_t(we_all) * p.we_unit + size_t(wp_all) * p.wp_kb + size_t(a2) * 2 * 16384 + 4096;
+                    if (total <= 227 * 1024) { p.resident = 1; p.we_slots = we_all; p.wp_slots = wp_all; p.a2_bufs = a2; p.x_bufs = xbf; p.wp_group = 1; fits = true; }
+                }
+        }
+    }
     p.wp_unit = p.wp_group * p.wp_kb;
     if (fits) {
         uint32_t off = 0;
