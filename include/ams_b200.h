@@ -179,7 +179,7 @@ int ams_syncbn_connect(ams_net* net, const void* all_handles, int count);
 int ams_syncbn_enable(ams_net* net, int on);
 int ams_syncbn_status(ams_net* net, unsigned int* out_epoch, unsigned int* out_error);
 
-/* Frozen inference runs the stride-1 inverted-residual blocks whose project conv has <= 256 output channels (12 of the 17)
+/* Frozen inference runs the inverted-residual blocks (stride 1 and 2) whose project conv has <= 256 output channels (15 of the 17)
  * as ONE kernel each (expand GEMM with the expanded channels on the TMEM lanes -> BN/ReLU6 and the depthwise 3x3 in
  * registers, one channel per thread -> MN-major shared-memory A operand -> project GEMM): the 6C-wide tensors never reach
  * HBM and ams_get_activation() has nothing to return for the expand / depthwise layers of those blocks.  Same fp16
