@@ -100,9 +100,16 @@ stem_bwd_filter_kernel(const T* __restrict__ in, StemGeom g, const bf16* __restr
     pdl_entry();
     __shared__ float s_in[3][kStemRowFloats];
     __shared__ __align__(16) float s_dz[kStemBwdPix][32];
-    const int k = threadIdx.x / 8, co4 = threadIdx.x % 8;
-    const int ky = k / 9, kxc = k % 9;                                  // kxc = kx*3 + c
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    __shared__ float s_red[6][864];
+    // thread = (pixel lane of 6, filter row ky, input channel c, group of 8 output channels): per pixel 3 input words + two
+    // 128-bit dz reads feed 24 FMAs (the first version read one word + one 128-bit vector per 4 FMAs and kept the
+    // shared-memory pipe 87 % busy: ncu "Mem Busy")
+    const int cg = threadIdx.x & 3, c = (threadIdx.x >> 2) % 3, ky = (threadIdx.x / 12) % 3, pl = threadIdx.x / 36;
+    float acc[3][8];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[kx][q] = 0.f;
     const int total_rows = g.N * g.Ho;
     const int r_begin = blockIdx.x * rows_per_block, r_end = min(r_begin + rows_per_block, total_rows);
     const float pad_t = __fsub_rn(__fmul_rn(g.norm_scale, g.pad_value), g.norm_shift);
@@ -137,18 +144,34 @@ stem_bwd_filter_kernel(const T* __restrict__ in, StemGeom g, const bf16* __restr
                 *reinterpret_cast<float4*>(&s_dz[pp][c8 * 8 + 4]) = make_float4(f[4], f[5], f[6], f[7]);
             }
             __syncthreads();
-            const float* a_ptr = &s_in[ky][kxc];
-#pragma unroll 4
-            for (int pp = 0; pp < np; ++pp) {
-                const float a = a_ptr[pp * 6];
-                const float4 d = *reinterpret_cast<const float4*>(&s_dz[pp][co4 * 4]);
-                acc[0] = fmaf(a, d.x, acc[0]); acc[1] = fmaf(a, d.y, acc[1]);
-                acc[2] = fmaf(a, d.z, acc[2]); acc[3] = fmaf(a, d.w, acc[3]);
+            const float* a_ptr = &s_in[ky][c];
+#pragma unroll 2
+            for (int pp = pl; pp < np; pp += 6) {
+                const float a0 = a_ptr[pp * 6], a1 = a_ptr[pp * 6 + 3], a2 = a_ptr[pp * 6 + 6];
+                const float4 d0 = *reinterpret_cast<const float4*>(&s_dz[pp][cg * 8]);
+                const float4 d1 = *reinterpret_cast<const float4*>(&s_dz[pp][cg * 8 + 4]);
+                const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    acc[0][q] = fmaf(a0, d[q], acc[0][q]);
+                    acc[1][q] = fmaf(a1, d[q], acc[1][q]);
+                    acc[2][q] = fmaf(a2, d[q], acc[2][q]);
+                }
             }
         }
     }
-    float* o = partial + static_cast<long long>(blockIdx.x) * 864 + k * 32 + co4 * 4;
-    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2]; o[3] = acc[3];
+    // the six pixel lanes are summed in a fixed order; partial[block][k = ky*9 + kx*3 + c][32]
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s_red[pl][(ky * 9 + kx * 3 + c) * 32 + cg * 8 + q] = acc[kx][q];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 864; i += kStemBwdThreads) {
+        float t = s_red[0][i];
+#pragma unroll
+        for (int l = 1; l < 6; ++l) t += s_red[l][i];
+        partial[static_cast<long long>(blockIdx.x) * 864 + i] = t;
+    }
 }
 
 // out[i] = sum over chunks of partial[chunk][i]; one warp per output, fixed lane assignment (deterministic)
