@@ -100,6 +100,7 @@ ams_net* ams_create(const ams_config* cfg) {
     if (cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_pool, cudaEventDisableTiming) != cudaSuccess) return fail("event");
+    if (cudaEventCreateWithFlags(&net->ev_dwred, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_bucket, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaEventCreateWithFlags(&net->ev_bucket_main, cudaEventDisableTiming) != cudaSuccess) return fail("event");
     if (cudaStreamCreateWithFlags(&net->split_ss.main, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
@@ -211,6 +212,7 @@ void ams_destroy(ams_net* h) {
     if (net->ev_fork) cudaEventDestroy(net->ev_fork);
     if (net->ev_join) cudaEventDestroy(net->ev_join);
     if (net->ev_pool) cudaEventDestroy(net->ev_pool);
+    if (net->ev_dwred) cudaEventDestroy(net->ev_dwred);
     if (net->ev_bucket) cudaEventDestroy(net->ev_bucket);
     if (net->ev_bucket_main) cudaEventDestroy(net->ev_bucket_main);
     if (net->split_ss.main) cudaStreamDestroy(net->split_ss.main);

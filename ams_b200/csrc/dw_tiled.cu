@@ -721,7 +721,14 @@ long long dw_bwd_fused_rows(const Conv2dGeom& g) {
     return static_cast<long long>(g.N) * t.nty * t.ntx;
 }
 
-int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s) {
+int dw_conv_bwd_reduce(const DwBwdFused& a, const Conv2dGeom& g, cudaStream_t s) {
+    const DwBwdTile t = pick_bwd_tile(g, kBwdSmemCap);
+    const long long rows = static_cast<long long>(g.N) * t.nty * t.ntx;
+    AMS_LAUNCH((dw_reduce_rows_kernel), ceil_div(9 * g.C, 32), 1024, 0, s, a.dw_partial, static_cast<int>(rows), 9 * g.C, a.dw);
+    return 0;
+}
+
+int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s, bool defer_reduce) {
     AMS_REQUIRE(dw_tiled_supported(g), "fused depthwise backward: unsupported channels / stride / dilation");
     const DwBwdTile t = pick_bwd_tile(g, kBwdSmemCap);
     AMS_REQUIRE(t.blocks > 0, "fused depthwise backward: no tile fits shared memory");
@@ -745,7 +752,7 @@ int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, c
     else if (g.pad_left & 1) rc = launch_bwd_cb<2, 1, 1>(p, t, s);
     else rc = launch_bwd_cb<2, 1, 0>(p, t, s);
     if (rc) return rc;
-    AMS_LAUNCH((dw_reduce_rows_kernel), ceil_div(9 * g.C, 32), 1024, 0, s, a.dw_partial, static_cast<int>(rows), 9 * g.C, a.dw);
+    if (!defer_reduce) AMS_LAUNCH((dw_reduce_rows_kernel), ceil_div(9 * g.C, 32), 1024, 0, s, a.dw_partial, static_cast<int>(rows), 9 * g.C, a.dw);
     if (rows_out) *rows_out = static_cast<int>(rows);
     return 0;
 }

@@ -57,7 +57,10 @@ struct DwBwdFused {
     double* bn_partial;                     // [rows][2][C]
 };
 long long dw_bwd_fused_rows(const Conv2dGeom& g);
-int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s);
+// reduce_stream != null: the fixed-order reduction of the per-tile filter-gradient partials is NOT launched; the caller runs
+// dw_conv_bwd_reduce(a, g, stream) itself (on a side stream: nothing in the backward chain reads the filter gradient)
+int dw_conv_bwd_fused(const DwBwdFused& a, const Conv2dGeom& g, int* rows_out, cudaStream_t s, bool defer_reduce = false);
+int dw_conv_bwd_reduce(const DwBwdFused& a, const Conv2dGeom& g, cudaStream_t s);
 
 // ---- cross-GPU BatchNorm statistics (SURVEY 8e caveat 2: the reference normalises over the WHOLE batch in one process)
 // One exchange per BatchNorm layer and direction, inside the finalize kernels: every rank pushes its per-channel fp64

@@ -559,7 +559,7 @@ int net_backward(Net* net, Plan* p, bool normalize) {
     // Filter gradients of the 1x1 convs: nothing downstream in the backward chain reads them, so outside profiling
     // they go to a side stream (fork after their dz is ready, one join at the end) and overlap with the chain.
     const bool side = !net->prof.enabled && net->side_stream != nullptr;
-    bool forked = false, pool_bwd_pending = false;
+    bool forked = false, pool_bwd_pending = false, dw_reduce_pending = false;
     static const bool x_skip_wgrad = [] { const char* e = getenv("AMS_X_SKIP_WGRAD"); return e && e[0] == '1'; }();   // TIMING EXPERIMENT ONLY
     auto wgrad_on_side = [&](const WgradPlan& wp) -> int {
         if (x_skip_wgrad) return 0;
@@ -607,7 +607,20 @@ int net_backward(Net* net, Plan* p, bool normalize) {
             f.w = net->params + d.w_off; f.gout = p->buf[d.input].g; f.dw = net->grads + d.w_off;
             f.dw_partial = p->red_ws; f.dw_partial_floats = p->red_ws_floats; f.bn_partial = p->bn_ws;
             const double ib = 2.0 * p->N * d.in_h * d.in_w * d.cin;
-            PROF("dw_bwd_fused", 2.0 * tb + 2.0 * ib, dw_conv_bwd_fused(f, g, &p->pending_bn_rows, s));
+            if (side) {
+                // the per-tile filter-gradient partials are reduced on the side stream (nothing in the chain reads dW); the
+                // NEXT fused depthwise backward reuses red_ws, so it waits for this reduction first
+                if (dw_reduce_pending) { AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_dwred, 0)); dw_reduce_pending = false; }
+                if (dw_conv_bwd_fused(f, g, &p->pending_bn_rows, s, true)) return -1;
+                AMS_CUDA_CHECK(cudaEventRecord(net->ev_fork, s));
+                AMS_CUDA_CHECK(cudaStreamWaitEvent(net->side_stream, net->ev_fork, 0));
+                forked = true;
+                if (dw_conv_bwd_reduce(f, g, net->side_stream)) return -1;
+                AMS_CUDA_CHECK(cudaEventRecord(net->ev_dwred, net->side_stream));
+                dw_reduce_pending = true;
+            } else {
+                PROF("dw_bwd_fused", 2.0 * tb + 2.0 * ib, dw_conv_bwd_fused(f, g, &p->pending_bn_rows, s));
+            }
             continue;
         }
         static const bool x_skip_bfin = [] { const char* e = getenv("AMS_X_SKIP_BWD_FINALIZE"); return e && e[0] == '1'; }();
@@ -658,9 +671,11 @@ int net_backward(Net* net, Plan* p, bool normalize) {
         } else if (d.kind == kDepthwise) {
             Conv2dGeom g{p->N, d.in_h, d.in_w, d.cin, d.out_h, d.out_w, d.stride, d.dil, d.pad_top, d.pad_left};
             const double ib = 2.0 * p->N * d.in_h * d.in_w * d.cin;
+            if (dw_reduce_pending) { AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_dwred, 0)); dw_reduce_pending = false; }   // red_ws reuse
             PROF("dw_bwd_filter", ib + tb, dw_conv_bwd_filter(p->buf[d.input].y, b.gz, g, net->grads + d.w_off, p->red_ws, p->red_ws_floats, s));
             PROF("dw_bwd_data", ib + tb, dw_conv_bwd_data(b.gz, net->params + d.w_off, g, p->buf[d.input].g, s));
         } else if (d.kind == kStem) {
+            if (dw_reduce_pending) { AMS_CUDA_CHECK(cudaStreamWaitEvent(s, net->ev_dwred, 0)); dw_reduce_pending = false; }   // red_ws reuse
             PROF("stem_bwd_filter", tb + static_cast<double>(p->N) * c.height * c.width * 3,
                  stem_conv_bwd_filter(p->in_frames, p->in_dtype == AMS_FRAMES_U8, p->N, c.height, c.width, d.in_h, d.in_w,
                                       d.out_h, d.out_w, d.pad_top, d.pad_left, 127.5f, 0.007843137718737125f, 1.0f, b.gz,

@@ -126,7 +126,7 @@ struct Net {
     int num_sms = kNumSMs;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     // filter gradients of the 1x1 convs run on a side stream, concurrently with the backward chain that does not need them
-    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pool = nullptr;
+    cudaStream_t side_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pool = nullptr, ev_dwred = nullptr;
     // data-parallel bucketed gradient exchange: the late bucket = arena floats [bucket_split, n_train) (every layer of the
     // final-resolution stage, ASPP, logits); ev_bucket is recorded (as an external event node when the step is a CUDA graph)
     // once all of its gradients are complete, long before the backward pass ends
