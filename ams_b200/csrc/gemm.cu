@@ -305,9 +305,12 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* smC = smB + (p.b_resident ? 1 : p.stages) * stage_b;                          // 1024-aligned (stage sizes are multiples of 2 KB)
     float* s_scale = reinterpret_cast<float*>(smC + p.stage_bufs * cbuf_bytes);
     float* s_shift = s_scale + p.n_alloc;
+    // statistics scratch only in the kernels that compute statistics: 16 B per column + 128 B per tile column are the
+    // difference between two and three pipeline stages for the K, N >= 728 GEMMs of the teacher
+    constexpr bool kHasStats = (F & kEpiStats) != 0;
     double* s_run = reinterpret_cast<double*>(s_shift + p.n_alloc);   // [2][n_alloc] running column sums of this CTA
-    float2* s_part = reinterpret_cast<float2*>(s_run + 2 * p.n_alloc);   // [16 slices][block_n]
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + 16 * p.block_n);
+    float2* s_part = reinterpret_cast<float2*>(s_run + (kHasStats ? 2 * p.n_alloc : 0));   // [16 slices][block_n]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_part + (kHasStats ? 16 * p.block_n : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -331,8 +334,7 @@ gemm_kmajor_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int n = threadIdx.x; n < p.n_alloc; n += kGemm2Threads) {
         s_scale[n] = (n < p.N) ? (p.scale ? p.scale[n] : 1.f) : 0.f;
         s_shift[n] = (n < p.N && p.shift) ? p.shift[n] : 0.f;
-        s_run[n] = 0.0;
-        s_run[p.n_alloc + n] = 0.0;
+        if (kHasStats) { s_run[n] = 0.0; s_run[p.n_alloc + n] = 0.0; }
     }
     t5::fence_before_thread_sync();
     __syncthreads();
@@ -826,8 +828,10 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
             plan->pitch = d.N * 2 + (((d.N / 8) % 2 == 0) ? 16 : 0);
             plan->cbuf_bytes = plan->linear_out ? ((BLOCK_M * plan->pitch + 1023) / 1024) * 1024 : nboxes * BLOCK_M * 128;
             plan->stage_bufs = (plan->cbuf_bytes <= 16 * 1024) ? 2 : 1;
-            fixed += size_t(plan->stage_bufs) * plan->cbuf_bytes + size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8;
-            budget = 110 * 1024;
+            fixed += size_t(plan->stage_bufs) * plan->cbuf_bytes + (d.stats_partial ? size_t(npad) * 16 + size_t(plan->block_n) * 16 * 8 : 0);
+            // two CTAs per SM where two pipeline stages fit next to the fixed part in half an SM; else the whole SM for one CTA:
+            // a K >= 728 mainloop is bound by the bytes in flight (stages x 48 KB against ~1.4 us of TMA latency)
+            budget = (fixed + 2 * stage_bytes <= 110 * 1024) ? 110 * 1024 : 224 * 1024;
         }
         int stages = budget > fixed ? int((budget - fixed) / stage_bytes) : 0;
         stages = std::max(2, std::min(stages, kMaxStages));
