@@ -800,9 +800,21 @@ int gemm_plan(const GemmDesc& d, int num_sms, GemmPlan* plan) {
         plan->n_tiles = 1;
     } else {
         // several N tiles: whole 64-column TMA boxes per tile (the last tile is clipped by the tensor extent)
-        const int t = ceil_div(npad, 256);
+        int t = ceil_div(npad, 256);
         plan->block_n = ceil_div(ceil_div(npad, t), 64) * 64;
         plan->n_tiles = ceil_div(npad, plan->block_n);
+        if (d.K >= 512) {
+            // big-K GEMMs run one persistent CTA per SM, so whole waves of tiles count: N = 728 at M = 8,385 is 198 tiles of 256
+            // columns (two rounds on 148 SMs, the second one third full) or 264 tiles of 192 (two rounds, 0.75x the work each)
+            const int m_tiles = ceil_div(d.M, BLOCK_M);
+            long long best = -1;
+            for (int tt = t; tt <= t + 2; ++tt) {
+                const int bn = ceil_div(ceil_div(npad, tt), 64) * 64;
+                const int nt = ceil_div(npad, bn);
+                const long long cost = ceil_div_ll(static_cast<long long>(m_tiles) * nt, num_sms) * (bn + 64);
+                if (best < 0 || cost < best) { best = cost; plan->block_n = bn; plan->n_tiles = nt; }
+            }
+        }
     }
     npad = plan->block_n * plan->n_tiles;                       // = n_alloc of the kernels
     plan->m_tiles = ceil_div(d.M, BLOCK_M);
