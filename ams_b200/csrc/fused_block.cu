@@ -87,10 +87,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         :: "r"(t5::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(t5::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
-__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!t5::mbar_try_wait(bar, parity)) { if (++spins > kSpinLimit) __trap(); }
-}
 __device__ __forceinline__ void wait_bar_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!t5::mbar_try_wait(bar, parity)) { __nanosleep(32); if (++spins > (kSpinLimit >> 4)) __trap(); }
@@ -315,7 +311,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             int r = t;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
             const int ty = r % p.tiles_y;
-            const int n = r / p.tiles_y;
             const int y0 = ty * TH * S - p.pad_top, x0 = tx * kTW * S - p.pad_left;     // image coordinates of halo position (0, 0)
             const int col_hi = p.W - x0;                    // halo columns >= col_hi lie right of the image
             for (int j = 0; j < p.n_chunks; ++j, ++g) {
