@@ -27,7 +27,8 @@ def rnd(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize('M,K,N', [(300, 16, 96), (1000, 24, 144), (257, 144, 24), (4097, 32, 16), (2145, 960, 320),
-                                   (2145, 160, 960), (5000, 384, 64), (2145, 320, 256), (129, 576, 160), (640, 64, 384)])
+                                   (2145, 160, 960), (5000, 384, 64), (2145, 320, 256), (129, 576, 160), (640, 64, 384),
+                                   (8385, 728, 728), (2145, 1536, 2048), (1100, 2048, 256)])     # teacher: K >= 512 plans (whole SM, wave-aware N tiles)
 def test_conv1x1_plain(M, K, N):
     L = nat.lib()
     a = ac_round(rnd(M, K, seed=1))
